@@ -1,0 +1,103 @@
+/*
+ * twb200.h — C ABI of the B200-native Whisper transcription hot path.
+ *
+ * This is the drop-in boundary.  The reference (crmorton/Turbo-Whisper-Workspace)
+ * has no native code: its hot path is `AudioProcessingPipeline.transcribe`
+ * (ref: vocalis/core/audio_pipeline.py:323-369) calling a Hugging Face ASR pipeline object
+ * (ref: vocalis/core/audio_pipeline.py:195-200,351-358).  All arithmetic behind that call lives in
+ * `transformers` ($TF = transformers 5.5.0 as installed; the reference pins 4.54.1).  Each entry
+ * point below names the $TF function whose arithmetic it replaces.  The Python host side
+ * (`turbo-whisper-workspace_b200/pipeline.py`) keeps the HF pipeline call signature and binds these
+ * symbols with ctypes; INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch types.  `void* stream` is a `cudaStream_t`.
+ *  - device pointers are borrowed for the duration of the call (stream-ordered); the caller
+ *    (PyTorch, as the device allocator) owns every buffer.  The library allocates nothing on the
+ *    device.
+ *  - bf16 tensors are passed as `void*` (16-bit storage), row-major unless stated.
+ *  - every function returns 0 on success; on failure a non-zero status and `tw_last_error()`
+ *    (thread-local, NUL-terminated) describes it.  Nothing is launched on argument errors.
+ *  - there is no CPU fallback: without an sm_100 device the launch functions fail.
+ */
+#ifndef TWB200_H_
+#define TWB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TW_ABI_VERSION 1
+
+const char* tw_last_error(void);
+int tw_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1  log-mel front end.
+ * Replaces WhisperFeatureExtractor._torch_extract_fbank_features
+ * ($TF/models/whisper/feature_extraction_whisper.py:135-164) for clips already cut to <= 30 s:
+ * zero-pad to 480000 samples, reflect-padded 400-point STFT at hop 160 (periodic Hann), power,
+ * 128 slaney mel filters, log10(max(.,1e-10)), max(x, clipmax-8), (x+4)/4.
+ * ---------------------------------------------------------------------------------------------- */
+size_t tw_logmel_tables_bytes(void);
+size_t tw_logmel_scratch_bytes(int32_t batch);
+/* mel_filters: host fp32 [201,128] exactly as WhisperFeatureExtractor.mel_filters (cast to fp32). */
+int tw_logmel_init(void* tables_dev, const float* mel_filters_host_201x128);
+/* pcm: device fp32 [batch, pcm_stride] (pcm_stride >= 480000); n_valid: device int32 [batch] number
+ * of real samples per clip (NULL = 480000), samples beyond it are treated as zeros.
+ * out_f32: device fp32 [batch,128,3000] or NULL.  out_bf16_t: device bf16 time-major
+ * [batch, rows, 128] or NULL, frame t is written to row (out_t_row_off + t); out_t_bstride in
+ * elements. */
+int tw_logmel(const void* tables_dev, const float* pcm, int64_t pcm_stride, const int32_t* n_valid,
+              int32_t batch, void* scratch, float* out_f32, void* out_bf16_t,
+              int64_t out_t_bstride, int32_t out_t_row_off, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K4  LayerNorm over the last dimension, fp32 in -> bf16 out (eps as nn.LayerNorm, 1e-5).
+ * Replaces the nn.LayerNorm calls of WhisperEncoderLayer / WhisperDecoderLayer
+ * ($TF/models/whisper/modeling_whisper.py:380-414, 449-506) and the final layer_norm (:640, :789).
+ * ---------------------------------------------------------------------------------------------- */
+int tw_layernorm(const float* x, const float* gamma, const float* beta, void* out_bf16,
+                 int64_t rows, int32_t cols, float eps, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K5  TMA-fed tcgen05/TMEM bf16 GEMM with fused epilogue:
+ *       out[b, r, n] = act( sum_k A[b, a_row_off[b] + r, k] * W[n, k] + bias[n] ) + resid[b, r, n]
+ * A is a (possibly overlapping-row) strided view: element (b, r, k) lives at
+ *   a + b*a_batch_stride + r*a_row_stride + k   (strides in elements, multiples of 8).
+ * That view expresses nn.Linear (batches = 1) and both Conv1d layers of the encoder stem as
+ * implicit GEMMs over time-major activations (im2col is a stride trick, never materialised).
+ * Replaces nn.Linear / nn.Conv1d + GELU + residual adds in WhisperEncoder.forward and
+ * WhisperAttention ($TF/models/whisper/modeling_whisper.py:284-357, 380-414, 593-647).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct tw_gemm_args {
+    const void* a;          /* bf16 */
+    int64_t a_row_stride;   /* elements */
+    int64_t a_batch_stride; /* elements */
+    int32_t a_rows;         /* addressable rows per batch in the view (TMA bound; OOB reads 0) */
+    const int32_t* a_row_off; /* device int32 [batches] or NULL */
+    const void* w;          /* bf16 [N, K] row-major (nn.Linear weight layout) */
+    int32_t batches;
+    int32_t rows;           /* output rows per batch (M) */
+    int32_t n;              /* N, multiple of 8 */
+    int32_t k;              /* K, multiple of 8 */
+    const float* bias;      /* fp32 [N] or NULL */
+    int32_t act;            /* 0 none, 1 exact-erf GELU */
+    const float* resid;     /* fp32 or NULL; element (b, r, n) at resid + (b*resid_batch_rows + r)*resid_ld + n */
+    int64_t resid_ld;
+    int64_t resid_batch_rows;
+    void* out;              /* element (b, r, n) at out + (b*out_batch_rows + out_row_off + r)*out_ld + n */
+    int32_t out_f32;        /* 0: bf16, 1: fp32 */
+    int64_t out_ld;
+    int64_t out_batch_rows;
+    int32_t out_row_off;
+} tw_gemm_args;
+int tw_gemm_bf16(const tw_gemm_args* args, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TWB200_H_ */

@@ -1,0 +1,65 @@
+"""ctypes binding of libtwb200.so (C ABI: include/twb200.h).  Fails loudly when the library is
+missing — there is no fallback implementation of any kernel."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtwb200.so")
+
+c_void_p, c_int32, c_int64, c_float, c_size_t = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
+
+
+class TwError(RuntimeError):
+    pass
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("a", c_void_p), ("a_row_stride", c_int64), ("a_batch_stride", c_int64), ("a_rows", c_int32),
+        ("a_row_off", c_void_p), ("w", c_void_p), ("batches", c_int32), ("rows", c_int32),
+        ("n", c_int32), ("k", c_int32), ("bias", c_void_p), ("act", c_int32), ("resid", c_void_p),
+        ("resid_ld", c_int64), ("resid_batch_rows", c_int64), ("out", c_void_p), ("out_f32", c_int32),
+        ("out_ld", c_int64), ("out_batch_rows", c_int64), ("out_row_off", c_int32),
+    ]
+
+
+# name -> (restype, argtypes); mirrors include/twb200.h one to one (tests/test_abi.py checks it)
+SIGNATURES = {
+    "tw_last_error": (C.c_char_p, []),
+    "tw_abi_version": (C.c_int, []),
+    "tw_logmel_tables_bytes": (c_size_t, []),
+    "tw_logmel_scratch_bytes": (c_size_t, [c_int32]),
+    "tw_logmel_init": (C.c_int, [c_void_p, c_void_p]),
+    "tw_logmel": (C.c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_void_p, c_void_p, c_void_p,
+                            c_int64, c_int32, c_void_p]),
+    "tw_layernorm": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_float, c_void_p]),
+    "tw_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), c_void_p]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise TwError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  turbo-whisper-workspace_b200 has no CPU or PyTorch fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        if lib.tw_abi_version() != 1:
+            raise TwError("libtwb200.so ABI version mismatch")
+        _lib = lib
+    return _lib
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        msg = load().tw_last_error().decode("utf-8", "replace")
+        raise TwError(f"{what or 'libtwb200'} failed (status {status}): {msg}")

@@ -1,0 +1,298 @@
+// K5 — persistent, warp-specialised, TMA-fed tcgen05/TMEM bf16 GEMM with fused epilogue.
+//
+//   out[b, r, n] = act( sum_k A[b, a_row_off[b] + r, k] * W[n, k] + bias[n] ) + resid[b, r, n]
+//
+// A (activations) and W (nn.Linear weight [N,K]) are both K-major, which is exactly the operand
+// layout tcgen05.mma wants, so no transposes exist anywhere.  A is addressed through a rank-3 TMA
+// tensor map (k, row, batch) whose row stride is a free parameter: nn.Linear uses stride K, the two
+// Conv1d layers of the Whisper stem use overlapping rows (stride C resp. 2C, length 3C) over
+// time-major activations, so im2col is never materialised
+// ($TF/models/whisper/modeling_whisper.py:619-620 conv1/conv2 + gelu).
+//
+// CTA = 192 threads: warp 0 TMA producer, warp 1 MMA issuer (+TMEM owner), warps 2-5 epilogue.
+// Tile 128 x 256 x 64, 4-stage smem ring (48 KB / stage), two 256-column fp32 accumulators in
+// TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.  Grid = #SMs, static tile striding.
+#include "common.cuh"
+#include "twb200_internal.h"
+
+namespace tw {
+namespace gemm {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 512;
+constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+
+struct Params {
+    int rows, batches, N, K;
+    int m_tiles_per_batch, n_tiles, num_tiles, num_k_blocks;
+    const int* a_row_off;
+    const float* bias;
+    const float* resid;
+    long long resid_ld, resid_batch_rows;
+    void* out;
+    int out_f32;
+    long long out_ld, out_batch_rows;
+    int out_row_off;
+    int act;
+};
+
+struct TileCoord {
+    int b, m0, n0;
+};
+TW_DEVINL TileCoord decode_tile(const Params& p, int tile) {
+    TileCoord t;
+    const int nt = tile % p.n_tiles;
+    const int mt_all = tile / p.n_tiles;
+    t.b = mt_all / p.m_tiles_per_batch;
+    t.m0 = (mt_all - t.b * p.m_tiles_per_batch) * BM;
+    t.n0 = nt * BN;
+    return t;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                               ~uintptr_t(1023));
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
+    uint64_t* full_bar = bars;                    // [STAGES]
+    uint64_t* empty_bar = bars + STAGES;          // [STAGES]
+    uint64_t* tmem_full_bar = bars + 2 * STAGES;  // [2]
+    uint64_t* tmem_empty_bar = bars + 2 * STAGES + 2;  // [2]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tmem_full_bar[s], 1);
+            mbar_init(&tmem_empty_bar[s], 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===================== TMA producer =====================
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const TileCoord t = decode_tile(p, tile);
+                const int row0 = t.m0 + (p.a_row_off ? p.a_row_off[t.b] : 0);
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
+                    tma_load_3d(&tmA, &full_bar[stage], sA + stage * A_STAGE_BYTES, kb * BK, row0, t.b);
+                    tma_load_2d(&tmB, &full_bar[stage], sB + stage * B_STAGE_BYTES, kb * BK, t.n0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===================== MMA issuer =====================
+            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tcgen05_fence_after();
+                    const uint32_t a_addr = smem_u32(sA + stage * A_STAGE_BYTES);
+                    const uint32_t b_addr = smem_u32(sB + stage * B_STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t adesc = umma_desc_sw128(a_addr + k * UMMA_K * 2, 16, 1024);
+                        const uint64_t bdesc = umma_desc_sw128(b_addr + k * UMMA_K * 2, 16, 1024);
+                        tcgen05_mma_f16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    tcgen05_commit(&empty_bar[stage]);  // frees the smem slot when the MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tcgen05_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+        const int row_in_tile = quarter * 32 + lane;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const TileCoord t = decode_tile(p, tile);
+            const int r = t.m0 + row_in_tile;
+            const bool row_ok = r < p.rows;
+            mbar_wait(&tmem_full_bar[acc], acc_phase);
+            tcgen05_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
+            const size_t out_row = ((size_t)t.b * p.out_batch_rows + p.out_row_off + r) * p.out_ld;
+            const size_t res_row = ((size_t)t.b * p.resid_batch_rows + r) * p.resid_ld;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                const int n_base = t.n0 + c * 32;
+                if (n_base >= p.N) break;  // warp-uniform
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(taddr + c * 32, v);
+                tmem_ld_wait();
+                if (row_ok) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {  // groups of 8 columns
+                        const int n = n_base + g * 8;
+                        if (n < p.N) {
+                            float f[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[g * 8 + i]);
+                            if (p.bias) {
+                                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n) + 1);
+                                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                            }
+                            if (p.act == 1) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) f[i] = gelu_erf_fast(f[i]);
+                            }
+                            if (p.resid) {
+                                const float4* rp = reinterpret_cast<const float4*>(p.resid + res_row + n);
+                                const float4 r0 = rp[0], r1 = rp[1];
+                                f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
+                                f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
+                            }
+                            if (p.out_f32) {
+                                float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_row + n);
+                                op[0] = make_float4(f[0], f[1], f[2], f[3]);
+                                op[1] = make_float4(f[4], f[5], f[6], f[7]);
+                            } else {
+                                uint4 pk;
+                                pk.x = pack_bf16x2(f[0], f[1]);
+                                pk.y = pack_bf16x2(f[2], f[3]);
+                                pk.z = pack_bf16x2(f[4], f[5]);
+                                pk.w = pack_bf16x2(f[6], f[7]);
+                                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + out_row + n) = pk;
+                            }
+                        }
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            mbar_arrive(&tmem_empty_bar[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+}  // namespace gemm
+}  // namespace tw
+
+using namespace tw;
+using namespace tw::gemm;
+
+extern "C" int tw_gemm_bf16(const tw_gemm_args* a, void* stream) {
+    TW_REQUIRE(a != nullptr, "tw_gemm_bf16: null args");
+    TW_REQUIRE(a->a && a->w && a->out, "tw_gemm_bf16: null tensor pointer");
+    TW_REQUIRE(a->batches >= 0 && a->rows >= 0 && a->n > 0 && a->k > 0, "tw_gemm_bf16: bad shape");
+    TW_REQUIRE(a->n % 8 == 0 && a->k % 8 == 0, "tw_gemm_bf16: N (%d) and K (%d) must be multiples of 8",
+               a->n, a->k);
+    TW_REQUIRE(a->a_row_stride % 8 == 0 && a->a_batch_stride % 8 == 0,
+               "tw_gemm_bf16: A strides must be multiples of 8 elements (16 B)");
+    TW_REQUIRE(((uintptr_t)a->a & 15) == 0 && ((uintptr_t)a->w & 15) == 0 && ((uintptr_t)a->out & 15) == 0,
+               "tw_gemm_bf16: pointers must be 16-byte aligned");
+    TW_REQUIRE(a->out_ld % 8 == 0, "tw_gemm_bf16: out_ld must be a multiple of 8");
+    TW_REQUIRE(!a->resid || (a->resid_ld % 4 == 0 && ((uintptr_t)a->resid & 15) == 0),
+               "tw_gemm_bf16: resid must be 16-byte aligned with ld %% 4 == 0");
+    TW_REQUIRE(a->act == 0 || a->act == 1, "tw_gemm_bf16: unknown activation %d", a->act);
+    if (a->batches == 0 || a->rows == 0) return 0;
+
+    CUtensorMap tmA, tmB;
+    {
+        const int batches = a->batches;
+        const uint64_t dims[3] = {(uint64_t)a->k, (uint64_t)a->a_rows, (uint64_t)batches};
+        // a size-1 batch dimension still needs a legal (16 B multiple, non-zero) stride
+        const uint64_t bstride = (batches > 1 ? (uint64_t)a->a_batch_stride
+                                              : (uint64_t)a->a_rows * (uint64_t)a->a_row_stride) * 2;
+        const uint64_t strides[2] = {(uint64_t)a->a_row_stride * 2, bstride};
+        const uint32_t box[3] = {BK, BM, 1};
+        if (encode_tensor_map(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a->a, dims, strides, box,
+                              CU_TENSOR_MAP_SWIZZLE_128B))
+            return 1;
+    }
+    {
+        const uint64_t dims[2] = {(uint64_t)a->k, (uint64_t)a->n};
+        const uint64_t strides[1] = {(uint64_t)a->k * 2};
+        const uint32_t box[2] = {BK, BN};
+        if (encode_tensor_map(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->w, dims, strides, box,
+                              CU_TENSOR_MAP_SWIZZLE_128B))
+            return 1;
+    }
+    Params p;
+    p.rows = a->rows;
+    p.batches = a->batches;
+    p.N = a->n;
+    p.K = a->k;
+    p.m_tiles_per_batch = (a->rows + BM - 1) / BM;
+    p.n_tiles = (a->n + BN - 1) / BN;
+    p.num_tiles = p.m_tiles_per_batch * p.batches * p.n_tiles;
+    p.num_k_blocks = (a->k + BK - 1) / BK;
+    p.a_row_off = a->a_row_off;
+    p.bias = a->bias;
+    p.resid = a->resid;
+    p.resid_ld = a->resid_ld;
+    p.resid_batch_rows = a->resid_batch_rows;
+    p.out = a->out;
+    p.out_f32 = a->out_f32;
+    p.out_ld = a->out_ld;
+    p.out_batch_rows = a->out_batch_rows;
+    p.out_row_off = a->out_row_off;
+    p.act = a->act;
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        TW_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           SMEM_BYTES));
+        attr_set = true;
+    }
+    const int sms = num_sms();
+    TW_REQUIRE(sms > 0, "tw_gemm_bf16: no CUDA device");
+    const int grid = p.num_tiles < sms ? p.num_tiles : sms;
+    gemm_bf16_kernel<<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmB, p);
+    TW_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}

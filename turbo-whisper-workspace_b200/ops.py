@@ -1,0 +1,128 @@
+"""Operator-level Python wrappers over the C ABI (torch tensors in, raw pointers out).
+
+PyTorch is used for device memory and the current stream only; every computation happens in
+libtwb200.so.  These mirror the entry points of include/twb200.h one to one and are what the
+`-m gpu` parity tests drive."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import GemmArgs, check
+
+N_SAMPLES, N_MELS, N_FRAMES = 480000, 128, 3000
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.TwError("turbo-whisper-workspace_b200 operators need CUDA tensors (no CPU path)")
+
+
+def slaney_mel_filters() -> np.ndarray:
+    """[201,128] fp32 — the filterbank WhisperFeatureExtractor(feature_size=128) builds
+    ($TF/models/whisper/feature_extraction_whisper.py:95-103; $TF/audio_utils.py:453-544):
+    128 triangular filters on the slaney mel scale over 0-8 kHz, slaney area normalisation."""
+    def hz_to_mel(f):
+        f = np.asarray(f, dtype=np.float64)
+        return np.where(f >= 1000.0, 15.0 + np.log(np.maximum(f, 1e-300) / 1000.0) * (27.0 / np.log(6.4)),
+                        3.0 * f / 200.0)
+
+    def mel_to_hz(m):
+        return np.where(m >= 15.0, 1000.0 * np.exp((np.log(6.4) / 27.0) * (m - 15.0)), 200.0 * m / 3.0)
+
+    pts = mel_to_hz(np.linspace(hz_to_mel(0.0), hz_to_mel(8000.0), N_MELS + 2))
+    bins = np.linspace(0, 8000, 201)
+    d = np.diff(pts)
+    slopes = pts[None, :] - bins[:, None]
+    fb = np.maximum(0.0, np.minimum(-slopes[:, :-2] / d[:-1], slopes[:, 2:] / d[1:]))
+    fb *= (2.0 / (pts[2:] - pts[:-2]))[None, :]
+    return np.ascontiguousarray(fb.astype(np.float32))
+
+
+class LogMel:
+    """K1 front end bound to one device: owns the constant tables and the scratch buffer."""
+
+    def __init__(self, device, max_batch: int):
+        lib = _lib.load()
+        self.device = torch.device(device)
+        self.max_batch = max_batch
+        self.tables = torch.empty(lib.tw_logmel_tables_bytes(), dtype=torch.uint8, device=self.device)
+        self.scratch = torch.empty(lib.tw_logmel_scratch_bytes(max_batch), dtype=torch.uint8, device=self.device)
+        fb = slaney_mel_filters()
+        with torch.cuda.device(self.device):
+            check(lib.tw_logmel_init(_ptr(self.tables), fb.ctypes.data_as(C.c_void_p)), "tw_logmel_init")
+
+    def __call__(self, pcm, n_valid=None, out_f32=None, out_t=None, out_t_row_off: int = 0):
+        """pcm: cuda fp32 [B, >=480000]; n_valid: cuda int32 [B] or None.
+        out_f32: cuda fp32 [B,128,3000] or None; out_t: cuda bf16 [B, rows, 128] or None."""
+        lib = _lib.load()
+        _need_cuda(pcm, n_valid, out_f32, out_t)
+        B = pcm.shape[0]
+        if B > self.max_batch:
+            raise _lib.TwError(f"batch {B} exceeds LogMel max_batch {self.max_batch}")
+        assert pcm.dtype == torch.float32 and pcm.stride(1) == 1
+        if out_f32 is not None:
+            assert out_f32.dtype == torch.float32 and out_f32.is_contiguous() and tuple(out_f32.shape) == (B, N_MELS, N_FRAMES)
+        tb = 0
+        if out_t is not None:
+            assert out_t.dtype == torch.bfloat16 and out_t.shape[0] >= B and out_t.shape[2] == N_MELS and out_t.stride(2) == 1
+            assert out_t.stride(1) == N_MELS and out_t.shape[1] >= out_t_row_off + N_FRAMES
+            tb = out_t.stride(0)
+        with torch.cuda.device(self.device):
+            check(lib.tw_logmel(_ptr(self.tables), _ptr(pcm), pcm.stride(0), _ptr(n_valid), B, _ptr(self.scratch),
+                                _ptr(out_f32), _ptr(out_t), tb, out_t_row_off, _stream()), "tw_logmel")
+
+
+def layernorm(x, gamma, beta, out=None, eps: float = 1e-5):
+    """fp32 [rows, cols] -> bf16 [rows, cols]."""
+    lib = _lib.load()
+    _need_cuda(x, gamma, beta)
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 2
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.tw_layernorm(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(out), x.shape[0], x.shape[1], eps, _stream()),
+              "tw_layernorm")
+    return out
+
+
+def gemm(a, w, *, rows, batches=1, a_row_stride=None, a_batch_stride=0, a_rows=None, a_row_off=None, bias=None,
+         act=0, resid=None, resid_ld=0, resid_batch_rows=0, out=None, out_ld=None, out_batch_rows=0,
+         out_row_off=0, k=None):
+    """K5 GEMM (see include/twb200.h tw_gemm_args).  `a` is any bf16 cuda tensor used as a flat base;
+    `w` is bf16 [N, K]."""
+    lib = _lib.load()
+    _need_cuda(a, w, out, bias, resid, a_row_off)
+    N, K = w.shape if k is None else (w.shape[0], k)
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and w.is_contiguous()
+    args = GemmArgs()
+    args.a = a.data_ptr()
+    args.a_row_stride = K if a_row_stride is None else a_row_stride
+    args.a_batch_stride = a_batch_stride
+    args.a_rows = rows if a_rows is None else a_rows
+    args.a_row_off = None if a_row_off is None else a_row_off.data_ptr()
+    args.w = w.data_ptr()
+    args.batches, args.rows, args.n, args.k = batches, rows, N, K
+    args.bias = None if bias is None else bias.data_ptr()
+    args.act = act
+    args.resid = None if resid is None else resid.data_ptr()
+    args.resid_ld, args.resid_batch_rows = resid_ld, resid_batch_rows
+    args.out = out.data_ptr()
+    args.out_f32 = 1 if out.dtype == torch.float32 else 0
+    args.out_ld = N if out_ld is None else out_ld
+    args.out_batch_rows, args.out_row_off = out_batch_rows, out_row_off
+    with torch.cuda.device(a.device):
+        check(lib.tw_gemm_bf16(C.byref(args), _stream()), "tw_gemm_bf16")
+    return out
