@@ -97,6 +97,23 @@ typedef struct tw_gemm_args {
 } tw_gemm_args;
 int tw_gemm_bf16(const tw_gemm_args* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * K6  encoder self-attention (non-causal, no mask, head_dim 64), flash-style on tcgen05/TMEM.
+ * qkv: bf16 [batch*seq, 3*heads*64] = the fused q|k|v projection (q already scaled by 1/8, which
+ * the engine folds into Wq/bq).  out: bf16 [batch*seq, out_ld] with head h at columns 64h..64h+63.
+ * Replaces the attention_interface call of WhisperAttention.forward for the encoder
+ * ($TF/models/whisper/modeling_whisper.py:335-352; sdpa/eager softmax(QK^T)V with scaling=1.0).
+ * ---------------------------------------------------------------------------------------------- */
+int tw_attention_enc(const void* qkv_bf16, void* out_bf16, int32_t batch, int32_t seq, int32_t heads,
+                     int64_t out_ld, void* stream);
+
+/* Gather a seek-shifted 30 s window of time-major features (WhisperGenerationMixin._get_input_segment,
+ * $TF/models/whisper/generation_whisper.py:1831-1850): dst[b, row_off + t, :] =
+ * src[src_row[b], row_off + seek[b] + t, :] for t < frames - seek[b], zeros after.  bf16 [*, rows, cols]. */
+int tw_shift_frames(const void* src_bf16, void* dst_bf16, const int32_t* src_row, const int32_t* seek,
+                    int32_t batch, int32_t frames, int32_t cols, int64_t batch_stride, int32_t row_off,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

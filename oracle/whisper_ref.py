@@ -1,0 +1,310 @@
+"""Oracle: Whisper encoder / decoder / greedy generate, plain PyTorch fp32 on CPU
+(test infrastructure, see oracle/__init__.py).
+
+Restates, for the one configuration the reference's call reaches (greedy, timestamps on, no
+prompt, no temperature fallback, `condition_on_prev_tokens` off), the following functions of
+transformers 5.5.0 (`$TF/`):
+  * WhisperEncoder.forward / WhisperEncoderLayer      $TF/models/whisper/modeling_whisper.py:593-647, 380-414
+  * WhisperAttention.forward                          $TF/models/whisper/modeling_whisper.py:284-357
+  * WhisperDecoder.forward / WhisperDecoderLayer      $TF/models/whisper/modeling_whisper.py:691-796, 449-506
+  * proj_out (tied to embed_tokens)                   $TF/models/whisper/modeling_whisper.py:964-1090
+  * sinusoids                                         $TF/models/whisper/modeling_whisper.py:55-64
+  * WhisperGenerationMixin.generate (seek loop)       $TF/models/whisper/generation_whisper.py:383-968
+  * detect_language / _retrieve_init_tokens           $TF/models/whisper/generation_whisper.py:1610-1673, 1455-1608
+  * _retrieve_segment                                 $TF/models/whisper/generation_whisper.py:1976-2073
+  * GenerationMixin._sample (greedy)                  $TF/generation/utils.py:2658-2841
+  * Suppress*/WhisperTimeStamp logits processors      $TF/generation/logits_process.py:1812-2043
+The weights are read from an HF-layout ``state_dict`` (names as in SURVEY.md appendix B).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.nn.functional as F
+
+# large-v3 special-token layout
+EOS = 50257
+SOT = 50258
+LANG_FIRST, LANG_LAST = 50259, 50358
+TRANSLATE, TRANSCRIBE = 50359, 50360
+NO_TIMESTAMPS = 50364
+TIMESTAMP_BEGIN = 50365
+VOCAB = 51866
+
+SUPPRESS_TOKENS = [
+    1, 2, 7, 8, 9, 10, 14, 25, 26, 27, 28, 29, 31, 58, 59, 60, 61, 62, 63, 90, 91, 92, 93, 359, 503, 522, 542, 873,
+    893, 902, 918, 922, 931, 1350, 1853, 1982, 2460, 2627, 3246, 3253, 3268, 3536, 3846, 3961, 4183, 4667, 6585, 6647,
+    7273, 9061, 9383, 10428, 10929, 11938, 12033, 12331, 12562, 13793, 14157, 14635, 15265, 15618, 16553, 16604, 18362,
+    18956, 20075, 21675, 22520, 26130, 26161, 26435, 28279, 29464, 31650, 32302, 32470, 36865, 42863, 47425, 49870,
+    50254, 50258, 50359, 50360, 50361, 50362, 50363,
+]
+BEGIN_SUPPRESS_TOKENS = [220, 50257]
+
+
+@dataclass
+class WhisperDims:
+    d_model: int = 1280
+    heads: int = 20
+    ffn: int = 5120
+    enc_layers: int = 32
+    dec_layers: int = 4
+    n_mels: int = 128
+    max_source_positions: int = 1500
+    max_target_positions: int = 448
+    vocab: int = VOCAB
+
+    @property
+    def head_dim(self) -> int:
+        return self.d_model // self.heads
+
+
+@dataclass
+class GenConfig:
+    """The generation_config.json fields of the openai/whisper-large-v3(-turbo) checkpoints that the
+    path reads."""
+    eos_token_id: int = EOS
+    pad_token_id: int = EOS
+    decoder_start_token_id: int = SOT
+    no_timestamps_token_id: int = NO_TIMESTAMPS
+    max_length: int = 448
+    max_initial_timestamp_index: int = 50
+    suppress_tokens: List[int] = field(default_factory=lambda: list(SUPPRESS_TOKENS))
+    begin_suppress_tokens: List[int] = field(default_factory=lambda: list(BEGIN_SUPPRESS_TOKENS))
+    lang_ids: List[int] = field(default_factory=lambda: list(range(LANG_FIRST, LANG_LAST + 1)))
+    task_to_id: Dict[str, int] = field(default_factory=lambda: {"transcribe": TRANSCRIBE, "translate": TRANSLATE})
+
+
+def sinusoids(length: int, channels: int, max_timescale: float = 10000.0) -> torch.Tensor:
+    inc = math.log(max_timescale) / (channels // 2 - 1)
+    inv = torch.exp(-inc * torch.arange(channels // 2))
+    t = torch.arange(length).view(-1, 1) * inv.view(1, -1)
+    return torch.cat([t.sin(), t.cos()], dim=1)
+
+
+class WhisperRef:
+    def __init__(self, dims: WhisperDims, state_dict: Dict[str, torch.Tensor]):
+        self.dims = dims
+        self.sd = {k: v.detach().to(torch.float32) for k, v in state_dict.items()}
+
+    # -------------------------------------------------------------------------------- attention
+    def _attn(self, pfx: str, x: torch.Tensor, kv_src: Optional[torch.Tensor] = None, causal: bool = False,
+              cache: Optional[dict] = None) -> torch.Tensor:
+        """Multi-head attention; q is scaled by head_dim**-0.5 after the bias ($TF ...:310)."""
+        sd, H, dh = self.sd, self.dims.heads, self.dims.head_dim
+        B, T, _ = x.shape
+        q = F.linear(x, sd[pfx + "q_proj.weight"], sd[pfx + "q_proj.bias"]) * (dh ** -0.5)
+        if cache is not None and "k" in cache and kv_src is not None:
+            k, v = cache["k"], cache["v"]  # cross-attention K/V computed once
+        else:
+            src = x if kv_src is None else kv_src
+            k = F.linear(src, sd[pfx + "k_proj.weight"])  # no bias on k
+            v = F.linear(src, sd[pfx + "v_proj.weight"], sd[pfx + "v_proj.bias"])
+            k = k.view(B, -1, H, dh).transpose(1, 2)
+            v = v.view(B, -1, H, dh).transpose(1, 2)
+            if cache is not None:
+                if kv_src is None and "k" in cache:  # growing self-attention cache
+                    k = torch.cat([cache["k"], k], dim=2)
+                    v = torch.cat([cache["v"], v], dim=2)
+                cache["k"], cache["v"] = k, v
+        q = q.view(B, T, H, dh).transpose(1, 2)
+        s = q @ k.transpose(-1, -2)
+        if causal and T > 1:
+            S = k.shape[2]
+            mask = torch.ones(T, S, dtype=torch.bool).tril(diagonal=S - T)
+            s = s.masked_fill(~mask, float("-inf"))
+        p = torch.softmax(s, dim=-1)
+        o = (p @ v).transpose(1, 2).reshape(B, T, H * dh)
+        return F.linear(o, sd[pfx + "out_proj.weight"], sd[pfx + "out_proj.bias"])
+
+    def _ln(self, pfx: str, x: torch.Tensor) -> torch.Tensor:
+        return F.layer_norm(x, (x.shape[-1],), self.sd[pfx + "weight"], self.sd[pfx + "bias"], 1e-5)
+
+    def _mlp(self, pfx: str, x: torch.Tensor) -> torch.Tensor:
+        sd = self.sd
+        h = F.gelu(F.linear(x, sd[pfx + "fc1.weight"], sd[pfx + "fc1.bias"]))
+        return F.linear(h, sd[pfx + "fc2.weight"], sd[pfx + "fc2.bias"])
+
+    # -------------------------------------------------------------------------------- encoder
+    def conv_stem(self, feats: torch.Tensor) -> torch.Tensor:
+        sd = self.sd
+        x = F.gelu(F.conv1d(feats, sd["model.encoder.conv1.weight"], sd["model.encoder.conv1.bias"], padding=1))
+        x = F.gelu(F.conv1d(x, sd["model.encoder.conv2.weight"], sd["model.encoder.conv2.bias"], stride=2, padding=1))
+        return x.permute(0, 2, 1) + sd["model.encoder.embed_positions.weight"]
+
+    def encode(self, feats: torch.Tensor, return_layers: bool = False):
+        """feats fp32 [B, n_mels, 3000] -> [B, 1500, d_model]; attention_mask is ignored by HF (:608-611)."""
+        x = self.conv_stem(feats.to(torch.float32))
+        layers = [x]
+        for i in range(self.dims.enc_layers):
+            p = f"model.encoder.layers.{i}."
+            x = x + self._attn(p + "self_attn.", self._ln(p + "self_attn_layer_norm.", x))
+            x = x + self._mlp(p, self._ln(p + "final_layer_norm.", x))
+            layers.append(x)
+        out = self._ln("model.encoder.layer_norm.", x)
+        return (out, layers) if return_layers else out
+
+    # -------------------------------------------------------------------------------- decoder
+    def new_cache(self) -> List[dict]:
+        return [{"self": {}, "cross": {}} for _ in range(self.dims.dec_layers)]
+
+    def decode(self, tokens: torch.Tensor, enc_out: torch.Tensor, cache: Optional[List[dict]] = None,
+               past_len: int = 0) -> torch.Tensor:
+        """tokens [B, T] (new positions only when a cache is given) -> fp32 logits [B, T, vocab]."""
+        sd = self.sd
+        B, T = tokens.shape
+        x = sd["model.decoder.embed_tokens.weight"][tokens] + sd["model.decoder.embed_positions.weight"][past_len:past_len + T]
+        for i in range(self.dims.dec_layers):
+            p = f"model.decoder.layers.{i}."
+            c = cache[i] if cache is not None else {"self": None, "cross": None}
+            x = x + self._attn(p + "self_attn.", self._ln(p + "self_attn_layer_norm.", x), causal=True, cache=c["self"])
+            x = x + self._attn(p + "encoder_attn.", self._ln(p + "encoder_attn_layer_norm.", x), kv_src=enc_out,
+                               cache=c["cross"])
+            x = x + self._mlp(p, self._ln(p + "final_layer_norm.", x))
+        x = self._ln("model.decoder.layer_norm.", x)
+        return F.linear(x, sd["model.decoder.embed_tokens.weight"])  # tied proj_out, no bias
+
+    # -------------------------------------------------------------------------------- processors
+    @staticmethod
+    def process_logits(scores: torch.Tensor, generated: Sequence[Sequence[int]], gc: GenConfig) -> torch.Tensor:
+        """SuppressTokens -> SuppressTokensAtBegin -> WhisperTimeStamp, on fp32 scores [B, V].
+        ``generated[k]`` = tokens of row k after the decoder prompt (begin_index)."""
+        s = scores.clone().float()
+        NEG = float("-inf")
+        TB = gc.no_timestamps_token_id + 1
+        s[:, gc.suppress_tokens] = NEG
+        g = len(generated[0])
+        if g == 0:
+            s[:, gc.begin_suppress_tokens] = NEG
+        s[:, gc.no_timestamps_token_id] = NEG
+        for k, seq in enumerate(generated):
+            last_ts = len(seq) >= 1 and seq[-1] >= TB
+            pen_ts = len(seq) < 2 or seq[-2] >= TB
+            if last_ts:
+                if pen_ts:
+                    s[k, TB:] = NEG
+                else:
+                    s[k, :gc.eos_token_id] = NEG
+            ts = [t for t in seq if t >= TB]
+            if ts:
+                ts_last = ts[-1] if (last_ts and not pen_ts) else ts[-1] + 1
+                s[k, TB:ts_last] = NEG
+        if g == 0:
+            s[:, :TB] = NEG
+            if gc.max_initial_timestamp_index is not None:
+                s[:, TB + gc.max_initial_timestamp_index + 1:] = NEG
+        logp = torch.log_softmax(s, dim=-1)
+        for k in range(s.shape[0]):
+            if logp[k, TB:].logsumexp(dim=-1) > logp[k, :TB].max():
+                s[k, :TB] = NEG
+        return s
+
+    # -------------------------------------------------------------------------------- generation
+    def detect_language(self, enc_out: torch.Tensor, gc: GenConfig) -> List[int]:
+        B = enc_out.shape[0]
+        logits = self.decode(torch.full((B, 1), gc.decoder_start_token_id, dtype=torch.long), enc_out)[:, -1]
+        mask = torch.ones(logits.shape[-1], dtype=torch.bool)
+        mask[gc.lang_ids] = False
+        logits = logits.masked_fill(mask[None], float("-inf"))
+        return logits.argmax(-1).tolist()
+
+    def greedy(self, enc_out: torch.Tensor, prompt: torch.Tensor, gc: GenConfig, record: Optional[list] = None):
+        """GenerationMixin._sample, greedy: returns generated tokens per row, [B, <=max_length-len(prompt)];
+        finished rows keep emitting pad (= eos).  ``record`` collects (raw fp32 logits, processed scores)."""
+        B, P = prompt.shape
+        cache = self.new_cache()
+        tokens = prompt.clone()
+        finished = torch.zeros(B, dtype=torch.bool)
+        logits = self.decode(prompt, enc_out, cache, 0)[:, -1]
+        while True:
+            gen = [tokens[k, P:].tolist() for k in range(B)]
+            scores = self.process_logits(logits, gen, gc)
+            if record is not None:
+                record.append((logits.clone(), scores.clone()))
+            nxt = scores.argmax(-1)
+            nxt = torch.where(finished, torch.full_like(nxt, gc.pad_token_id), nxt)
+            tokens = torch.cat([tokens, nxt[:, None]], dim=1)
+            finished = finished | (nxt == gc.eos_token_id)
+            if bool(finished.all()) or tokens.shape[1] >= gc.max_length:
+                break
+            logits = self.decode(nxt[:, None], enc_out, cache, tokens.shape[1] - 1)[:, -1]
+        return tokens[:, P:]
+
+    @staticmethod
+    def retrieve_segment(seq: List[int], seek_num_frames: int, TB: int):
+        """_retrieve_segment: returns (list of token lists, seek advance in mel frames)."""
+        is_ts = [t >= TB for t in seq]
+        single_ending = is_ts[-2:] == [False, True]
+        idxs = [i + 1 for i in range(len(seq) - 1) if is_ts[i] and is_ts[i + 1]]
+        if idxs:
+            slices = list(idxs)
+            if single_ending:
+                slices.append(len(seq))
+            else:
+                slices[-1] += 1
+            segs, last = [], 0
+            for cur in slices:
+                segs.append(seq[last:cur])
+                last = cur
+            if single_ending:
+                return segs, seek_num_frames
+            return segs, (seq[last - 2] - TB) * 2
+        return [list(seq)], seek_num_frames
+
+    def generate(self, feats: torch.Tensor, task: str = "transcribe", gc: Optional[GenConfig] = None,
+                 trace: Optional[dict] = None) -> List[List[int]]:
+        """WhisperGenerationMixin.generate for a batch of <=30 s windows (short-form), greedy, timestamps on.
+        feats [B, n_mels, 3000] fp32.  Returns the generated ids per row (segments concatenated, no padding)."""
+        gc = gc or GenConfig()
+        TB = gc.no_timestamps_token_id + 1
+        B = feats.shape[0]
+        feats = feats.to(torch.float32)
+        enc0 = self.encode(feats)
+        langs = self.detect_language(enc0, gc)
+        init = torch.tensor([[gc.decoder_start_token_id, langs[b], gc.task_to_id[task]] for b in range(B)],
+                            dtype=torch.long)
+        seek = [0] * B
+        max_frames = [feats.shape[-1]] * B
+        out: List[List[int]] = [[] for _ in range(B)]
+        if trace is not None:
+            trace.update({"langs": langs, "iterations": []})
+        guard = 0
+        while any(s < m for s, m in zip(seek, max_frames)):
+            guard += 1
+            if guard > 64:
+                raise RuntimeError("seek loop does not advance")
+            rows = [b for b in range(B) if seek[b] < max_frames[b]]
+            nfr = {b: min(max_frames[b] - seek[b], 3000) for b in rows}
+            seg = torch.zeros(len(rows), feats.shape[1], 3000)
+            for i, b in enumerate(rows):
+                seg[i, :, :nfr[b]] = feats[b, :, seek[b]:seek[b] + nfr[b]]
+            enc = enc0 if (guard == 1) else self.encode(seg)
+            rec = [] if trace is not None else None
+            toks = self.greedy(enc, init[rows], gc, record=rec)
+            if trace is not None:
+                trace["iterations"].append({"rows": rows, "seek": [seek[b] for b in rows], "tokens": toks.clone(),
+                                            "record": rec, "enc": enc})
+            for i, b in enumerate(rows):
+                s = toks[i].tolist()
+                if s[-1] == gc.pad_token_id:  # strip padding, then the eos itself
+                    n_pad = sum(1 for t in s if t == gc.pad_token_id)
+                    if gc.pad_token_id == gc.eos_token_id:
+                        n_pad -= 1
+                    if n_pad:
+                        s = s[:-n_pad]
+                if s[-1] == gc.eos_token_id:
+                    s = s[:-1]
+                segs, adv = self.retrieve_segment(s, nfr[b], TB)
+                seek[b] += adv
+                for sg in segs:
+                    out[b].extend(sg)
+        return out
+
+
+def dims_from_hf_config(cfg) -> WhisperDims:
+    return WhisperDims(d_model=cfg.d_model, heads=cfg.encoder_attention_heads, ffn=cfg.encoder_ffn_dim,
+                       enc_layers=cfg.encoder_layers, dec_layers=cfg.decoder_layers, n_mels=cfg.num_mel_bins,
+                       max_source_positions=cfg.max_source_positions, max_target_positions=cfg.max_target_positions,
+                       vocab=cfg.vocab_size)

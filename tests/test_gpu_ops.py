@@ -160,3 +160,36 @@ def test_gemm_conv_views(ops, cuda_device):
     xs[0] = x[0]
     ref_s = F.gelu(F.conv1d(xs.float(), w1.float(), b1, padding=1)).transpose(1, 2)
     torch.testing.assert_close(h1s[:, 2:T + 1].float().cpu(), ref_s[:, 1:], rtol=1e-2, atol=1e-2)
+
+
+# ------------------------------------------------------------------ K6 encoder attention
+@pytest.mark.parametrize("B,T,H", [(1, 128, 1), (1, 256, 2), (2, 1500, 4), (1, 100, 3), (3, 1500, 20)])
+def test_attention_enc(ops, cuda_device, B, T, H):
+    g = torch.Generator(device="cpu").manual_seed(B * 1000 + T + H)
+    D = H * 64
+    qkv = torch.randn(B * T, 3 * D, generator=g)
+    qkv[:, :D] *= 0.35   # q already carries the 1/8 scale in the engine; keep softmax peaky but finite
+    qkv = _bf(qkv).to(cuda_device)
+    out = ops.attention_enc(qkv, B, T, H)
+    torch.cuda.synchronize()
+    q, k, v = [t.float().view(B, T, H, 64).transpose(1, 2) for t in qkv.split(D, dim=1)]
+    ref = (torch.softmax(q @ k.transpose(-1, -2), dim=-1) @ v).transpose(1, 2).reshape(B * T, D)
+    # P is rounded to bf16 before PV (2^-9 relative per term) and the output is stored in bf16
+    torch.testing.assert_close(out.float(), ref, rtol=2e-2, atol=2e-2)
+    assert float((out.float() - ref).abs().mean()) < 2e-3
+
+
+def test_shift_frames(ops, cuda_device):
+    g = torch.Generator(device="cpu").manual_seed(5)
+    src = torch.zeros(3, 3002, 128, dtype=torch.bfloat16)
+    src[:, 1:3001] = _bf(torch.randn(3, 3000, 128, generator=g))
+    src = src.to(cuda_device)
+    dst = torch.full_like(src[:2], 7.0)
+    dst[:, 0] = 0
+    dst[:, 3001] = 0
+    seek = torch.tensor([1234, 0], dtype=torch.int32, device=cuda_device)
+    rows = torch.tensor([2, 0], dtype=torch.int32, device=cuda_device)
+    ops.shift_frames(src, dst, seek, src_row=rows)
+    assert torch.equal(dst[0, 1:3001 - 1234], src[2, 1235:3001])
+    assert float(dst[0, 3001 - 1234:].abs().max()) == 0.0
+    assert torch.equal(dst[1], src[0])

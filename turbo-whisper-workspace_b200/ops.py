@@ -126,3 +126,29 @@ def gemm(a, w, *, rows, batches=1, a_row_stride=None, a_batch_stride=0, a_rows=N
     with torch.cuda.device(a.device):
         check(lib.tw_gemm_bf16(C.byref(args), _stream()), "tw_gemm_bf16")
     return out
+
+
+def attention_enc(qkv, batch: int, seq: int, heads: int, out=None):
+    """K6: qkv bf16 [batch*seq, 3*heads*64] -> bf16 [batch*seq, heads*64]."""
+    lib = _lib.load()
+    _need_cuda(qkv, out)
+    D = heads * 64
+    assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and tuple(qkv.shape) == (batch * seq, 3 * D)
+    if out is None:
+        out = torch.empty(batch * seq, D, dtype=torch.bfloat16, device=qkv.device)
+    with torch.cuda.device(qkv.device):
+        check(lib.tw_attention_enc(_ptr(qkv), _ptr(out), batch, seq, heads, out.stride(0), _stream()), "tw_attention_enc")
+    return out
+
+
+def shift_frames(src, dst, seek, src_row=None, frames: int = N_FRAMES, row_off: int = 1):
+    """dst[b, row_off+t] = src[src_row[b], row_off+seek[b]+t] (zeros past `frames`); bf16 [*, rows, cols]."""
+    lib = _lib.load()
+    _need_cuda(src, dst, seek, src_row)
+    assert src.dtype == torch.bfloat16 and dst.dtype == torch.bfloat16 and src.stride() == dst.stride()
+    assert seek.dtype == torch.int32 and (src_row is None or src_row.dtype == torch.int32)
+    B = seek.shape[0]
+    with torch.cuda.device(src.device):
+        check(lib.tw_shift_frames(_ptr(src), _ptr(dst), _ptr(src_row), _ptr(seek), B, frames, src.shape[2],
+                                  src.stride(0), row_off, _stream()), "tw_shift_frames")
+    return dst
