@@ -114,6 +114,66 @@ int tw_shift_frames(const void* src_bf16, void* dst_bf16, const int32_t* src_row
                     int32_t batch, int32_t frames, int32_t cols, int64_t batch_stride, int32_t row_off,
                     void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * K7 / K8  batched greedy decode step (<= 32 rows per call).  All per-row state lives on the
+ * device so a step is a fixed launch sequence (CUDA-graph capturable):
+ *   row_state: int32 [batch][8] = {pos, finished, last_ts, text_lo, ts_lo, ts_hi, begin, mode}
+ *     pos   index in tokens[] of the token fed this step;  mode 1 = language detection
+ *     text_lo / ts_lo / ts_hi / begin encode what WhisperTimeStampLogitsProcessor and the two
+ *     Suppress* processors allow for the NEXT token ($TF/generation/logits_process.py:1812-2043).
+ *   self-attention KV cache is paged: pool layer base bf16 [2][n_pages][64][D],
+ *   block_table int32 [batch][pages_per_row].
+ * Replaces WhisperDecoder.forward / WhisperDecoderLayer with cache
+ * ($TF/models/whisper/modeling_whisper.py:691-796, 449-506), DynamicLayer.update
+ * ($TF/cache_utils.py:102-119), the logits processors and GenerationMixin._sample's
+ * fp32-logits -> processors -> argmax -> pad-if-finished step ($TF/generation/utils.py:2762-2797).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct tw_skinny_args {
+    const void* w;      /* bf16 [n, k] */
+    const void* x;      /* bf16 [batch, ldx] */
+    int32_t ldx;
+    const float* bias;  /* fp32 [n] or NULL */
+    int32_t batch;      /* 1..32 */
+    int32_t n;
+    int32_t k;          /* multiple of 256 */
+} tw_skinny_args;
+
+typedef struct tw_grammar {
+    int32_t eos, pad, no_timestamps, ts_begin, vocab, lang_first, lang_last, max_initial_ts, begin_index;
+} tw_grammar;
+
+/* x[b,:] = tok_emb[tokens[b, pos_b], :] + pos_emb[pos_b, :]   (fp32 residual stream [batch, d_model]) */
+int tw_dec_embed(const int32_t* tokens, int32_t tokens_ld, const void* row_state, const void* tok_emb_bf16,
+                 const float* pos_emb, float* x, int32_t batch, int32_t d_model, void* stream);
+/* out = x W^T + bias with epilogue 0: bf16 [batch, ldo]; 3: GELU -> bf16 [batch, ldo];
+ * 2: fp32 residual update in place, out[b, n] += result (out is fp32 [batch, n]). */
+int tw_dec_linear(const tw_skinny_args* args, int32_t epilogue, void* out, int32_t ldo, void* stream);
+/* fused q|k|v projection (n = 3*D): q -> q_out bf16 [batch, D]; k, v -> paged cache at position pos_b. */
+int tw_dec_qkv(const tw_skinny_args* args, void* q_out_bf16, void* kv_pool_layer, const int32_t* block_table,
+               int32_t pages_per_row, int32_t n_pages, const void* row_state, void* stream);
+int tw_dec_self_attn(const void* q_bf16, void* out_bf16, const void* kv_pool_layer, const int32_t* block_table,
+                     int32_t pages_per_row, int32_t n_pages, const void* row_state, int32_t batch, int32_t heads,
+                     void* stream);
+/* cross-attention of one query per (row, head) over src_len encoder positions; K/V row j of decode row
+ * b at k + (enc_row[b]*src_len + j)*kv_ld (+ head*64); `splits` CTAs per (row, head) with a last-CTA
+ * combine (part: fp32 [batch][heads][splits][66], counters: zero-initialised uint32 [batch][heads]). */
+int tw_dec_cross_attn(const void* q_bf16, void* out_bf16, const void* k_bf16, const void* v_bf16, int64_t kv_ld,
+                      const int32_t* enc_row, int32_t src_len, int32_t batch, int32_t heads, int32_t splits,
+                      float* part, uint32_t* counters, void* stream);
+/* LM head (tied embedding, no bias) + logits processors + per-CTA partial arg-max / log-sum-exp.
+ * part_val fp32 [batch][parts][3], part_idx int32 [batch][parts][2], parts = tw_dec_lmhead_parts(vocab).
+ * logits_out: optional raw fp32 logits [batch, vocab] (parity tests), else NULL. */
+int32_t tw_dec_lmhead_parts(int32_t vocab);
+int tw_dec_lmhead(const tw_skinny_args* args, const tw_grammar* g, const void* row_state,
+                  const uint32_t* suppress_bits, const uint32_t* begin_suppress_bits, float* part_val,
+                  int32_t* part_idx, float* logits_out, void* stream);
+/* combine partials, pick the token (forced[b, i] >= 0 overrides index i; finished rows emit pad),
+ * write tokens[b, pos_b + 1] and advance row_state.  choices: optional int32 [batch, tokens_ld] that
+ * receives the engine's own pick before the forced override (teacher-forced parity tests), or NULL. */
+int tw_dec_finalize(const float* part_val, const int32_t* part_idx, int32_t n_parts, int32_t* tokens,
+                    int32_t tokens_ld, const int32_t* forced, int32_t* choices, void* row_state,
+                    const tw_grammar* g, int32_t batch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

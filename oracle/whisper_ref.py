@@ -44,6 +44,10 @@ SUPPRESS_TOKENS = [
 BEGIN_SUPPRESS_TOKENS = [220, 50257]
 
 
+# generated-token steps whose raw logits WhisperRef.greedy keeps when recording
+RECORD_LOGIT_STEPS = (0, 1, 2, 3, 7, 20, 100, 300, 444)
+
+
 @dataclass
 class WhisperDims:
     d_model: int = 1280
@@ -168,7 +172,8 @@ class WhisperRef:
 
     # -------------------------------------------------------------------------------- processors
     @staticmethod
-    def process_logits(scores: torch.Tensor, generated: Sequence[Sequence[int]], gc: GenConfig) -> torch.Tensor:
+    def process_logits(scores: torch.Tensor, generated: Sequence[Sequence[int]], gc: GenConfig,
+                       apply_rule: bool = True) -> torch.Tensor:
         """SuppressTokens -> SuppressTokensAtBegin -> WhisperTimeStamp, on fp32 scores [B, V].
         ``generated[k]`` = tokens of row k after the decoder prompt (begin_index)."""
         s = scores.clone().float()
@@ -195,11 +200,17 @@ class WhisperRef:
             s[:, :TB] = NEG
             if gc.max_initial_timestamp_index is not None:
                 s[:, TB + gc.max_initial_timestamp_index + 1:] = NEG
+        if not apply_rule:
+            return s
         logp = torch.log_softmax(s, dim=-1)
         for k in range(s.shape[0]):
             if logp[k, TB:].logsumexp(dim=-1) > logp[k, :TB].max():
                 s[k, :TB] = NEG
         return s
+
+    @staticmethod
+    def _pre_rule_scores(scores, generated, gc):
+        return WhisperRef.process_logits(scores, generated, gc, apply_rule=False)
 
     # -------------------------------------------------------------------------------- generation
     def detect_language(self, enc_out: torch.Tensor, gc: GenConfig) -> List[int]:
@@ -222,7 +233,16 @@ class WhisperRef:
             gen = [tokens[k, P:].tolist() for k in range(B)]
             scores = self.process_logits(logits, gen, gc)
             if record is not None:
-                record.append((logits.clone(), scores.clone()))
+                # decisiveness of this step: top-1 margin of the processed scores and the gap of the
+                # timestamp-probability rule; raw logits are kept only for the sampled steps
+                TB = gc.no_timestamps_token_id + 1
+                top2 = scores.topk(2, dim=-1).values
+                raw = logits.float().clone()
+                pre = self._pre_rule_scores(raw, gen, gc)
+                rule_gap = (pre[:, TB:].logsumexp(-1) - pre[:, :TB].max(-1).values).abs()
+                step = tokens.shape[1] - P
+                record.append({"margin": (top2[:, 0] - top2[:, 1]), "rule_gap": rule_gap,
+                               "logits": raw if step in RECORD_LOGIT_STEPS else None})
             nxt = scores.argmax(-1)
             nxt = torch.where(finished, torch.full_like(nxt, gc.pad_token_id), nxt)
             tokens = torch.cat([tokens, nxt[:, None]], dim=1)

@@ -25,6 +25,16 @@ class GemmArgs(C.Structure):
     ]
 
 
+class SkinnyArgs(C.Structure):
+    _fields_ = [("w", c_void_p), ("x", c_void_p), ("ldx", c_int32), ("bias", c_void_p), ("batch", c_int32),
+                ("n", c_int32), ("k", c_int32)]
+
+
+class Grammar(C.Structure):
+    _fields_ = [(n, c_int32) for n in ("eos", "pad", "no_timestamps", "ts_begin", "vocab", "lang_first", "lang_last",
+                                       "max_initial_ts", "begin_index")]
+
+
 # name -> (restype, argtypes); mirrors include/twb200.h one to one (tests/test_abi.py checks it)
 SIGNATURES = {
     "tw_last_error": (C.c_char_p, []),
@@ -37,6 +47,18 @@ SIGNATURES = {
     "tw_layernorm": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_float, c_void_p]),
     "tw_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), c_void_p]),
     "tw_attention_enc": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int64, c_void_p]),
+    "tw_dec_embed": (C.c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
+    "tw_dec_linear": (C.c_int, [C.POINTER(SkinnyArgs), c_int32, c_void_p, c_int32, c_void_p]),
+    "tw_dec_qkv": (C.c_int, [C.POINTER(SkinnyArgs), c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
+    "tw_dec_self_attn": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_int32, c_int32,
+                                   c_void_p]),
+    "tw_dec_cross_attn": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_int32, c_int32,
+                                    c_int32, c_void_p, c_void_p, c_void_p]),
+    "tw_dec_lmhead_parts": (c_int32, [c_int32]),
+    "tw_dec_lmhead": (C.c_int, [C.POINTER(SkinnyArgs), C.POINTER(Grammar), c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_void_p]),
+    "tw_dec_finalize": (C.c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_void_p,
+                                  C.POINTER(Grammar), c_int32, c_void_p]),
     "tw_shift_frames": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int64,
                                   c_int32, c_void_p]),
 }

@@ -1,0 +1,656 @@
+// K7 / K8 — batched greedy decode step.  HBM-bound by design: every kernel
+// streams weights or KV once with 16-byte loads and keeps all per-row state on the device, so one
+// step is a fixed kernel sequence (CUDA-graph friendly; positions are read from device memory).
+//
+//   decode_embed_kernel   tok-embed + learned pos-embed -> fp32 residual stream
+//                         ($TF/models/whisper/modeling_whisper.py:736-759)
+//   skinny_gemm_kernel    out[b,n] = sum_k x[b,k] W[n,k] for B <= 32 rows: the weight is the M side
+//                         of mma.sync.m16n8k16 (16 output features x 8 batch rows per instruction),
+//                         K is split over the 8 warps of a CTA, fragments are loaded straight from
+//                         global memory with a k-permutation that makes both operands 16-byte
+//                         vector loads.  Epilogues: bias->bf16, QKV scatter into the paged
+//                         self-attention KV cache, residual add (fp32, in place), GELU->bf16, and
+//                         the LM head epilogue (Whisper logits processors + per-CTA arg-max /
+//                         log-sum-exp partials).
+//   decode_attn_kernel    one query per (row, head) against a key range: self-attention over the
+//                         paged cache, cross-attention over the per-window encoder K/V with a
+//                         split over the 1500 keys and a last-CTA-done combine.
+//   decode_finalize_kernel  combines the LM-head partials, applies the timestamp probability
+//                         rule, picks the token, handles forced tokens / finished rows and
+//                         advances the per-row grammar state
+//                         ($TF/generation/logits_process.py:1812-2043, $TF/generation/utils.py:2762-2797).
+#include "common.cuh"
+#include "twb200_internal.h"
+
+namespace tw {
+namespace dec {
+
+constexpr int MAXB = 32;
+constexpr int PAGE = 64;  // positions per KV page
+
+// ------------------------------------------------------------------------------------------------
+// per-row decoding state (device resident)
+// ------------------------------------------------------------------------------------------------
+struct RowState {
+    int pos;        // index of the token being fed this step (0-based position in tokens[])
+    int finished;   // row has emitted eos
+    int last_ts;    // last timestamp token generated so far, or -1
+    int text_lo;    // non-timestamp ids < text_lo are forbidden next step
+    int ts_lo;      // timestamp ids < ts_lo forbidden
+    int ts_hi;      // timestamp ids > ts_hi forbidden (ts_hi < ts_lo: none allowed)
+    int begin;      // 1 if the next token is the first generated one (begin-suppress applies)
+    int mode;       // 0 normal, 1 language detection (only language ids allowed)
+};
+
+struct GrammarConst {
+    int eos, pad, no_timestamps, ts_begin, vocab, lang_first, lang_last, max_initial_ts, begin_index;
+};
+
+// ------------------------------------------------------------------------------------------------
+// embedding
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) decode_embed_kernel(const int* __restrict__ tokens, int tokens_ld,
+                                                          const RowState* __restrict__ st,
+                                                          const __nv_bfloat16* __restrict__ tok_emb,
+                                                          const float* __restrict__ pos_emb,
+                                                          float* __restrict__ x, int D) {
+    const int b = blockIdx.x;
+    const int pos = st[b].pos;
+    const int tok = tokens[b * tokens_ld + pos];
+    for (int i = threadIdx.x; i < D; i += blockDim.x)
+        x[(size_t)b * D + i] = __bfloat162float(tok_emb[(size_t)tok * D + i]) + pos_emb[(size_t)pos * D + i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// skinny GEMM
+// ------------------------------------------------------------------------------------------------
+enum Epi { EPI_BF16 = 0, EPI_QKV = 1, EPI_RESID = 2, EPI_GELU_BF16 = 3, EPI_LOGITS = 4 };
+
+struct SkinnyParams {
+    const __nv_bfloat16* W;  // [N, K]
+    const __nv_bfloat16* X;  // [B, ldx]
+    int ldx;
+    const float* bias;       // [N] or null
+    int B, N, K;
+    int slabs_per_cta;
+    // EPI_BF16 / EPI_GELU_BF16
+    __nv_bfloat16* out_bf16;
+    int ldo;
+    // EPI_RESID
+    float* resid;            // [B, N] fp32, updated in place
+    // EPI_QKV
+    __nv_bfloat16* q_out;    // [B, D]
+    __nv_bfloat16* kv_pool;  // layer base: [2][n_pages][PAGE][D]
+    const int* block_table;  // [B, pages_per_row]
+    int pages_per_row, n_pages, D;
+    const RowState* st;
+    // EPI_LOGITS
+    float* logits_out;       // optional raw logits [B, N]
+    const uint32_t* suppress_bits;        // vocab bitmap
+    const uint32_t* begin_suppress_bits;  // vocab bitmap
+    GrammarConst gc;
+    float* part_val;         // [B][n_ctas][3]  (max_text, max_ts, sumexp_ts)
+    int* part_idx;           // [B][n_ctas][2]
+};
+
+TW_DEVINL uint4 ldg_stream(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+TW_DEVINL void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                              uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+        "{%0, %1, %2, %3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+TW_DEVINL bool token_allowed(int v, const RowState& s, const GrammarConst& gc, const uint32_t* sup,
+                             const uint32_t* bsup) {
+    if (s.mode == 1) return v >= gc.lang_first && v <= gc.lang_last;
+    if ((sup[v >> 5] >> (v & 31)) & 1u) return false;
+    if (s.begin && ((bsup[v >> 5] >> (v & 31)) & 1u)) return false;
+    if (v == gc.no_timestamps) return false;
+    if (v >= gc.ts_begin) return v >= s.ts_lo && v <= s.ts_hi;
+    return v >= s.text_lo;
+}
+
+template <int NB, int EPI>
+__global__ void __launch_bounds__(256) skinny_gemm_kernel(const SkinnyParams p) {
+    __shared__ float red[8][NB * 8][17];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, tg = lane & 3;
+    const int kw = p.K >> 3;  // K per warp (multiple of 32)
+    const int k_begin = warp * kw;
+    const int steps = kw >> 5;
+
+    // EPI_LOGITS running partials (threads 0..B-1 own one batch row each)
+    float best_text = -INFINITY, best_ts = -INFINITY, sum_ts = 0.f;
+    int idx_text = 0x7fffffff, idx_ts = 0x7fffffff;
+
+    for (int sl = 0; sl < p.slabs_per_cta; ++sl) {
+        const int n0 = (blockIdx.x * p.slabs_per_cta + sl) * 16;
+        if (n0 >= p.N) break;
+        const int ra = min(n0 + g, p.N - 1), rb = min(n0 + g + 8, p.N - 1);
+        const __nv_bfloat16* wa = p.W + (size_t)ra * p.K + k_begin + tg * 8;
+        const __nv_bfloat16* wb = p.W + (size_t)rb * p.K + k_begin + tg * 8;
+        const __nv_bfloat16* xr[NB];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) xr[j] = p.X + (size_t)min(j * 8 + g, p.B - 1) * p.ldx + k_begin + tg * 8;
+        float acc[NB][4];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+
+#pragma unroll 5
+        for (int s = 0; s < steps; ++s) {
+            const uint4 alo = ldg_stream(wa + s * 32);
+            const uint4 ahi = ldg_stream(wb + s * 32);
+            uint4 xb[NB];
+#pragma unroll
+            for (int j = 0; j < NB; ++j) xb[j] = *reinterpret_cast<const uint4*>(xr[j] + s * 32);
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+                mma_bf16_16816(acc[j], alo.x, ahi.x, alo.y, ahi.y, xb[j].x, xb[j].y);
+                mma_bf16_16816(acc[j], alo.z, ahi.z, alo.w, ahi.w, xb[j].z, xb[j].w);
+            }
+        }
+        __syncthreads();  // previous slab's reduction buffer fully consumed
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+            red[warp][j * 8 + 2 * tg][g] = acc[j][0];
+            red[warp][j * 8 + 2 * tg + 1][g] = acc[j][1];
+            red[warp][j * 8 + 2 * tg][g + 8] = acc[j][2];
+            red[warp][j * 8 + 2 * tg + 1][g + 8] = acc[j][3];
+        }
+        __syncthreads();
+
+        if (EPI != EPI_LOGITS) {
+            for (int o = threadIdx.x; o < NB * 8 * 16; o += 256) {
+                const int bb = o >> 4, rr = o & 15;
+                const int n = n0 + rr;
+                if (bb >= p.B || n >= p.N) continue;
+                float v = 0.f;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) v += red[w][bb][rr];
+                if (p.bias) v += p.bias[n];
+                if (EPI == EPI_BF16) {
+                    p.out_bf16[(size_t)bb * p.ldo + n] = __float2bfloat16(v);
+                } else if (EPI == EPI_GELU_BF16) {
+                    p.out_bf16[(size_t)bb * p.ldo + n] = __float2bfloat16(gelu_erf(v));
+                } else if (EPI == EPI_RESID) {
+                    p.resid[(size_t)bb * p.N + n] += v;
+                } else if (EPI == EPI_QKV) {
+                    const int which = n / p.D, c = n - which * p.D;
+                    if (which == 0) {
+                        p.q_out[(size_t)bb * p.D + c] = __float2bfloat16(v);
+                    } else {
+                        const int pos = p.st[bb].pos;
+                        const int page = p.block_table[bb * p.pages_per_row + pos / PAGE];
+                        __nv_bfloat16* dst = p.kv_pool + ((size_t)(which - 1) * p.n_pages + page) * PAGE * p.D +
+                                             (size_t)(pos % PAGE) * p.D + c;
+                        *dst = __float2bfloat16(v);
+                    }
+                }
+            }
+        } else {
+            // 16 vocab rows x B batch rows of logits for this slab
+            if (threadIdx.x < p.B) {
+                const int bb = threadIdx.x;
+                const RowState s = p.st[bb];
+#pragma unroll 4
+                for (int rr = 0; rr < 16; ++rr) {
+                    const int n = n0 + rr;
+                    if (n >= p.N) break;
+                    float v = 0.f;
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) v += red[w][bb][rr];
+                    if (p.logits_out) p.logits_out[(size_t)bb * p.N + n] = v;
+                    if (!token_allowed(n, s, p.gc, p.suppress_bits, p.begin_suppress_bits)) continue;
+                    if (n >= p.gc.ts_begin && s.mode == 0) {
+                        if (v > best_ts) {
+                            sum_ts = sum_ts * __expf(best_ts - v) + 1.0f;
+                            best_ts = v;
+                            idx_ts = n;
+                        } else {
+                            sum_ts += __expf(v - best_ts);
+                        }
+                    } else if (v > best_text) {
+                        best_text = v;
+                        idx_text = n;
+                    }
+                }
+            }
+        }
+    }
+    if (EPI == EPI_LOGITS && threadIdx.x < p.B) {
+        const size_t o = (size_t)threadIdx.x * gridDim.x + blockIdx.x;
+        p.part_val[o * 3 + 0] = best_text;
+        p.part_val[o * 3 + 1] = best_ts;
+        p.part_val[o * 3 + 2] = sum_ts;
+        p.part_idx[o * 2 + 0] = idx_text;
+        p.part_idx[o * 2 + 1] = idx_ts;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// finalize: combine partials, choose the token, advance the grammar state
+// ------------------------------------------------------------------------------------------------
+struct FinalizeParams {
+    const float* part_val;
+    const int* part_idx;
+    int n_parts;
+    int* tokens;        // [B, tokens_ld]
+    int tokens_ld;
+    const int* forced;  // [B, tokens_ld]: forced[b][i] >= 0 overrides the token written at index i
+    int* choices;       // optional [B, tokens_ld]: the engine's own pick before the forced override
+    RowState* st;
+    GrammarConst gc;
+    int max_len;        // generation stops writing at tokens_ld / max_length
+};
+
+__global__ void __launch_bounds__(128) decode_finalize_kernel(const FinalizeParams p) {
+    __shared__ float s_text[128], s_ts[128], s_sum[128];
+    __shared__ int s_itext[128], s_its[128];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    float bt = -INFINITY, bs = -INFINITY, sm = 0.f;
+    int it = 0x7fffffff, is = 0x7fffffff;
+    for (int i = tid; i < p.n_parts; i += 128) {
+        const size_t o = (size_t)b * p.n_parts + i;
+        const float vt = p.part_val[o * 3 + 0], vs = p.part_val[o * 3 + 1], ss = p.part_val[o * 3 + 2];
+        const int xt = p.part_idx[o * 2 + 0], xs = p.part_idx[o * 2 + 1];
+        if (vt > bt || (vt == bt && xt < it)) { bt = vt; it = xt; }
+        if (vs > -INFINITY) {
+            if (vs > bs || (vs == bs && xs < is)) {
+                sm = (bs > -INFINITY ? sm * __expf(bs - vs) : 0.f) + ss;
+                bs = vs;
+                is = xs;
+            } else {
+                sm += ss * __expf(vs - bs);
+            }
+        }
+    }
+    s_text[tid] = bt; s_ts[tid] = bs; s_sum[tid] = sm; s_itext[tid] = it; s_its[tid] = is;
+    __syncthreads();
+    if (tid == 0) {
+        for (int i = 1; i < 128; ++i) {
+            const float vt = s_text[i], vs = s_ts[i], ss = s_sum[i];
+            const int xt = s_itext[i], xs = s_its[i];
+            if (vt > bt || (vt == bt && xt < it)) { bt = vt; it = xt; }
+            if (vs > -INFINITY) {
+                if (vs > bs || (vs == bs && xs < is)) {
+                    sm = (bs > -INFINITY ? sm * __expf(bs - vs) : 0.f) + ss;
+                    bs = vs;
+                    is = xs;
+                } else {
+                    sm += ss * __expf(vs - bs);
+                }
+            }
+        }
+        RowState s = p.st[b];
+        const GrammarConst& gc = p.gc;
+        int tok;
+        if (s.mode == 1) {
+            tok = it;  // language id arg-max
+        } else {
+            // sum of timestamp probability above every text token -> sample a timestamp
+            // (log-softmax normaliser cancels on both sides of the comparison)
+            const float lse_ts = (bs > -INFINITY) ? bs + logf(sm) : -INFINITY;
+            if (lse_ts > bt) tok = is;
+            else tok = (bs > bt) ? is : it;  // ties resolve to the lower (text) id, as torch.argmax
+        }
+        const int wi = s.pos + 1;  // index the new token is written to
+        if (s.finished) tok = gc.pad;
+        if (p.choices && wi < p.tokens_ld) p.choices[b * p.tokens_ld + wi] = tok;
+        const int f = (wi < p.tokens_ld) ? p.forced[b * p.tokens_ld + wi] : -1;
+        if (f >= 0) tok = f;
+        if (wi < p.tokens_ld) p.tokens[b * p.tokens_ld + wi] = tok;
+
+        // ---- advance the state for the step that will feed `tok` ----
+        const int gen_before = wi - gc.begin_index;  // generated tokens before this one (may be < 0)
+        if (gen_before >= 0 && tok == gc.eos) s.finished = 1;
+        s.pos = wi;
+        s.mode = 0;
+        const int gen_now = gen_before + 1;  // generated tokens after appending tok
+        if (gen_now <= 0) {
+            // still inside the prompt: the next token is either forced or the first generated one
+            s.last_ts = -1;
+            s.begin = (gen_now == 0);
+            s.text_lo = gc.ts_begin;  // first generated token must be a timestamp ...
+            s.ts_lo = gc.ts_begin;
+            s.ts_hi = gc.ts_begin + gc.max_initial_ts;  // ... no later than max_initial_timestamp
+        } else {
+            const int prev = (gen_now >= 2) ? p.tokens[b * p.tokens_ld + wi - 1] : -1;
+            const bool last_is_ts = tok >= gc.ts_begin;
+            const bool pen_is_ts = (gen_now < 2) || prev >= gc.ts_begin;
+            if (last_is_ts) s.last_ts = tok;
+            s.begin = 0;
+            s.text_lo = 0;
+            s.ts_lo = gc.ts_begin;
+            s.ts_hi = gc.vocab - 1;
+            if (last_is_ts) {
+                if (pen_is_ts) s.ts_hi = gc.ts_begin - 1;  // timestamps forbidden
+                else s.text_lo = gc.eos;                    // text below eos forbidden
+            }
+            if (s.last_ts >= 0) {
+                const int bound = (last_is_ts && !pen_is_ts) ? s.last_ts : s.last_ts + 1;
+                if (bound > s.ts_lo) s.ts_lo = bound;
+            }
+        }
+        p.st[b] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// decode attention: one query per (row, head); lane-per-key dot products, no shuffles in the loop
+// ------------------------------------------------------------------------------------------------
+struct AttnParams {
+    const __nv_bfloat16* q;   // [B, D]
+    __nv_bfloat16* out;       // [B, D]
+    int D, H;
+    int is_cross;
+    // self: paged pool  [2][n_pages][PAGE][D] (layer base)
+    const __nv_bfloat16* kv_pool;
+    const int* block_table;
+    int pages_per_row, n_pages;
+    const RowState* st;
+    // cross: K at ck + (b*S + j)*ld, V at cv + (b*S + j)*ld
+    const __nv_bfloat16* ck;
+    const __nv_bfloat16* cv;
+    const int* enc_row;       // [B] row of the encoder batch this decode row reads (or null = b)
+    long long ld;
+    int S, splits;
+    float* part;              // [B][H][splits][66]
+    unsigned int* counters;   // [B][H]
+};
+
+TW_DEVINL void bf16x8_to_f32(const uint4& u, float* f) {
+    f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xffff0000u);
+    f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xffff0000u);
+    f[4] = __uint_as_float(u.z << 16); f[5] = __uint_as_float(u.z & 0xffff0000u);
+    f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xffff0000u);
+}
+
+constexpr int ATT_THREADS = 128;
+constexpr int ATT_MAXKEYS = 512;  // keys handled by one CTA (self: <= 448; cross: S / splits)
+
+__global__ void __launch_bounds__(ATT_THREADS) decode_attn_kernel(const AttnParams p) {
+    __shared__ float s_score[ATT_MAXKEYS];
+    __shared__ float s_red[ATT_THREADS / 32];
+    __shared__ float s_o[ATT_THREADS / 32][64];
+    __shared__ float s_q[64];
+    __shared__ int s_last;
+    const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    int j0, j1;
+    if (p.is_cross) {
+        const int per = (p.S + p.splits - 1) / p.splits;
+        j0 = split * per;
+        j1 = min(p.S, j0 + per);
+    } else {
+        j0 = 0;
+        j1 = p.st[b].pos + 1;
+    }
+    const int nk = j1 - j0;
+    if (tid < 64) s_q[tid] = __bfloat162float(p.q[(size_t)b * p.D + h * 64 + tid]);
+    __syncthreads();
+    float q[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) q[i] = s_q[i];
+
+    const int eb = (p.is_cross && p.enc_row) ? p.enc_row[b] : b;
+    auto row_ptr = [&](int j, int kv) -> const __nv_bfloat16* {
+        if (p.is_cross) return (kv ? p.cv : p.ck) + ((size_t)eb * p.S + j) * p.ld + h * 64;
+        const int page = p.block_table[b * p.pages_per_row + j / PAGE];
+        return p.kv_pool + ((size_t)kv * p.n_pages + page) * PAGE * p.D + (size_t)(j % PAGE) * p.D + h * 64;
+    };
+
+    // pass 1: scores
+    float mx = -INFINITY;
+    for (int j = j0 + tid; j < j1; j += ATT_THREADS) {
+        const uint4* kp = reinterpret_cast<const uint4*>(row_ptr(j, 0));
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            float f[8];
+            bf16x8_to_f32(p.is_cross ? ldg_stream(kp + c) : kp[c], f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s = fmaf(q[c * 8 + i], f[i], s);
+        }
+        s_score[j - j0] = s;
+        mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    if (lane == 0) s_red[warp] = mx;
+    __syncthreads();
+    mx = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
+    __syncthreads();
+    // pass 2: p = exp(s - max), partial PV
+    float o[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) o[i] = 0.f;
+    float sum = 0.f;
+    for (int j = j0 + tid; j < j1; j += ATT_THREADS) {
+        const float pj = __expf(s_score[j - j0] - mx);
+        sum += pj;
+        const uint4* vp = reinterpret_cast<const uint4*>(row_ptr(j, 1));
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            float f[8];
+            bf16x8_to_f32(p.is_cross ? ldg_stream(vp + c) : vp[c], f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[c * 8 + i] = fmaf(pj, f[i], o[c * 8 + i]);
+        }
+    }
+    sum = warp_sum(sum);
+#pragma unroll
+    for (int i = 0; i < 64; ++i) o[i] = warp_sum(o[i]);
+    if (lane == 0) {
+        s_red[warp] = sum;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) s_o[warp][i] = o[i];
+    }
+    __syncthreads();
+    const float tot = s_red[0] + s_red[1] + s_red[2] + s_red[3];
+    (void)nk;
+
+    if (!p.is_cross || p.splits == 1) {
+        if (tid < 64) {
+            const float v = (s_o[0][tid] + s_o[1][tid]) + (s_o[2][tid] + s_o[3][tid]);
+            p.out[(size_t)b * p.D + h * 64 + tid] = __float2bfloat16(v / tot);
+        }
+        return;
+    }
+    // split-K: publish (max, sum, o[64]); the last CTA of this (row, head) combines in split order
+    float* my = p.part + (((size_t)b * p.H + h) * p.splits + split) * 66;
+    if (tid < 64) my[2 + tid] = (s_o[0][tid] + s_o[1][tid]) + (s_o[2][tid] + s_o[3][tid]);
+    if (tid == 0) { my[0] = mx; my[1] = tot; }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned int prev = atomicAdd(&p.counters[b * p.H + h], 1u);
+        s_last = (prev == (unsigned)p.splits - 1);
+        if (s_last) p.counters[b * p.H + h] = 0;  // re-arm for the next launch
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (tid < 64) {
+        const float* base = p.part + ((size_t)b * p.H + h) * p.splits * 66;
+        float M = -INFINITY;
+        for (int s = 0; s < p.splits; ++s) M = fmaxf(M, __ldcg(base + s * 66));
+        float L = 0.f, O = 0.f;
+        for (int s = 0; s < p.splits; ++s) {
+            const float w = __expf(__ldcg(base + s * 66) - M);
+            L = fmaf(__ldcg(base + s * 66 + 1), w, L);
+            O = fmaf(__ldcg(base + s * 66 + 2 + tid), w, O);
+        }
+        p.out[(size_t)b * p.D + h * 64 + tid] = __float2bfloat16(O / L);
+    }
+}
+
+}  // namespace dec
+}  // namespace tw
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+using namespace tw;
+using namespace tw::dec;
+
+static_assert(sizeof(RowState) == 32, "RowState layout is part of the ABI (8 x int32)");
+
+template <int EPI>
+static int launch_skinny(const SkinnyParams& p, cudaStream_t st) {
+    const int slabs = (p.N + 15) / 16;
+    const int grid = (slabs + p.slabs_per_cta - 1) / p.slabs_per_cta;
+    const int nb = (p.B + 7) / 8;
+    switch (nb) {
+        case 1: skinny_gemm_kernel<1, EPI><<<grid, 256, 0, st>>>(p); break;
+        case 2: skinny_gemm_kernel<2, EPI><<<grid, 256, 0, st>>>(p); break;
+        case 3: skinny_gemm_kernel<3, EPI><<<grid, 256, 0, st>>>(p); break;
+        case 4: skinny_gemm_kernel<4, EPI><<<grid, 256, 0, st>>>(p); break;
+        default: set_error("skinny gemm: batch %d > %d", p.B, MAXB); return 2;
+    }
+    TW_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tw_dec_embed(const int32_t* tokens, int32_t tokens_ld, const void* row_state, const void* tok_emb_bf16,
+                            const float* pos_emb, float* x, int32_t batch, int32_t d_model, void* stream) {
+    TW_REQUIRE(tokens && row_state && tok_emb_bf16 && pos_emb && x, "tw_dec_embed: null argument");
+    if (batch <= 0) return 0;
+    decode_embed_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(tokens, tokens_ld, (const RowState*)row_state,
+                                                                (const __nv_bfloat16*)tok_emb_bf16, pos_emb, x, d_model);
+    TW_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+static int check_skinny(const tw_skinny_args* a, const char* who) {
+    TW_REQUIRE(a && a->w && a->x, "%s: null argument", who);
+    TW_REQUIRE(a->batch >= 1 && a->batch <= MAXB, "%s: batch %d not in [1,%d]", who, a->batch, MAXB);
+    TW_REQUIRE(a->k % 256 == 0, "%s: K (%d) must be a multiple of 256", who, a->k);
+    TW_REQUIRE(a->ldx % 8 == 0 && ((uintptr_t)a->x & 15) == 0 && ((uintptr_t)a->w & 15) == 0, "%s: alignment", who);
+    TW_REQUIRE(a->n > 0, "%s: bad N", who);
+    return 0;
+}
+
+static void fill_common(SkinnyParams& p, const tw_skinny_args* a) {
+    p = SkinnyParams{};
+    p.W = (const __nv_bfloat16*)a->w;
+    p.X = (const __nv_bfloat16*)a->x;
+    p.ldx = a->ldx;
+    p.bias = a->bias;
+    p.B = a->batch;
+    p.N = a->n;
+    p.K = a->k;
+    p.slabs_per_cta = 1;
+}
+
+extern "C" int tw_dec_linear(const tw_skinny_args* a, int32_t epilogue, void* out, int32_t ldo, void* stream) {
+    if (int rc = check_skinny(a, "tw_dec_linear")) return rc;
+    TW_REQUIRE(out, "tw_dec_linear: null out");
+    SkinnyParams p;
+    fill_common(p, a);
+    if (epilogue == 0) { p.out_bf16 = (__nv_bfloat16*)out; p.ldo = ldo; return launch_skinny<EPI_BF16>(p, (cudaStream_t)stream); }
+    if (epilogue == 3) { p.out_bf16 = (__nv_bfloat16*)out; p.ldo = ldo; return launch_skinny<EPI_GELU_BF16>(p, (cudaStream_t)stream); }
+    if (epilogue == 2) { p.resid = (float*)out; return launch_skinny<EPI_RESID>(p, (cudaStream_t)stream); }
+    set_error("tw_dec_linear: unknown epilogue %d", epilogue);
+    return 2;
+}
+
+extern "C" int tw_dec_qkv(const tw_skinny_args* a, void* q_out_bf16, void* kv_pool_layer, const int32_t* block_table,
+                          int32_t pages_per_row, int32_t n_pages, const void* row_state, void* stream) {
+    if (int rc = check_skinny(a, "tw_dec_qkv")) return rc;
+    TW_REQUIRE(q_out_bf16 && kv_pool_layer && block_table && row_state, "tw_dec_qkv: null argument");
+    TW_REQUIRE(a->n % 3 == 0, "tw_dec_qkv: N must be 3*D");
+    SkinnyParams p;
+    fill_common(p, a);
+    p.q_out = (__nv_bfloat16*)q_out_bf16;
+    p.kv_pool = (__nv_bfloat16*)kv_pool_layer;
+    p.block_table = block_table;
+    p.pages_per_row = pages_per_row;
+    p.n_pages = n_pages;
+    p.D = a->n / 3;
+    p.st = (const RowState*)row_state;
+    return launch_skinny<EPI_QKV>(p, (cudaStream_t)stream);
+}
+
+static GrammarConst to_gc(const tw_grammar* g) {
+    GrammarConst gc;
+    gc.eos = g->eos; gc.pad = g->pad; gc.no_timestamps = g->no_timestamps; gc.ts_begin = g->ts_begin;
+    gc.vocab = g->vocab; gc.lang_first = g->lang_first; gc.lang_last = g->lang_last;
+    gc.max_initial_ts = g->max_initial_ts; gc.begin_index = g->begin_index;
+    return gc;
+}
+
+extern "C" int32_t tw_dec_lmhead_parts(int32_t vocab) { return ((vocab + 15) / 16 + 3) / 4; }
+
+extern "C" int tw_dec_lmhead(const tw_skinny_args* a, const tw_grammar* g, const void* row_state,
+                             const uint32_t* suppress_bits, const uint32_t* begin_suppress_bits, float* part_val,
+                             int32_t* part_idx, float* logits_out, void* stream) {
+    if (int rc = check_skinny(a, "tw_dec_lmhead")) return rc;
+    TW_REQUIRE(g && row_state && suppress_bits && begin_suppress_bits && part_val && part_idx, "tw_dec_lmhead: null argument");
+    TW_REQUIRE(a->n == g->vocab, "tw_dec_lmhead: N (%d) != vocab (%d)", a->n, g->vocab);
+    SkinnyParams p;
+    fill_common(p, a);
+    p.slabs_per_cta = 4;
+    p.st = (const RowState*)row_state;
+    p.suppress_bits = suppress_bits;
+    p.begin_suppress_bits = begin_suppress_bits;
+    p.gc = to_gc(g);
+    p.part_val = part_val;
+    p.part_idx = part_idx;
+    p.logits_out = logits_out;
+    return launch_skinny<EPI_LOGITS>(p, (cudaStream_t)stream);
+}
+
+extern "C" int tw_dec_finalize(const float* part_val, const int32_t* part_idx, int32_t n_parts, int32_t* tokens,
+                               int32_t tokens_ld, const int32_t* forced, int32_t* choices, void* row_state,
+                               const tw_grammar* g, int32_t batch, void* stream) {
+    TW_REQUIRE(part_val && part_idx && tokens && forced && row_state && g, "tw_dec_finalize: null argument");
+    if (batch <= 0) return 0;
+    FinalizeParams p;
+    p.part_val = part_val; p.part_idx = part_idx; p.n_parts = n_parts; p.tokens = tokens; p.tokens_ld = tokens_ld;
+    p.forced = forced; p.choices = choices; p.st = (RowState*)row_state; p.gc = to_gc(g); p.max_len = tokens_ld;
+    decode_finalize_kernel<<<batch, 128, 0, (cudaStream_t)stream>>>(p);
+    TW_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tw_dec_self_attn(const void* q_bf16, void* out_bf16, const void* kv_pool_layer, const int32_t* block_table,
+                                int32_t pages_per_row, int32_t n_pages, const void* row_state, int32_t batch,
+                                int32_t heads, void* stream) {
+    TW_REQUIRE(q_bf16 && out_bf16 && kv_pool_layer && block_table && row_state, "tw_dec_self_attn: null argument");
+    TW_REQUIRE(pages_per_row * PAGE <= ATT_MAXKEYS, "tw_dec_self_attn: more than %d positions", ATT_MAXKEYS);
+    if (batch <= 0) return 0;
+    AttnParams p{};
+    p.q = (const __nv_bfloat16*)q_bf16; p.out = (__nv_bfloat16*)out_bf16; p.D = heads * 64; p.H = heads;
+    p.is_cross = 0; p.kv_pool = (const __nv_bfloat16*)kv_pool_layer; p.block_table = block_table;
+    p.pages_per_row = pages_per_row; p.n_pages = n_pages; p.st = (const RowState*)row_state; p.splits = 1;
+    decode_attn_kernel<<<dim3(1, heads, batch), ATT_THREADS, 0, (cudaStream_t)stream>>>(p);
+    TW_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tw_dec_cross_attn(const void* q_bf16, void* out_bf16, const void* k_bf16, const void* v_bf16,
+                                 int64_t kv_ld, const int32_t* enc_row, int32_t src_len, int32_t batch, int32_t heads,
+                                 int32_t splits, float* part, uint32_t* counters, void* stream) {
+    TW_REQUIRE(q_bf16 && out_bf16 && k_bf16 && v_bf16, "tw_dec_cross_attn: null argument");
+    TW_REQUIRE(splits >= 1 && (src_len + splits - 1) / splits <= ATT_MAXKEYS,
+               "tw_dec_cross_attn: %d keys / %d splits exceeds %d per CTA", src_len, splits, ATT_MAXKEYS);
+    TW_REQUIRE(splits == 1 || (part && counters), "tw_dec_cross_attn: split needs scratch");
+    TW_REQUIRE(kv_ld % 8 == 0, "tw_dec_cross_attn: kv_ld alignment");
+    if (batch <= 0) return 0;
+    AttnParams p{};
+    p.q = (const __nv_bfloat16*)q_bf16; p.out = (__nv_bfloat16*)out_bf16; p.D = heads * 64; p.H = heads;
+    p.is_cross = 1; p.ck = (const __nv_bfloat16*)k_bf16; p.cv = (const __nv_bfloat16*)v_bf16; p.ld = kv_ld;
+    p.enc_row = enc_row; p.S = src_len; p.splits = splits; p.part = part; p.counters = counters;
+    decode_attn_kernel<<<dim3(splits, heads, batch), ATT_THREADS, 0, (cudaStream_t)stream>>>(p);
+    TW_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}

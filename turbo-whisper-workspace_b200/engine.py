@@ -1,0 +1,474 @@
+"""Per-GPU Whisper engine: weight packing, workspaces, encoder forward, CUDA-graphed greedy decode
+and the short-form seek loop — all arithmetic through the C ABI (include/twb200.h).
+
+Host logic restated from transformers 5.5.0 (`$TF/`):
+  * WhisperGenerationMixin.generate seek loop      $TF/models/whisper/generation_whisper.py:785-903
+  * detect_language / _retrieve_init_tokens        $TF/models/whisper/generation_whisper.py:1610-1673, 1455-1608
+  * _retrieve_segment                              $TF/models/whisper/generation_whisper.py:1976-2073
+  * generate_with_fallback pad / eos stripping     $TF/models/whisper/generation_whisper.py:1063-1086
+PyTorch supplies device memory, streams and CUDA-graph capture; nothing here computes with torch ops
+on the data path (tensor allocation, H2D / D2H copies and int bookkeeping only).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from ._lib import Grammar, SkinnyArgs, check
+from .config import N_FRAMES, N_SAMPLES, GenerationSettings, WhisperDims
+
+MAX_DECODE_BATCH = 32
+PAGE = 64
+ROWSTATE_INTS = 8
+
+
+def _bf16(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.float32).to(torch.bfloat16).contiguous()
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.float32).contiguous()
+
+
+def pack_weights(sd: Dict[str, torch.Tensor], dims: WhisperDims, device) -> Dict[str, torch.Tensor]:
+    """HF ``WhisperForConditionalGeneration.state_dict()`` -> packed device tensors.
+
+    * nn.Linear weights stay [out, in] (K-major = the tcgen05 B-operand layout), rounded to bf16.
+    * q/k/v are fused into one [3D, D] matrix; the head_dim**-0.5 query scale
+      ($TF/models/whisper/modeling_whisper.py:310) is folded into Wq / bq (exact: 0.125 is a power
+      of two); k_proj has no bias -> zeros.
+    * Conv1d weights [out, in, 3] become [out, 3*in] (tap-major) for the implicit-GEMM view.
+    * all decoder layers' cross-attention k/v projections are stacked into one [L*2*D, D] matrix so
+      the per-window cross K/V is one GEMM.
+    * biases, LayerNorm parameters and positional embeddings stay fp32.
+    """
+    D = dims.d_model
+    scale = (D // dims.heads) ** -0.5
+    dev = torch.device(device)
+    w: Dict[str, torch.Tensor] = {}
+
+    def put(name, t):
+        w[name] = t.to(dev)
+
+    def attn(prefix_src, prefix_dst):
+        q_w, q_b = _f32(sd[prefix_src + "q_proj.weight"]) * scale, _f32(sd[prefix_src + "q_proj.bias"]) * scale
+        k_w = _f32(sd[prefix_src + "k_proj.weight"])
+        v_w, v_b = _f32(sd[prefix_src + "v_proj.weight"]), _f32(sd[prefix_src + "v_proj.bias"])
+        put(prefix_dst + "qkv_w", _bf16(torch.cat([q_w, k_w, v_w], 0)))
+        put(prefix_dst + "qkv_b", torch.cat([q_b, torch.zeros_like(q_b), v_b], 0))
+        put(prefix_dst + "out_w", _bf16(sd[prefix_src + "out_proj.weight"]))
+        put(prefix_dst + "out_b", _f32(sd[prefix_src + "out_proj.bias"]))
+
+    def ln(src, dst):
+        put(dst + "_w", _f32(sd[src + ".weight"]))
+        put(dst + "_b", _f32(sd[src + ".bias"]))
+
+    def mlp(src, dst):
+        put(dst + "fc1_w", _bf16(sd[src + "fc1.weight"]))
+        put(dst + "fc1_b", _f32(sd[src + "fc1.bias"]))
+        put(dst + "fc2_w", _bf16(sd[src + "fc2.weight"]))
+        put(dst + "fc2_b", _f32(sd[src + "fc2.bias"]))
+
+    e = "model.encoder."
+    put("conv1_w", _bf16(sd[e + "conv1.weight"].permute(0, 2, 1).reshape(D, -1)))
+    put("conv1_b", _f32(sd[e + "conv1.bias"]))
+    put("conv2_w", _bf16(sd[e + "conv2.weight"].permute(0, 2, 1).reshape(D, -1)))
+    put("conv2_b", _f32(sd[e + "conv2.bias"]))
+    put("enc_pos", _f32(sd[e + "embed_positions.weight"]))
+    for i in range(dims.enc_layers):
+        s, d = f"{e}layers.{i}.", f"enc{i}."
+        ln(s + "self_attn_layer_norm", d + "ln1")
+        attn(s + "self_attn.", d)
+        ln(s + "final_layer_norm", d + "ln2")
+        mlp(s, d)
+    ln(e + "layer_norm", "enc_ln")
+
+    dd = "model.decoder."
+    put("tok_emb", _bf16(sd[dd + "embed_tokens.weight"]))
+    put("dec_pos", _f32(sd[dd + "embed_positions.weight"]))
+    ckv_w, ckv_b = [], []
+    for i in range(dims.dec_layers):
+        s, d = f"{dd}layers.{i}.", f"dec{i}."
+        ln(s + "self_attn_layer_norm", d + "ln1")
+        attn(s + "self_attn.", d)
+        ln(s + "encoder_attn_layer_norm", d + "ln2")
+        put(d + "cq_w", _bf16(_f32(sd[s + "encoder_attn.q_proj.weight"]) * scale))
+        put(d + "cq_b", _f32(sd[s + "encoder_attn.q_proj.bias"]) * scale)
+        put(d + "cout_w", _bf16(sd[s + "encoder_attn.out_proj.weight"]))
+        put(d + "cout_b", _f32(sd[s + "encoder_attn.out_proj.bias"]))
+        ckv_w += [_f32(sd[s + "encoder_attn.k_proj.weight"]), _f32(sd[s + "encoder_attn.v_proj.weight"])]
+        vb = _f32(sd[s + "encoder_attn.v_proj.bias"])
+        ckv_b += [torch.zeros_like(vb), vb]
+        ln(s + "final_layer_norm", d + "ln3")
+        mlp(s, d)
+    put("ckv_w", _bf16(torch.cat(ckv_w, 0)))
+    put("ckv_b", torch.cat(ckv_b, 0))
+    ln(dd + "layer_norm", "dec_ln")
+    return w
+
+
+def _bitmap(ids: Sequence[int], vocab: int) -> np.ndarray:
+    bits = np.zeros((vocab + 31) // 32, dtype=np.uint32)
+    for t in ids:
+        if 0 <= t < vocab:
+            bits[t >> 5] |= np.uint32(1 << (t & 31))
+    return bits
+
+
+def retrieve_segment(seq: List[int], seek_num_frames: int, ts_begin: int):
+    """_retrieve_segment ($TF/models/whisper/generation_whisper.py:1976-2073) on python ints:
+    slices at consecutive timestamp pairs, returns (segments, seek advance in mel frames)."""
+    is_ts = [t >= ts_begin for t in seq]
+    single_ending = is_ts[-2:] == [False, True]
+    cuts = [i + 1 for i in range(len(seq) - 1) if is_ts[i] and is_ts[i + 1]]
+    if not cuts:
+        return [list(seq)], seek_num_frames
+    if single_ending:
+        cuts.append(len(seq))
+    else:
+        cuts[-1] += 1
+    segs, last = [], 0
+    for c in cuts:
+        segs.append(seq[last:c])
+        last = c
+    if single_ending:
+        return segs, seek_num_frames
+    return segs, (seq[last - 2] - ts_begin) * 2  # input_stride = 2 mel frames per encoder position
+
+
+class WhisperEngine:
+    """One engine per GPU.  ``max_batch`` bounds the number of 30 s windows processed together."""
+
+    def __init__(self, dims: WhisperDims, state_dict: Dict[str, torch.Tensor], device="cuda:0",
+                 gen: Optional[GenerationSettings] = None, max_batch: int = 24, cross_splits: int = 4):
+        dims.validate()
+        _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.TwError("turbo-whisper-workspace_b200 needs a CUDA (sm_100a) device; there is no CPU path")
+        if max_batch < 1 or max_batch > MAX_DECODE_BATCH:
+            raise ValueError(f"max_batch must be in [1, {MAX_DECODE_BATCH}]")
+        self.dims, self.gen = dims, gen or GenerationSettings()
+        self.device = torch.device(device)
+        self.max_batch = max_batch
+        self.cross_splits = cross_splits
+        D, F, L, Bm = dims.d_model, dims.ffn, dims.dec_layers, max_batch
+        S, T = dims.max_source_positions, N_FRAMES
+        dev = self.device
+        with torch.cuda.device(dev):
+            self.w = pack_weights(state_dict, dims, dev)
+            bf, f32, i32 = torch.bfloat16, torch.float32, torch.int32
+            z = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, device=dev)
+            self.logmel = ops.LogMel(dev, Bm)
+            # ---- encoder workspaces
+            self.pcm = z(Bm, N_SAMPLES, dtype=f32)
+            self.n_valid = z(Bm, dtype=i32)
+            self.mel_t = z(Bm, T + 2, dims.n_mels, dtype=bf)    # row 1+t = frame t; rows 0, T+1 = conv padding
+            self.mel_s = z(Bm, T + 2, dims.n_mels, dtype=bf)    # seek-shifted windows
+            self.h1 = z(Bm, T + 2, D, dtype=bf)                 # conv1 output, same padding convention
+            self.x = z(Bm * S, D, dtype=f32)                    # residual stream
+            self.xn = z(Bm * S, D, dtype=bf)                    # LayerNorm output / encoder output
+            self.qkv = z(Bm * S, 3 * D, dtype=bf)
+            self.att = z(Bm * S, D, dtype=bf)
+            self.hid = z(Bm * S, F, dtype=bf)
+            self.ckv = z(Bm * S, L * 2 * D, dtype=bf)           # cross-attention K/V of every decoder layer
+            # ---- decoder workspaces
+            self.max_len = min(self.gen.max_length, dims.max_target_positions)
+            self.pages_per_row = (self.max_len + PAGE - 1) // PAGE
+            self.n_pages = Bm * self.pages_per_row
+            self.kv_pool = z(L, 2, self.n_pages, PAGE, D, dtype=bf)
+            self.block_table = torch.arange(self.n_pages, dtype=i32, device=dev).view(Bm, self.pages_per_row).contiguous()
+            self.tokens = z(Bm, self.max_len, dtype=i32)
+            self.forced = torch.full((Bm, self.max_len), -1, dtype=i32, device=dev)
+            self.state = z(Bm, ROWSTATE_INTS, dtype=i32)
+            self.dx = z(Bm, D, dtype=f32)
+            self.dxn = z(Bm, D, dtype=bf)
+            self.dq = z(Bm, D, dtype=bf)
+            self.datt = z(Bm, D, dtype=bf)
+            self.dhid = z(Bm, F, dtype=bf)
+            self.n_parts = int(_lib.load().tw_dec_lmhead_parts(dims.vocab))
+            self.part_val = z(Bm, self.n_parts, 3, dtype=f32)
+            self.part_idx = z(Bm, self.n_parts, 2, dtype=i32)
+            self.cross_part = z(Bm, dims.heads, cross_splits, 66, dtype=f32)
+            self.cross_cnt = z(Bm, dims.heads, dtype=i32)
+            self.logits = None   # optional [Bm, vocab] fp32 raw-logit tap for parity tests
+            self.choices = None  # optional [Bm, max_len] int32 tap of the un-forced picks
+            self.sup_bits = torch.from_numpy(_bitmap(self.gen.suppress_tokens, dims.vocab).view(np.int32)).to(dev)
+            self.bsup_bits = torch.from_numpy(_bitmap(self.gen.begin_suppress_tokens, dims.vocab).view(np.int32)).to(dev)
+        g = Grammar()
+        g.eos, g.pad, g.no_timestamps = self.gen.eos_token_id, self.gen.pad_token_id, self.gen.no_timestamps_token_id
+        g.ts_begin, g.vocab = self.gen.timestamp_begin, dims.vocab
+        g.lang_first, g.lang_last = self.gen.lang_first, self.gen.lang_last
+        g.max_initial_ts = self.gen.max_initial_timestamp_index
+        g.begin_index = 3
+        self.grammar = g
+        self._graphs: Dict[int, torch.cuda.CUDAGraph] = {}
+        self.use_graphs = True
+        self.finish_check_every = 16
+        self.stats = {"enc_windows": 0, "dec_steps": 0, "launches": 0}
+
+    # ------------------------------------------------------------------------------------ helpers
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def enable_taps(self):
+        """Parity-test taps: raw fp32 logits of the last step and the un-forced picks of every step."""
+        if self.logits is None:
+            self.logits = torch.zeros(self.max_batch, self.dims.vocab, dtype=torch.float32, device=self.device)
+            self.choices = torch.zeros(self.max_batch, self.max_len, dtype=torch.int32, device=self.device)
+            self._graphs.clear()
+
+    # ------------------------------------------------------------------------------------ front end
+    def load_pcm(self, clips: Sequence[np.ndarray]) -> int:
+        """H2D of up to max_batch clips (each <= 30 s of fp32 PCM at 16 kHz; longer clips are truncated
+        like WhisperFeatureExtractor(truncation=True)).  Returns the batch size."""
+        B = len(clips)
+        if B > self.max_batch:
+            raise ValueError(f"{B} windows > max_batch {self.max_batch}")
+        host = torch.zeros(B, N_SAMPLES, dtype=torch.float32).pin_memory()
+        nv = torch.zeros(B, dtype=torch.int32)
+        for i, c in enumerate(clips):
+            c = np.asarray(c, dtype=np.float32).reshape(-1)[:N_SAMPLES]
+            host[i, :len(c)] = torch.from_numpy(c)
+            nv[i] = len(c)
+        self.pcm[:B].copy_(host, non_blocking=True)
+        self.n_valid[:B].copy_(nv.pin_memory(), non_blocking=True)
+        return B
+
+    def features(self, B: int, out_f32: Optional[torch.Tensor] = None):
+        """K1: PCM (self.pcm[:B]) -> time-major bf16 features in self.mel_t (and optionally fp32 [B,128,3000])."""
+        self.logmel(self.pcm[:B], self.n_valid[:B], out_f32=out_f32, out_t=self.mel_t, out_t_row_off=1)
+        self.stats["launches"] += 2
+
+    # ------------------------------------------------------------------------------------ encoder
+    def encode(self, B: int, mel: Optional[torch.Tensor] = None, taps: Optional[dict] = None) -> torch.Tensor:
+        """WhisperEncoder.forward for B windows whose time-major features are in ``mel`` (default
+        self.mel_t).  Leaves the final-LayerNorm output in self.xn[:B*1500] and the cross-attention
+        K/V of all decoder layers in self.ckv."""
+        d, w = self.dims, self.w
+        D, S, T, F = d.d_model, d.max_source_positions, N_FRAMES, d.ffn
+        M = B * S
+        mel = self.mel_t if mel is None else mel
+        C1 = d.n_mels
+        with torch.cuda.device(self.device):
+            # conv1 (k=3, pad 1) + GELU: A row t = [x[t-1], x[t], x[t+1]] = 3*128 contiguous elements of the padded buffer
+            ops.gemm(mel, w["conv1_w"], rows=T, batches=B, a_row_stride=C1, a_batch_stride=(T + 2) * C1, a_rows=T,
+                     bias=w["conv1_b"], act=1, out=self.h1, out_ld=D, out_batch_rows=T + 2, out_row_off=1)
+            # conv2 (k=3, stride 2, pad 1) + GELU + positional embedding -> fp32 residual stream
+            ops.gemm(self.h1, w["conv2_w"], rows=S, batches=B, a_row_stride=2 * D, a_batch_stride=(T + 2) * D,
+                     a_rows=S, bias=w["conv2_b"], act=1, resid=w["enc_pos"], resid_ld=D, resid_batch_rows=0,
+                     out=self.x, out_ld=D, out_batch_rows=S)
+            x, xn, qkv, att, hid = self.x[:M], self.xn[:M], self.qkv[:M], self.att[:M], self.hid[:M]
+            if taps is not None:
+                taps["stem"] = x.clone()
+            for i in range(d.enc_layers):
+                p = f"enc{i}."
+                ops.layernorm(x, w[p + "ln1_w"], w[p + "ln1_b"], out=xn)
+                ops.gemm(xn, w[p + "qkv_w"], rows=M, bias=w[p + "qkv_b"], out=qkv)
+                ops.attention_enc(qkv, B, S, d.heads, out=att)
+                ops.gemm(att, w[p + "out_w"], rows=M, bias=w[p + "out_b"], resid=x, resid_ld=D, out=x)
+                ops.layernorm(x, w[p + "ln2_w"], w[p + "ln2_b"], out=xn)
+                ops.gemm(xn, w[p + "fc1_w"], rows=M, bias=w[p + "fc1_b"], act=1, out=hid)
+                ops.gemm(hid, w[p + "fc2_w"], rows=M, bias=w[p + "fc2_b"], resid=x, resid_ld=D, out=x)
+                if taps is not None and i in taps.get("layers", ()):
+                    taps[f"layer{i}"] = x.clone()
+            ops.layernorm(x, w["enc_ln_w"], w["enc_ln_b"], out=xn)
+            ops.gemm(xn, w["ckv_w"], rows=M, bias=w["ckv_b"], out=self.ckv[:M])
+        self.stats["enc_windows"] += B
+        self.stats["launches"] += 2 + 7 * d.enc_layers + 2
+        return xn
+
+    # ------------------------------------------------------------------------------------ decoder
+    def _skinny(self, wname, x, bias, B, k):
+        a = SkinnyArgs()
+        wt = self.w[wname]
+        a.w, a.x, a.ldx = wt.data_ptr(), x.data_ptr(), x.stride(0)
+        a.bias = None if bias is None else self.w[bias].data_ptr()
+        a.batch, a.n, a.k = B, wt.shape[0], k
+        return a
+
+    def _decode_step(self, B: int) -> None:
+        """One greedy step for rows 0..B-1: fixed launch sequence, positions read from self.state."""
+        lib, d, w, st = _lib.load(), self.dims, self.w, self._stream()
+        D, F, L, H = d.d_model, d.ffn, d.dec_layers, d.heads
+        p = lambda t: C.c_void_p(t.data_ptr())
+        S = d.max_source_positions
+        check(lib.tw_dec_embed(p(self.tokens), self.max_len, p(self.state), p(w["tok_emb"]), p(w["dec_pos"]), p(self.dx),
+                               B, D, st), "tw_dec_embed")
+        kv_ld = L * 2 * D
+        for i in range(L):
+            q = f"dec{i}."
+            pool = C.c_void_p(self.kv_pool[i].data_ptr())
+            check(lib.tw_layernorm(p(self.dx), p(w[q + "ln1_w"]), p(w[q + "ln1_b"]), p(self.dxn), B, D, 1e-5, st), "ln1")
+            check(lib.tw_dec_qkv(C.byref(self._skinny(q + "qkv_w", self.dxn, q + "qkv_b", B, D)), p(self.dq), pool,
+                                 p(self.block_table), self.pages_per_row, self.n_pages, p(self.state), st), "tw_dec_qkv")
+            check(lib.tw_dec_self_attn(p(self.dq), p(self.datt), pool, p(self.block_table), self.pages_per_row,
+                                       self.n_pages, p(self.state), B, H, st), "tw_dec_self_attn")
+            check(lib.tw_dec_linear(C.byref(self._skinny(q + "out_w", self.datt, q + "out_b", B, D)), 2, p(self.dx), D, st),
+                  "self out_proj")
+            check(lib.tw_layernorm(p(self.dx), p(w[q + "ln2_w"]), p(w[q + "ln2_b"]), p(self.dxn), B, D, 1e-5, st), "ln2")
+            check(lib.tw_dec_linear(C.byref(self._skinny(q + "cq_w", self.dxn, q + "cq_b", B, D)), 0, p(self.dq), D, st),
+                  "cross q_proj")
+            kptr = C.c_void_p(self.ckv.data_ptr() + (i * 2 * D) * 2)
+            vptr = C.c_void_p(self.ckv.data_ptr() + (i * 2 * D + D) * 2)
+            check(lib.tw_dec_cross_attn(p(self.dq), p(self.datt), kptr, vptr, kv_ld, None, S, B, H, self.cross_splits,
+                                        p(self.cross_part), p(self.cross_cnt), st), "tw_dec_cross_attn")
+            check(lib.tw_dec_linear(C.byref(self._skinny(q + "cout_w", self.datt, q + "cout_b", B, D)), 2, p(self.dx), D, st),
+                  "cross out_proj")
+            check(lib.tw_layernorm(p(self.dx), p(w[q + "ln3_w"]), p(w[q + "ln3_b"]), p(self.dxn), B, D, 1e-5, st), "ln3")
+            check(lib.tw_dec_linear(C.byref(self._skinny(q + "fc1_w", self.dxn, q + "fc1_b", B, D)), 3, p(self.dhid), F, st),
+                  "fc1")
+            check(lib.tw_dec_linear(C.byref(self._skinny(q + "fc2_w", self.dhid, q + "fc2_b", B, F)), 2, p(self.dx), D, st),
+                  "fc2")
+        check(lib.tw_layernorm(p(self.dx), p(w["dec_ln_w"]), p(w["dec_ln_b"]), p(self.dxn), B, D, 1e-5, st), "dec_ln")
+        check(lib.tw_dec_lmhead(C.byref(self._skinny("tok_emb", self.dxn, None, B, D)), C.byref(self.grammar), p(self.state),
+                                p(self.sup_bits), p(self.bsup_bits), p(self.part_val), p(self.part_idx),
+                                None if self.logits is None else p(self.logits), st), "tw_dec_lmhead")
+        check(lib.tw_dec_finalize(p(self.part_val), p(self.part_idx), self.n_parts, p(self.tokens), self.max_len,
+                                  p(self.forced), None if self.choices is None else p(self.choices), p(self.state),
+                                  C.byref(self.grammar), B, st), "tw_dec_finalize")
+
+    @property
+    def launches_per_step(self) -> int:
+        return 1 + 11 * self.dims.dec_layers + 3
+
+    def _graph_for(self, B: int) -> torch.cuda.CUDAGraph:
+        g = self._graphs.get(B)
+        if g is None:
+            # a warm-up step outside capture (sets kernel attributes); state is re-initialised afterwards
+            state_backup = self.state.clone()
+            tokens_backup = self.tokens.clone()
+            self._decode_step(B)
+            torch.cuda.synchronize(self.device)
+            self.state.copy_(state_backup)
+            self.tokens.copy_(tokens_backup)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._decode_step(B)
+            self.state.copy_(state_backup)
+            self.tokens.copy_(tokens_backup)
+            self._graphs[B] = g
+        return g
+
+    def decode(self, B: int, prompts: Optional[torch.Tensor], n_steps: Optional[int] = None,
+               forced: Optional[torch.Tensor] = None, on_step=None) -> torch.Tensor:
+        """Greedy decode of B rows against the encoder state left by encode().
+
+        prompts: int32 [B, 3] = [<|startoftranscript|>, language, task]; a language of -1 asks for
+                 language detection at position 0 (detect_language, $TF/...generation_whisper.py:1610-1673).
+        forced:  optional int32 [B, max_len] teacher-forcing table (-1 = free running).
+        Returns the int32 token matrix [B, max_len] on the device (prompt included)."""
+        dev = self.device
+        max_len = self.max_len
+        with torch.cuda.device(dev):
+            tok0 = torch.full((B, max_len), self.gen.pad_token_id, dtype=torch.int32)
+            frc = torch.full((B, max_len), -1, dtype=torch.int32) if forced is None else forced.clone().cpu().to(torch.int32)
+            st0 = torch.zeros(B, ROWSTATE_INTS, dtype=torch.int32)
+            st0[:, 2] = -1
+            pr = prompts.cpu()
+            for b in range(B):
+                tok0[b, 0] = int(pr[b, 0])
+                if int(pr[b, 1]) < 0:
+                    st0[b, 7] = 1          # language detection at position 0
+                else:
+                    frc[b, 1] = int(pr[b, 1])
+                frc[b, 2] = int(pr[b, 2])
+            self.tokens[:B].copy_(tok0.to(dev, non_blocking=False))
+            self.forced[:B].copy_(frc.to(dev))
+            self.state[:B].copy_(st0.to(dev))
+            steps = (max_len - 1) if n_steps is None else min(n_steps, max_len - 1)
+            graph = self._graph_for(B) if self.use_graphs else None
+            for s in range(steps):
+                if graph is not None:
+                    graph.replay()
+                else:
+                    self._decode_step(B)
+                if on_step is not None:
+                    on_step(s)
+                if self.finish_check_every and (s + 1) % self.finish_check_every == 0 and s + 1 < steps:
+                    if bool(self.state[:B].cpu()[:, 1].all()):   # every row has emitted eos
+                        steps = s + 1
+                        break
+            self.stats["dec_steps"] += steps
+            self.stats["launches"] += steps * self.launches_per_step
+            return self.tokens[:B]
+
+    # ------------------------------------------------------------------------------------ generate
+    def generate_from_pcm(self, clips: Sequence[np.ndarray], task: str = "transcribe",
+                          language: Optional[str] = None) -> List[List[int]]:
+        """PCM windows (<= 30 s each) -> generated token ids per window (segments concatenated), the
+        output contract of ``WhisperGenerationMixin.generate(..., return_timestamps=True)`` minus padding."""
+        B = self.load_pcm(clips)
+        self.features(B)
+        return self.generate(B, task=task, language=language)
+
+    def _strip(self, row: List[int]) -> List[int]:
+        """generate_with_fallback's pad / eos stripping ($TF/...generation_whisper.py:1063-1086)."""
+        pad, eos = self.gen.pad_token_id, self.gen.eos_token_id
+        s = list(row)
+        if s and s[-1] == pad:
+            n_pad = sum(1 for t in s if t == pad)
+            if pad == eos:
+                n_pad -= 1
+            if n_pad:
+                s = s[:-n_pad]
+        if s and s[-1] == eos:
+            s = s[:-1]
+        return s
+
+    def generate(self, B: int, task: str = "transcribe", language: Optional[str] = None,
+                 trace: Optional[dict] = None) -> List[List[int]]:
+        """Short-form seek loop over the features in self.mel_t[:B] (greedy, timestamps on)."""
+        gen = self.gen
+        if task not in gen.task_to_id:
+            raise ValueError(f"The `{task}` task is not supported. The task should be one of {list(gen.task_to_id)}")
+        lang_id = -1
+        if language is not None:
+            key = language if language.startswith("<|") else f"<|{language}|>"
+            if key not in gen.lang_to_id:
+                raise ValueError(f"Unsupported language: {language}")
+            lang_id = gen.lang_to_id[key]
+        ts_begin = gen.timestamp_begin
+        P = 3
+        seek = [0] * B
+        max_frames = [N_FRAMES] * B
+        langs = [lang_id] * B
+        out: List[List[int]] = [[] for _ in range(B)]
+        it = 0
+        with torch.cuda.device(self.device):
+            while any(s < m for s, m in zip(seek, max_frames)):
+                it += 1
+                if it > 64:
+                    raise RuntimeError("whisper seek loop does not advance (degenerate timestamp output)")
+                rows = [b for b in range(B) if seek[b] < max_frames[b]]
+                nfr = {b: min(max_frames[b] - seek[b], N_FRAMES) for b in rows}
+                n = len(rows)
+                if it == 1:
+                    mel = self.mel_t       # seek = 0 for every row: the window is the clip itself
+                else:
+                    ops.shift_frames(self.mel_t, self.mel_s,
+                                     torch.tensor([seek[b] for b in rows], dtype=torch.int32, device=self.device),
+                                     src_row=torch.tensor(rows, dtype=torch.int32, device=self.device))
+                    self.stats["launches"] += 1
+                    mel = self.mel_s
+                self.encode(n, mel)
+                prompts = torch.tensor([[gen.decoder_start_token_id, langs[b], gen.task_to_id[task]] for b in rows],
+                                       dtype=torch.int32)
+                toks = self.decode(n, prompts).cpu().tolist()
+                if trace is not None:
+                    trace.setdefault("iterations", []).append({"rows": list(rows), "seek": [seek[b] for b in rows],
+                                                               "tokens": [list(t) for t in toks]})
+                for i, b in enumerate(rows):
+                    if langs[b] < 0:
+                        langs[b] = toks[i][1]
+                    s = self._strip(toks[i][P:])
+                    segs, adv = retrieve_segment(s, nfr[b], ts_begin)
+                    seek[b] += adv
+                    for sg in segs:
+                        out[b].extend(sg)
+        if trace is not None:
+            trace["langs"] = langs
+        return out

@@ -1,0 +1,235 @@
+"""Drop-in replacement for the Hugging Face ASR pipeline object the reference calls.
+
+The reference's hot path is ``self.transcription_model(audio_path, chunk_length_s=60, batch_size=...,
+stride_length_s=5, generate_kwargs={"task": task}, return_timestamps=True)``
+(ref:vocalis/core/audio_pipeline.py:351-358), an object made by
+``transformers.pipeline("automatic-speech-recognition", ...)`` (ref:vocalis/core/audio_pipeline.py:195-200).
+:class:`B200WhisperPipeline` keeps that call signature and output dict
+(``{"text": str, "chunks": [{"timestamp": (start, end), "text": str}, ...]}``) and restates the host
+logic of ``AutomaticSpeechRecognitionPipeline`` (transformers 5.5.0, ``$TF/``):
+  * preprocess / chunk_iter     $TF/pipelines/automatic_speech_recognition.py:341-477, 61-84
+  * _forward (stride plumbing)  $TF/pipelines/automatic_speech_recognition.py:479-560
+  * postprocess                 $TF/pipelines/automatic_speech_recognition.py:562-656
+  * batching of windows         $TF/pipelines/base.py:1298-1318, $TF/pipelines/pt_utils.py:156-298
+Token -> text/chunk stitching is the tokenizer's own ``_decode_asr`` (the tokenizer object is an input
+of the pipeline, exactly as in HF).  Everything between PCM and token ids runs on the GPU engine(s).
+"""
+from __future__ import annotations
+
+import io
+import subprocess
+import wave
+from typing import Any, Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from .config import N_SAMPLES, SAMPLING_RATE, GenerationSettings, WhisperDims
+
+
+# ------------------------------------------------------------------------------------------------
+# audio ingest (host)
+# ------------------------------------------------------------------------------------------------
+def _read_wav_bytes(payload: bytes, sampling_rate: int) -> Optional[np.ndarray]:
+    """RIFF/WAVE PCM16 / PCM32 / 8-bit reader for 16 kHz files; returns None when not applicable."""
+    if len(payload) < 12 or payload[:4] != b"RIFF" or payload[8:12] != b"WAVE":
+        return None
+    try:
+        with wave.open(io.BytesIO(payload)) as wf:
+            sr, ch, sw, n = wf.getframerate(), wf.getnchannels(), wf.getsampwidth(), wf.getnframes()
+            raw = wf.readframes(n)
+    except wave.Error:
+        return None
+    if sr != sampling_rate:
+        return None
+    if sw == 2:
+        x = np.frombuffer(raw, dtype="<i2").astype(np.float32) / 32768.0
+    elif sw == 4:
+        x = np.frombuffer(raw, dtype="<i4").astype(np.float32) / 2147483648.0
+    elif sw == 1:
+        x = (np.frombuffer(raw, dtype=np.uint8).astype(np.float32) - 128.0) / 128.0
+    else:
+        return None
+    if ch > 1:
+        x = x.reshape(-1, ch).mean(axis=1)
+    return np.ascontiguousarray(x, dtype=np.float32)
+
+
+def ffmpeg_read(payload: bytes, sampling_rate: int) -> np.ndarray:
+    """bytes -> mono fp32 at ``sampling_rate`` ($TF/pipelines/audio_utils.py:9-45).  16 kHz WAV files are
+    decoded in-process; anything else goes through the same ``ffmpeg -i pipe:0 -ac 1 -ar SR -f f32le``
+    subprocess HF uses."""
+    x = _read_wav_bytes(payload, sampling_rate)
+    if x is not None:
+        return x
+    cmd = ["ffmpeg", "-i", "pipe:0", "-ac", "1", "-ar", str(sampling_rate), "-f", "f32le", "-hide_banner",
+           "-loglevel", "quiet", "pipe:1"]
+    try:
+        with subprocess.Popen(cmd, stdin=subprocess.PIPE, stdout=subprocess.PIPE) as proc:
+            out = proc.communicate(payload)[0]
+    except FileNotFoundError as e:
+        raise ValueError("ffmpeg was not found but is required to load audio files from filename") from e
+    audio = np.frombuffer(out, np.float32)
+    if audio.shape[0] == 0:
+        raise ValueError("Soundfile is either not in the correct format or is malformed. Ensure that the soundfile "
+                         "has a valid audio file extension (e.g. wav, flac or mp3) and is not corrupted.")
+    return audio
+
+
+def load_audio(inputs: Any, sampling_rate: int = SAMPLING_RATE) -> Tuple[np.ndarray, Dict[str, Any]]:
+    """The input handling of ``preprocess`` ($TF/pipelines/automatic_speech_recognition.py:341-426):
+    str path | bytes | np.ndarray | torch.Tensor | {"raw"|"array", "sampling_rate"} -> fp32 mono PCM."""
+    extra: Dict[str, Any] = {}
+    if isinstance(inputs, str):
+        if inputs.startswith("http://") or inputs.startswith("https://"):
+            raise ValueError("remote URLs are not supported by the offline engine; pass bytes or an array")
+        with open(inputs, "rb") as f:
+            inputs = f.read()
+    if isinstance(inputs, bytes):
+        inputs = ffmpeg_read(inputs, sampling_rate)
+    if hasattr(inputs, "detach") and hasattr(inputs, "cpu"):  # torch.Tensor
+        inputs = inputs.detach().cpu().numpy()
+    if isinstance(inputs, dict):
+        inputs = dict(inputs)
+        if inputs.pop("stride", None) is not None:
+            raise ValueError("Stride is only usable with CTC models, try removing it !")
+        if not ("sampling_rate" in inputs and ("raw" in inputs or "array" in inputs)):
+            raise ValueError(
+                "When passing a dictionary to AutomaticSpeechRecognitionPipeline, the dict needs to contain a "
+                '"raw" key containing the numpy array or torch tensor representing the audio and a "sampling_rate" key, '
+                "containing the sampling_rate associated with that array")
+        arr = inputs.pop("raw", None)
+        if arr is None:
+            inputs.pop("path", None)
+            arr = inputs.pop("array", None)
+        in_sr = inputs.pop("sampling_rate")
+        extra = inputs
+        if hasattr(arr, "detach"):
+            arr = arr.detach().cpu().numpy()
+        if in_sr != sampling_rate:
+            try:
+                import torch
+                from torchaudio import functional as AF
+            except ImportError as e:
+                raise ImportError("torchaudio is required to resample audio samples in "
+                                  "AutomaticSpeechRecognitionPipeline.") from e
+            arr = AF.resample(torch.from_numpy(np.asarray(arr)), in_sr, sampling_rate).numpy()
+        inputs = arr
+    if not isinstance(inputs, np.ndarray):
+        raise TypeError(f"We expect a numpy ndarray or torch tensor as input, got `{type(inputs)}`")
+    if inputs.ndim != 1:
+        inputs = inputs.mean(axis=0)
+    return np.ascontiguousarray(inputs, dtype=np.float32), extra
+
+
+# ------------------------------------------------------------------------------------------------
+# windowing
+# ------------------------------------------------------------------------------------------------
+def chunk_windows(n_samples: int, chunk_len: int, stride_left: int, stride_right: int
+                  ) -> List[Tuple[int, int, Tuple[int, int, int], bool]]:
+    """``chunk_iter`` ($TF/pipelines/automatic_speech_recognition.py:61-84) as index arithmetic:
+    returns [(start, end, (len, stride_left, stride_right), is_last)], dropping windows that are not
+    longer than their left stride."""
+    out = []
+    step = chunk_len - stride_left - stride_right
+    for start in range(0, n_samples, step):
+        end = start + chunk_len
+        length = min(end, n_samples) - start
+        sl = 0 if start == 0 else stride_left
+        is_last = end >= n_samples
+        sr = 0 if is_last else stride_right
+        if length > sl:
+            out.append((start, start + length, (length, sl, sr), is_last))
+        if is_last:
+            break
+    return out
+
+
+class B200WhisperPipeline:
+    """Callable with the HF ASR-pipeline signature, backed by one :class:`WhisperEngine` per GPU."""
+
+    def __init__(self, state_dict, dims: WhisperDims, tokenizer, generation: Optional[GenerationSettings] = None,
+                 devices: Sequence[Union[str, int]] = ("cuda:0",), max_batch: int = 24, time_precision: float = 0.02):
+        from .scheduler import WindowScheduler
+        self.dims = dims
+        self.tokenizer = tokenizer
+        self.generation = generation or GenerationSettings()
+        self.sampling_rate = SAMPLING_RATE
+        self.time_precision = time_precision  # chunk_length 30 s / max_source_positions 1500
+        self.scheduler = WindowScheduler(state_dict, dims, self.generation, devices, max_batch)
+        self.last_stats: Dict[str, Any] = {}
+
+    @classmethod
+    def from_hf_model(cls, model, tokenizer, devices=("cuda:0",), max_batch: int = 24) -> "B200WhisperPipeline":
+        """Build from a ``transformers.WhisperForConditionalGeneration`` (weights, config, generation_config)."""
+        dims = WhisperDims.from_hf_config(model.config)
+        gen = GenerationSettings.from_hf(model.generation_config)
+        return cls(model.state_dict(), dims, tokenizer, gen, devices, max_batch)
+
+    # -------------------------------------------------------------------------------- call
+    def __call__(self, inputs, chunk_length_s: float = 0, stride_length_s=None, batch_size: Optional[int] = None,
+                 generate_kwargs: Optional[dict] = None, return_timestamps=None, return_language=None,
+                 **unused) -> Union[Dict[str, Any], List[Dict[str, Any]]]:
+        if isinstance(inputs, (list, tuple)):
+            return [self(i, chunk_length_s=chunk_length_s, stride_length_s=stride_length_s, batch_size=batch_size,
+                         generate_kwargs=generate_kwargs, return_timestamps=return_timestamps,
+                         return_language=return_language) for i in inputs]
+        generate_kwargs = dict(generate_kwargs or {})
+        task = generate_kwargs.pop("task", None) or "transcribe"
+        language = generate_kwargs.pop("language", None)
+        if generate_kwargs.pop("num_beams", 1) not in (1, None):
+            raise NotImplementedError("beam search is not implemented by the B200 engine (greedy only)")
+        if return_timestamps == "word":
+            raise NotImplementedError('return_timestamps="word" is not implemented by the B200 engine')
+        if return_timestamps == "char":
+            raise ValueError("Whisper cannot return `char` timestamps, only word level or segment level timestamps. "
+                             "Use `return_timestamps='word'` or `return_timestamps=True` respectively.")
+
+        audio, extra = load_audio(inputs, self.sampling_rate)
+        sr = self.sampling_rate
+        if chunk_length_s:
+            if stride_length_s is None:
+                stride_length_s = chunk_length_s / 6
+            if isinstance(stride_length_s, (int, float)):
+                stride_length_s = [stride_length_s, stride_length_s]
+            chunk_len = int(round(chunk_length_s * sr))
+            stride_left = int(round(stride_length_s[0] * sr))
+            stride_right = int(round(stride_length_s[1] * sr))
+            if chunk_len < stride_left + stride_right:
+                raise ValueError("Chunk length must be superior to stride length")
+            windows = chunk_windows(audio.shape[0], chunk_len, stride_left, stride_right)
+            with_stride = True
+        else:
+            if audio.shape[0] > N_SAMPLES:
+                raise NotImplementedError(
+                    "un-chunked long-form transcription (> 30 s without chunk_length_s) is not implemented; "
+                    "pass chunk_length_s as the reference does")
+            windows = [(0, audio.shape[0], (audio.shape[0], 0, 0), True)]
+            with_stride = False
+
+        # the feature extractor truncates every window to its first 30 s (truncation=True, max_length=480000)
+        clips = [audio[s:e][:N_SAMPLES] for (s, e, _, _) in windows]
+        token_rows = self.scheduler.run(clips, task=task, language=language)
+        self.last_stats = dict(self.scheduler.last_stats, windows=len(windows), audio_seconds=audio.shape[0] / sr)
+
+        # HF batches `batch_size` consecutive windows per generate call and right-pads each batch to its
+        # longest row with pad_token_id; _decode_asr ignores the padding, so the grouping only affects shapes.
+        bs = max(1, int(batch_size or 1))
+        pad = self.generation.pad_token_id
+        model_outputs = []
+        for g0 in range(0, len(windows), bs):
+            rows = token_rows[g0:g0 + bs]
+            width = max(1, max(len(r) for r in rows))
+            for i, r in enumerate(rows):
+                arr = np.full((1, width), pad, dtype=np.int64)
+                arr[0, :len(r)] = r
+                item: Dict[str, Any] = {"tokens": arr}
+                if with_stride:
+                    ln, sl, srr = windows[g0 + i][2]
+                    item["stride"] = (ln / sr, sl / sr, srr / sr)
+                model_outputs.append(item)
+        text, optional = self.tokenizer._decode_asr(model_outputs, return_timestamps=return_timestamps,
+                                                    return_language=return_language, time_precision=self.time_precision)
+        return {"text": text, **optional, **{k: [v] for k, v in extra.items()}}
+
+    def close(self):
+        self.scheduler.close()
