@@ -1,0 +1,125 @@
+"""CPU tests of the host-side mirror of the HF pipeline (windowing, strides, scheduling, seek-loop helpers)
+— no GPU, engines are replaced by fakes."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import helpers
+from turbo_whisper_workspace_b200 import pipeline as P
+from turbo_whisper_workspace_b200 import scheduler as S
+from turbo_whisper_workspace_b200.engine import retrieve_segment, _bitmap
+
+
+@pytest.mark.parametrize("n,cl,sl,sr", [(70 * 16000, 480000, 80000, 80000), (150 * 16000, 960000, 80000, 80000),
+                                        (480000, 480000, 80000, 80000), (480001, 480000, 80000, 80000),
+                                        (1000, 480000, 80000, 80000), (400000 + 320000, 480000, 80000, 80000),
+                                        (3600 * 16000, 480000, 80000, 80000), (0, 480000, 80000, 80000)])
+def test_chunk_windows_matches_hf_chunk_iter(n, cl, sl, sr):
+    """Same (stride, is_last) sequence and the same sample ranges as transformers' chunk_iter."""
+    asr = pytest.importorskip("transformers.pipelines.automatic_speech_recognition")
+
+    class FakeFE:
+        sampling_rate = 16000
+
+        def __call__(self, chunk, **kw):
+            return {"n": chunk.shape[0], "first": float(chunk[0]) if chunk.shape[0] else None}
+
+    audio = np.arange(n, dtype=np.float32)
+    want = list(asr.chunk_iter(audio, FakeFE(), cl, sl, sr))
+    got = P.chunk_windows(n, cl, sl, sr)
+    assert len(got) == len(want)
+    for (s, e, stride, is_last), w in zip(got, want):
+        assert stride == w["stride"] and is_last == w["is_last"]
+        assert e - s == w["n"] and float(audio[s]) == w["first"]
+
+
+def test_chunk_windows_counts_from_survey():
+    # 1 h @30/5/5 -> 180 windows; @60/5/5 (the reference's literal call) -> 72 windows
+    assert len(P.chunk_windows(3600 * 16000, 480000, 80000, 80000)) == 180
+    assert len(P.chunk_windows(3600 * 16000, 960000, 80000, 80000)) == 72
+    w = P.chunk_windows(150 * 16000, 960000, 80000, 80000)
+    assert [x[2] for x in w] == [(960000, 0, 80000), (960000, 80000, 80000), (800000, 80000, 0)]
+
+
+def test_partition_properties():
+    for n in (0, 1, 7, 23, 24, 180, 181):
+        for w in (1, 2, 3, 4, 8):
+            r = S.partition(n, w)
+            assert len(r) == w and r[0][0] == 0 and r[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
+            sizes = [e - s for s, e in r]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        S.partition(3, 0)
+
+
+class FakeEngine:
+    """Stands in for WhisperEngine: 'transcribes' a clip to [len(clip) % 1000, first sample * 1e3]."""
+    def __init__(self, device, max_batch=4):
+        self.device, self.max_batch, self.calls = device, max_batch, []
+
+    def generate_from_pcm(self, clips, task="transcribe", language=None):
+        assert len(clips) <= self.max_batch
+        self.calls.append(len(clips))
+        return [[len(c) % 1000, int(round(float(c[0]) * 1000))] for c in clips]
+
+
+def test_window_scheduler_orders_and_microbatches():
+    clips = [np.full(100 + i, i / 1000.0, dtype=np.float32) for i in range(23)]
+    sch = S.WindowScheduler(None, None, None, devices=["d0", "d1", "d2"], engine_factory=lambda d: FakeEngine(d, 4))
+    rows = sch.run(clips)
+    assert rows == [[(100 + i) % 1000, i] for i in range(23)]
+    assert [sum(e.calls) for e in sch.engines] == [8, 8, 7]
+    assert all(max(e.calls) <= 4 for e in sch.engines)
+    assert S.WindowScheduler(None, None, None, devices=["d0"], engine_factory=lambda d: FakeEngine(d)).run([]) == []
+
+
+def test_window_scheduler_propagates_worker_errors():
+    class Boom(FakeEngine):
+        def generate_from_pcm(self, clips, **kw):
+            raise RuntimeError("boom")
+    sch = S.WindowScheduler(None, None, None, devices=["a", "b"], engine_factory=lambda d: Boom(d))
+    with pytest.raises(RuntimeError, match="boom"):
+        sch.run([np.zeros(10, np.float32)] * 4)
+
+
+def test_retrieve_segment_matches_oracle_restatement():
+    from oracle.whisper_ref import WhisperRef, TIMESTAMP_BEGIN as TB
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        n = int(rng.integers(1, 40))
+        seq = [int(TB + rng.integers(0, 1500)) if rng.random() < 0.35 else int(rng.integers(0, 50000)) for _ in range(n)]
+        nf = int(rng.integers(1, 3001))
+        assert retrieve_segment(seq, nf, TB) == WhisperRef.retrieve_segment(seq, nf, TB)
+
+
+def test_bitmap():
+    b = _bitmap([0, 31, 32, 51865, 99999], 51866)
+    assert b[0] == (1 | (1 << 31)) and b[1] == 1 and (b[51865 >> 5] >> (51865 & 31)) & 1 and int(b.sum()) > 0
+
+
+def test_load_audio_variants(tmp_path):
+    x = helpers.quantize_pcm16(helpers.synth_clip(3, seconds=1.0))
+    p = tmp_path / "a.wav"
+    helpers.write_wav16(p, x)
+    a1, _ = P.load_audio(str(p))
+    a2, _ = P.load_audio(open(p, "rb").read())
+    a3, extra = P.load_audio({"raw": x, "sampling_rate": 16000, "foo": 1})
+    a4, _ = P.load_audio(np.stack([x, x]))
+    np.testing.assert_array_equal(a1, x)
+    np.testing.assert_array_equal(a2, x)
+    np.testing.assert_array_equal(a3, x)
+    np.testing.assert_allclose(a4, x)
+    assert extra == {"foo": 1}
+    with pytest.raises(ValueError):
+        P.load_audio({"raw": x})
+    with pytest.raises(TypeError):
+        P.load_audio(12)
+
+
+def test_mel_filters_match_oracle():
+    from oracle import logmel_ref as L
+    from turbo_whisper_workspace_b200.ops import slaney_mel_filters
+    np.testing.assert_array_equal(slaney_mel_filters(), L.mel_filter_bank().astype(np.float32))

@@ -1,0 +1,122 @@
+"""CPU tests: the oracle restatements against the committed golden fixtures generated from the installed
+third-party implementation (tests/golden/make_golden.py) and the known-answer values of SURVEY.md §8c."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from oracle import logmel_ref as L
+from oracle import whisper_ref as R
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def kat():
+    return np.load(os.path.join(GOLD, "logmel_kat.npz"))
+
+
+@pytest.fixture(scope="module")
+def model_gold():
+    return np.load(os.path.join(GOLD, "model_tiny.npz"))
+
+
+def _kat_inputs():
+    A = (0.1 * np.random.default_rng(0).standard_normal(480000)).astype(np.float32)
+    t = np.arange(480000) / 16000.0
+    return {"noise30": A, "noise10": A[:160000], "sine440": (0.5 * np.sin(2 * np.pi * 440.0 * t)).astype(np.float32),
+            "short": A[:12345], "mod": helpers.synth_clip(1, kind="mod")}
+
+
+@pytest.mark.parametrize("name", ["noise30", "noise10", "sine440", "short", "mod"])
+def test_logmel_oracle_vs_hf_golden(kat, name):
+    pcm = _kat_inputs()[name]
+    x = L.log_mel(pcm)
+    np.testing.assert_allclose(x[::8, ::25], kat[name + "_sub"], atol=2e-5, rtol=0)
+    np.testing.assert_allclose([x.mean(), x.min(), x.max()], kat[name + "_stats"], atol=2e-5)
+    assert int(L.attention_mask(len(pcm)).sum()) == int(kat[name + "_mask_sum"])
+
+
+def test_logmel_survey_known_answers():
+    """Values measured from the HF torch path during the survey."""
+    A = _kat_inputs()["noise30"]
+    x = L.log_mel(A)
+    assert x.shape == (128, 3000)
+    np.testing.assert_allclose(x[0, :4], [0.45651639, 0.56622541, 0.60694182, 0.39072639], atol=1e-5)
+    np.testing.assert_allclose(x[127, -4:], [0.74227071, 0.59086835, 0.66143847, 0.55686784], atol=1e-5)
+    assert abs(x.mean() - 0.597388) < 1e-5 and abs(x.min() + 0.501018) < 1e-5 and abs(x.max() - 0.942317) < 1e-5
+    x10 = L.log_mel(A[:160000])
+    assert int(L.attention_mask(160000).sum()) == 1000
+    np.testing.assert_allclose(x10[0, 999:1002], [0.65147579, 0.54963934, -0.22125149], atol=1e-5)
+    assert abs(x10[0, -1] + 1.05846596) < 1e-5
+    s = L.log_mel(_kat_inputs()["sine440"])
+    assert int(s[:, 1500].argmax()) == 18 and abs(s.max() - 1.48535407) < 1e-5 and abs(s.min() + 0.51464593) < 1e-5
+    w = L.hann_periodic()
+    assert w[0] == 0 and abs(w[200] - 1) < 1e-12 and abs(w[399] - 6.169e-5) < 1e-7
+
+
+def test_mel_filterbank_structure():
+    fb = L.mel_filter_bank()
+    nz = fb != 0
+    assert fb.shape == (201, 128) and int(nz.sum()) == 394 and int(nz.sum(0).max()) == 9 and int(nz.sum(1).max()) == 2
+
+
+def _clips_feats():
+    clips = [helpers.synth_clip(0), helpers.synth_clip(1, kind="mod"), helpers.synth_clip(2, seconds=11.3, kind="mod")]
+    feats = torch.stack([torch.from_numpy(L.log_mel(c)) for c in clips])
+    return clips, feats.to(torch.bfloat16).float()
+
+
+@pytest.mark.parametrize("variant", ["decisive", "varied"])
+def test_model_oracle_vs_hf_golden(model_gold, variant):
+    _, fb = _clips_feats()
+    dims = R.WhisperDims(**helpers.TINY)
+    ref = R.WhisperRef(dims, helpers.variant_state_dict(dims, variant))
+    enc = ref.encode(fb)
+    np.testing.assert_allclose(enc[:, ::50, ::8].numpy(), model_gold[f"{variant}_enc_sub"], atol=2e-4, rtol=1e-4)
+    dec_ids = torch.tensor([[50258, 50259, 50360, 50365, 400, 401, 50400, 50400, 402]] * 3)
+    logits = ref.decode(dec_ids, enc)
+    np.testing.assert_allclose(logits[:, :, ::97].numpy(), model_gold[f"{variant}_logits_sub"], atol=2e-3, rtol=1e-4)
+    assert ref.detect_language(enc, R.GenConfig()) == model_gold[f"{variant}_langs"].tolist()
+
+
+@pytest.mark.parametrize("variant", ["decisive", "varied"])
+def test_generate_oracle_vs_hf_golden(model_gold, variant):
+    """Token-exact agreement of the oracle's seek loop / logits processors with WhisperGenerationMixin.generate."""
+    _, fb = _clips_feats()
+    dims = R.WhisperDims(**helpers.TINY)
+    ref = R.WhisperRef(dims, helpers.variant_state_dict(dims, variant))
+    got = ref.generate(fb)
+    gold = model_gold[f"{variant}_generate"]
+    for b, row in enumerate(got):
+        want = gold[b].tolist()
+        while want and want[-1] == 50257:
+            want.pop()
+        assert row == want, f"row {b}"
+
+
+def test_retrieve_segment_cases():
+    TB = R.TIMESTAMP_BEGIN
+    f = R.WhisperRef.retrieve_segment
+    # single closing timestamp: everything consumed
+    segs, adv = f([TB, 5, 6, TB + 100, TB + 100, 7, TB + 200], 3000, TB)
+    assert adv == 3000 and segs == [[TB, 5, 6, TB + 100], [TB + 100, 7, TB + 200]]
+    # pair but no closing timestamp: keep up to the last pair, seek to it
+    segs, adv = f([TB, 5, TB + 100, TB + 100, 7, 8], 3000, TB)
+    assert adv == 200 and segs == [[TB, 5, TB + 100, TB + 100]]
+    # no consecutive pair: one segment, window consumed
+    segs, adv = f([TB, 5, 6, 7], 1234, TB)
+    assert adv == 1234 and segs == [[TB, 5, 6, 7]]
+
+
+def test_pipeline_golden_is_consistent_with_reference_entry_point():
+    """The fixture produced through the reference's own process_audio equals the HF pipeline call with the
+    reference's literal arguments (chunk_length_s=60, stride_length_s=5, batch_size=32 on CPU)."""
+    r = json.load(open(os.path.join(GOLD, "pipeline_tiny.json")))
+    ref = r["reference_process_audio_varied"]
+    assert ref["text"] == r["varied_60_5_32"]["text"]
+    assert ref["segments"] == r["varied_60_5_32"]["chunks"]
+    assert {"text", "segments", "merged_segments", "duration", "processing_times"} <= set(ref["keys"])

@@ -95,15 +95,14 @@ struct SkinnyParams {
 
 TW_DEVINL uint4 ldg_stream(const void* p) {
     uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+    asm("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                  : "l"(p));
     return r;
 }
 TW_DEVINL void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
                               uint32_t b1) {
-    asm volatile(
-        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
         "{%0, %1, %2, %3};"
         : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
@@ -120,7 +119,7 @@ TW_DEVINL bool token_allowed(int v, const RowState& s, const GrammarConst& gc, c
 }
 
 template <int NB, int EPI>
-__global__ void __launch_bounds__(256) skinny_gemm_kernel(const SkinnyParams p) {
+__global__ void __launch_bounds__(256, 2) skinny_gemm_kernel(const SkinnyParams p) {
     __shared__ float red[8][NB * 8][17];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, tg = lane & 3;
@@ -145,17 +144,29 @@ __global__ void __launch_bounds__(256) skinny_gemm_kernel(const SkinnyParams p) 
 #pragma unroll
         for (int j = 0; j < NB; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
 
-#pragma unroll 5
-        for (int s = 0; s < steps; ++s) {
-            const uint4 alo = ldg_stream(wa + s * 32);
-            const uint4 ahi = ldg_stream(wb + s * 32);
-            uint4 xb[NB];
+        // UN k-steps per round: all 16-byte fragment loads of the round are issued before the first mma,
+        // so one round costs one memory round trip (K = 1280 -> a single round per warp).
+        constexpr int UN = 5;
+        for (int s0 = 0; s0 < steps; s0 += UN) {
+            uint4 alo[UN], ahi[UN], xb[UN][NB];
 #pragma unroll
-            for (int j = 0; j < NB; ++j) xb[j] = *reinterpret_cast<const uint4*>(xr[j] + s * 32);
+            for (int u = 0; u < UN; ++u) {
+                if (s0 + u < steps) {
+                    alo[u] = ldg_stream(wa + (s0 + u) * 32);
+                    ahi[u] = ldg_stream(wb + (s0 + u) * 32);
 #pragma unroll
-            for (int j = 0; j < NB; ++j) {
-                mma_bf16_16816(acc[j], alo.x, ahi.x, alo.y, ahi.y, xb[j].x, xb[j].y);
-                mma_bf16_16816(acc[j], alo.z, ahi.z, alo.w, ahi.w, xb[j].z, xb[j].w);
+                    for (int j = 0; j < NB; ++j) xb[u][j] = __ldg(reinterpret_cast<const uint4*>(xr[j] + (s0 + u) * 32));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                if (s0 + u < steps) {
+#pragma unroll
+                    for (int j = 0; j < NB; ++j) {
+                        mma_bf16_16816(acc[j], alo[u].x, ahi[u].x, alo[u].y, ahi[u].y, xb[u][j].x, xb[u][j].y);
+                        mma_bf16_16816(acc[j], alo[u].z, ahi[u].z, alo[u].w, ahi[u].w, xb[u][j].z, xb[u][j].w);
+                    }
+                }
             }
         }
         __syncthreads();  // previous slab's reduction buffer fully consumed
@@ -375,16 +386,16 @@ TW_DEVINL void bf16x8_to_f32(const uint4& u, float* f) {
 }
 
 constexpr int ATT_THREADS = 128;
-constexpr int ATT_MAXKEYS = 512;  // keys handled by one CTA (self: <= 448; cross: S / splits)
+constexpr int ATT_GROUPS = ATT_THREADS / 8;  // 8 lanes share one key row (8 x 16 B = one 128-byte line)
+constexpr int ATT_KU = 4;                    // keys in flight per group
+constexpr int ATT_MAXKEYS = 512;             // keys handled by one CTA (self: <= 448; cross: S / splits)
 
 __global__ void __launch_bounds__(ATT_THREADS) decode_attn_kernel(const AttnParams p) {
-    __shared__ float s_score[ATT_MAXKEYS];
-    __shared__ float s_red[ATT_THREADS / 32];
-    __shared__ float s_o[ATT_THREADS / 32][64];
-    __shared__ float s_q[64];
+    __shared__ float s_m[ATT_GROUPS], s_l[ATT_GROUPS];
+    __shared__ float s_o[ATT_GROUPS][64];
     __shared__ int s_last;
     const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, grp = tid >> 3, l8 = tid & 7;
 
     int j0, j1;
     if (p.is_cross) {
@@ -395,80 +406,91 @@ __global__ void __launch_bounds__(ATT_THREADS) decode_attn_kernel(const AttnPara
         j0 = 0;
         j1 = p.st[b].pos + 1;
     }
-    const int nk = j1 - j0;
-    if (tid < 64) s_q[tid] = __bfloat162float(p.q[(size_t)b * p.D + h * 64 + tid]);
-    __syncthreads();
-    float q[64];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) q[i] = s_q[i];
+    float q[8];
+    bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(p.q + (size_t)b * p.D + h * 64) + l8), q);
 
     const int eb = (p.is_cross && p.enc_row) ? p.enc_row[b] : b;
-    auto row_ptr = [&](int j, int kv) -> const __nv_bfloat16* {
-        if (p.is_cross) return (kv ? p.cv : p.ck) + ((size_t)eb * p.S + j) * p.ld + h * 64;
-        const int page = p.block_table[b * p.pages_per_row + j / PAGE];
-        return p.kv_pool + ((size_t)kv * p.n_pages + page) * PAGE * p.D + (size_t)(j % PAGE) * p.D + h * 64;
+    auto row_ptr = [&](int j, int kv) -> const uint4* {
+        const __nv_bfloat16* r;
+        if (p.is_cross) {
+            r = (kv ? p.cv : p.ck) + ((size_t)eb * p.S + j) * p.ld + h * 64;
+        } else {
+            const int page = p.block_table[b * p.pages_per_row + j / PAGE];
+            r = p.kv_pool + ((size_t)kv * p.n_pages + page) * PAGE * p.D + (size_t)(j % PAGE) * p.D + h * 64;
+        }
+        return reinterpret_cast<const uint4*>(r) + l8;
     };
 
-    // pass 1: scores
-    float mx = -INFINITY;
-    for (int j = j0 + tid; j < j1; j += ATT_THREADS) {
-        const uint4* kp = reinterpret_cast<const uint4*>(row_ptr(j, 0));
-        float s = 0.f;
+    float m = -INFINITY, l = 0.f, o[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            float f[8];
-            bf16x8_to_f32(p.is_cross ? ldg_stream(kp + c) : kp[c], f);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) s = fmaf(q[c * 8 + i], f[i], s);
-        }
-        s_score[j - j0] = s;
-        mx = fmaxf(mx, s);
-    }
-    mx = warp_max(mx);
-    if (lane == 0) s_red[warp] = mx;
-    __syncthreads();
-    mx = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
-    __syncthreads();
-    // pass 2: p = exp(s - max), partial PV
-    float o[64];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) o[i] = 0.f;
-    float sum = 0.f;
-    for (int j = j0 + tid; j < j1; j += ATT_THREADS) {
-        const float pj = __expf(s_score[j - j0] - mx);
-        sum += pj;
-        const uint4* vp = reinterpret_cast<const uint4*>(row_ptr(j, 1));
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            float f[8];
-            bf16x8_to_f32(p.is_cross ? ldg_stream(vp + c) : vp[c], f);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[c * 8 + i] = fmaf(pj, f[i], o[c * 8 + i]);
-        }
-    }
-    sum = warp_sum(sum);
-#pragma unroll
-    for (int i = 0; i < 64; ++i) o[i] = warp_sum(o[i]);
-    if (lane == 0) {
-        s_red[warp] = sum;
-#pragma unroll
-        for (int i = 0; i < 64; ++i) s_o[warp][i] = o[i];
-    }
-    __syncthreads();
-    const float tot = s_red[0] + s_red[1] + s_red[2] + s_red[3];
-    (void)nk;
+    for (int i = 0; i < 8; ++i) o[i] = 0.f;
 
-    if (!p.is_cross || p.splits == 1) {
-        if (tid < 64) {
-            const float v = (s_o[0][tid] + s_o[1][tid]) + (s_o[2][tid] + s_o[3][tid]);
-            p.out[(size_t)b * p.D + h * 64 + tid] = __float2bfloat16(v / tot);
+    // trip count is uniform over the CTA (the shuffles below need every lane of the warp); key slots past
+    // j1 load a clamped row and are masked to -inf
+    for (int base = j0; base < j1; base += ATT_GROUPS * ATT_KU) {
+        const int jb = base + grp;
+        uint4 kr[ATT_KU], vr[ATT_KU];
+#pragma unroll
+        for (int u = 0; u < ATT_KU; ++u) {
+            const int j = min(jb + u * ATT_GROUPS, j1 - 1);
+            kr[u] = p.is_cross ? ldg_stream(row_ptr(j, 0)) : *row_ptr(j, 0);
+            vr[u] = p.is_cross ? ldg_stream(row_ptr(j, 1)) : *row_ptr(j, 1);
         }
+        float sc[ATT_KU];
+        float mx = m;
+#pragma unroll
+        for (int u = 0; u < ATT_KU; ++u) {
+            float f[8];
+            bf16x8_to_f32(kr[u], f);
+            float d = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) d = fmaf(q[i], f[i], d);
+            d += __shfl_xor_sync(0xffffffffu, d, 1);
+            d += __shfl_xor_sync(0xffffffffu, d, 2);
+            d += __shfl_xor_sync(0xffffffffu, d, 4);
+            sc[u] = (jb + u * ATT_GROUPS < j1) ? d : -INFINITY;
+            mx = fmaxf(mx, sc[u]);
+        }
+        if (mx == -INFINITY) continue;  // this group has no valid key in the round (no shuffles below)
+        const float alpha = (m == -INFINITY) ? 0.f : __expf(m - mx);
+        l *= alpha;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] *= alpha;
+#pragma unroll
+        for (int u = 0; u < ATT_KU; ++u) {
+            const float pj = __expf(sc[u] - mx);  // exp(-inf) = 0 for the padded slots
+            l += pj;
+            float f[8];
+            bf16x8_to_f32(vr[u], f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = fmaf(pj, f[i], o[i]);
+        }
+        m = mx;
+    }
+    if (l8 == 0) { s_m[grp] = m; s_l[grp] = l; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s_o[grp][l8 * 8 + i] = o[i];
+    __syncthreads();
+
+    float M = -INFINITY, L = 0.f, O = 0.f;
+    if (tid < 64) {
+#pragma unroll
+        for (int g = 0; g < ATT_GROUPS; ++g) M = fmaxf(M, s_m[g]);
+#pragma unroll
+        for (int g = 0; g < ATT_GROUPS; ++g) {
+            const float w = (s_m[g] == -INFINITY) ? 0.f : __expf(s_m[g] - M);
+            L = fmaf(s_l[g], w, L);
+            O = fmaf(s_o[g][tid], w, O);
+        }
+    }
+    if (!p.is_cross || p.splits == 1) {
+        if (tid < 64) p.out[(size_t)b * p.D + h * 64 + tid] = __float2bfloat16(O / L);
         return;
     }
     // split-K: publish (max, sum, o[64]); the last CTA of this (row, head) combines in split order
     float* my = p.part + (((size_t)b * p.H + h) * p.splits + split) * 66;
-    if (tid < 64) my[2 + tid] = (s_o[0][tid] + s_o[1][tid]) + (s_o[2][tid] + s_o[3][tid]);
-    if (tid == 0) { my[0] = mx; my[1] = tot; }
+    if (tid < 64) my[2 + tid] = O;
+    if (tid == 0) { my[0] = M; my[1] = L; }
     __threadfence();
     __syncthreads();
     if (tid == 0) {
@@ -481,15 +503,15 @@ __global__ void __launch_bounds__(ATT_THREADS) decode_attn_kernel(const AttnPara
     __threadfence();
     if (tid < 64) {
         const float* base = p.part + ((size_t)b * p.H + h) * p.splits * 66;
-        float M = -INFINITY;
-        for (int s = 0; s < p.splits; ++s) M = fmaxf(M, __ldcg(base + s * 66));
-        float L = 0.f, O = 0.f;
+        float Mg = -INFINITY;
+        for (int s = 0; s < p.splits; ++s) Mg = fmaxf(Mg, __ldcg(base + s * 66));
+        float Lg = 0.f, Og = 0.f;
         for (int s = 0; s < p.splits; ++s) {
-            const float w = __expf(__ldcg(base + s * 66) - M);
-            L = fmaf(__ldcg(base + s * 66 + 1), w, L);
-            O = fmaf(__ldcg(base + s * 66 + 2 + tid), w, O);
+            const float w = __expf(__ldcg(base + s * 66) - Mg);
+            Lg = fmaf(__ldcg(base + s * 66 + 1), w, Lg);
+            Og = fmaf(__ldcg(base + s * 66 + 2 + tid), w, Og);
         }
-        p.out[(size_t)b * p.D + h * 64 + tid] = __float2bfloat16(O / L);
+        p.out[(size_t)b * p.D + h * 64 + tid] = __float2bfloat16(Og / Lg);
     }
 }
 

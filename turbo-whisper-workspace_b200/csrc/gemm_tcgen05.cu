@@ -27,7 +27,8 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
 constexpr int NUM_THREADS = 192;
 constexpr int TMEM_COLS = 512;
-constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int EPI_STAGE_BYTES = 4 * 32 * 32 * 4;  // one 32x32 fp32 tile per epilogue warp
+constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align*/ + 256 /*barriers*/ + EPI_STAGE_BYTES;
 
 struct Params {
     int rows, batches, N, K;
@@ -56,6 +57,8 @@ TW_DEVINL TileCoord decode_tile(const Params& p, int tile) {
     return t;
 }
 
+// OUT_F32 / HAS_RESID / ACT are compile-time so the epilogue carries no per-element flag tests
+template <bool OUT_F32, bool HAS_RESID, int ACT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const Params p) {
@@ -145,19 +148,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================
+        // Two phases per 32-column chunk so that every global access is coalesced:
+        //   A  thread = accumulator row: tcgen05.ld 32 fp32 -> its 128-byte row of the warp's smem tile
+        //      (16-byte chunks XOR-swizzled by row, conflict-free)
+        //   B  8 lanes = one 128-byte row segment: bias, activation, fp32 residual (coalesced 128 B
+        //      loads), store (128 B fp32 / 64 B bf16 per row per instruction)
         const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-        const int row_in_tile = quarter * 32 + lane;
+        float* stage = reinterpret_cast<float*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256) +
+                       quarter * (32 * 32);
+        const int sub = lane & 7;    // phase B: 16-byte column chunk within the 32-column chunk
+        const int rgrp = lane >> 3;  // phase B: row = rgrp + 4*i
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             const TileCoord t = decode_tile(p, tile);
-            const int r = t.m0 + row_in_tile;
-            const bool row_ok = r < p.rows;
             mbar_wait(&tmem_full_bar[acc], acc_phase);
             tcgen05_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
-            const size_t out_row = ((size_t)t.b * p.out_batch_rows + p.out_row_off + r) * p.out_ld;
-            const size_t res_row = ((size_t)t.b * p.resid_batch_rows + r) * p.resid_ld;
+            const int row_base = t.m0 + quarter * 32;  // first row of this warp within the batch
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 const int n_base = t.n0 + c * 32;
@@ -165,45 +173,59 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(taddr + c * 32, v);
                 tmem_ld_wait();
-                if (row_ok) {
+                {
+                    float4* dst = reinterpret_cast<float4*>(stage + lane * 32);
+                    const int sw = lane & 7;
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {  // groups of 8 columns
-                        const int n = n_base + g * 8;
-                        if (n < p.N) {
-                            float f[8];
+                    for (int g = 0; g < 8; ++g)
+                        dst[g ^ sw] = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
+                                                  __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
+                }
+                __syncwarp();
+                const int n = n_base + sub * 4;
+                if (n < p.N) {
+                    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                    const int r0 = row_base + rgrp;  // this lane's rows are r0 + 4*i
+                    const float* rp = nullptr;
+                    if (HAS_RESID) rp = p.resid + ((size_t)t.b * p.resid_batch_rows + r0) * p.resid_ld + n;
+                    const size_t o0 = ((size_t)t.b * p.out_batch_rows + p.out_row_off + r0) * p.out_ld + n;
+                    float* of = reinterpret_cast<float*>(p.out) + o0;
+                    __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(p.out) + o0;
+                    const int nrows = p.rows - r0;  // rows r0 + 4*i with 4*i < nrows are valid
+                    float4 val[8];
+                    float4 res[8];
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[g * 8 + i]);
-                            if (p.bias) {
-                                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-                                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n) + 1);
-                                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-                            }
-                            if (p.act == 1) {
+                    for (int i = 0; i < 8; ++i) {
+                        const int rl = rgrp + 4 * i;
+                        val[i] = reinterpret_cast<const float4*>(stage + rl * 32)[sub ^ (rl & 7)];
+                        if (HAS_RESID) {
+                            res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (4 * i < nrows) res[i] = *reinterpret_cast<const float4*>(rp + (size_t)(4 * i) * p.resid_ld);
+                        }
+                    }
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) f[i] = gelu_erf_fast(f[i]);
-                            }
-                            if (p.resid) {
-                                const float4* rp = reinterpret_cast<const float4*>(p.resid + res_row + n);
-                                const float4 r0 = rp[0], r1 = rp[1];
-                                f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
-                                f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
-                            }
-                            if (p.out_f32) {
-                                float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_row + n);
-                                op[0] = make_float4(f[0], f[1], f[2], f[3]);
-                                op[1] = make_float4(f[4], f[5], f[6], f[7]);
+                    for (int i = 0; i < 8; ++i) {
+                        float4 f = val[i];
+                        f.x += bias4.x; f.y += bias4.y; f.z += bias4.z; f.w += bias4.w;
+                        if (ACT == 1) {
+                            f.x = gelu_erf_fast(f.x); f.y = gelu_erf_fast(f.y);
+                            f.z = gelu_erf_fast(f.z); f.w = gelu_erf_fast(f.w);
+                        }
+                        if (HAS_RESID) { f.x += res[i].x; f.y += res[i].y; f.z += res[i].z; f.w += res[i].w; }
+                        if (4 * i < nrows) {
+                            if (OUT_F32) {
+                                *reinterpret_cast<float4*>(of + (size_t)(4 * i) * p.out_ld) = f;
                             } else {
-                                uint4 pk;
-                                pk.x = pack_bf16x2(f[0], f[1]);
-                                pk.y = pack_bf16x2(f[2], f[3]);
-                                pk.z = pack_bf16x2(f[4], f[5]);
-                                pk.w = pack_bf16x2(f[6], f[7]);
-                                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + out_row + n) = pk;
+                                uint2 pk;
+                                pk.x = pack_bf16x2(f.x, f.y);
+                                pk.y = pack_bf16x2(f.z, f.w);
+                                *reinterpret_cast<uint2*>(ob + (size_t)(4 * i) * p.out_ld) = pk;
                             }
                         }
                     }
                 }
+                __syncwarp();  // the staging tile is rewritten by the next chunk
             }
             tcgen05_fence_before();
             mbar_arrive(&tmem_empty_bar[acc]);
@@ -283,16 +305,22 @@ extern "C" int tw_gemm_bf16(const tw_gemm_args* a, void* stream) {
     p.out_row_off = a->out_row_off;
     p.act = a->act;
 
-    static bool attr_set = false;
-    if (!attr_set) {
-        TW_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           SMEM_BYTES));
-        attr_set = true;
-    }
     const int sms = num_sms();
     TW_REQUIRE(sms > 0, "tw_gemm_bf16: no CUDA device");
     const int grid = p.num_tiles < sms ? p.num_tiles : sms;
-    gemm_bf16_kernel<<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmB, p);
+    typedef void (*kern_t)(const CUtensorMap, const CUtensorMap, const Params);
+    static const kern_t kernels[8] = {
+        gemm_bf16_kernel<false, false, 0>, gemm_bf16_kernel<false, false, 1>, gemm_bf16_kernel<false, true, 0>,
+        gemm_bf16_kernel<false, true, 1>,  gemm_bf16_kernel<true, false, 0>,  gemm_bf16_kernel<true, false, 1>,
+        gemm_bf16_kernel<true, true, 0>,   gemm_bf16_kernel<true, true, 1>};
+    static bool attr_set = false;
+    if (!attr_set) {
+        for (int i = 0; i < 8; ++i)
+            TW_CUDA_CHECK(cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr_set = true;
+    }
+    const kern_t k = kernels[(p.out_f32 ? 4 : 0) + (p.resid ? 2 : 0) + (p.act ? 1 : 0)];
+    k<<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmB, p);
     TW_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -208,7 +208,9 @@ class WhisperEngine:
         self._graphs: Dict[int, torch.cuda.CUDAGraph] = {}
         self.use_graphs = True
         self.finish_check_every = 16
-        self.stats = {"enc_windows": 0, "dec_steps": 0, "launches": 0}
+        self.stats = {"enc_windows": 0, "dec_steps": 0, "launches": 0, "h2d_bytes": 0, "d2h_bytes": 0}
+        self._pcm_host = torch.zeros(Bm, N_SAMPLES, dtype=torch.float32).pin_memory()
+        self._nv_host = torch.zeros(Bm, dtype=torch.int32).pin_memory()
 
     # ------------------------------------------------------------------------------------ helpers
     def _stream(self):
@@ -228,14 +230,18 @@ class WhisperEngine:
         B = len(clips)
         if B > self.max_batch:
             raise ValueError(f"{B} windows > max_batch {self.max_batch}")
-        host = torch.zeros(B, N_SAMPLES, dtype=torch.float32).pin_memory()
-        nv = torch.zeros(B, dtype=torch.int32)
+        torch.cuda.current_stream(self.device).synchronize()   # the pinned staging buffer may still be in flight
+        host, nv = self._pcm_host, self._nv_host
         for i, c in enumerate(clips):
             c = np.asarray(c, dtype=np.float32).reshape(-1)[:N_SAMPLES]
             host[i, :len(c)] = torch.from_numpy(c)
+            if len(c) < N_SAMPLES:
+                host[i, len(c):] = 0
             nv[i] = len(c)
-        self.pcm[:B].copy_(host, non_blocking=True)
-        self.n_valid[:B].copy_(nv.pin_memory(), non_blocking=True)
+        with torch.cuda.device(self.device):
+            self.pcm[:B].copy_(host[:B], non_blocking=True)
+            self.n_valid[:B].copy_(nv[:B], non_blocking=True)
+        self.stats["h2d_bytes"] += B * N_SAMPLES * 4 + B * 4
         return B
 
     def features(self, B: int, out_f32: Optional[torch.Tensor] = None):
@@ -379,6 +385,7 @@ class WhisperEngine:
             self.tokens[:B].copy_(tok0.to(dev, non_blocking=False))
             self.forced[:B].copy_(frc.to(dev))
             self.state[:B].copy_(st0.to(dev))
+            self.stats["h2d_bytes"] += 2 * B * max_len * 4 + B * ROWSTATE_INTS * 4
             steps = (max_len - 1) if n_steps is None else min(n_steps, max_len - 1)
             graph = self._graph_for(B) if self.use_graphs else None
             for s in range(steps):
@@ -389,6 +396,7 @@ class WhisperEngine:
                 if on_step is not None:
                     on_step(s)
                 if self.finish_check_every and (s + 1) % self.finish_check_every == 0 and s + 1 < steps:
+                    self.stats["d2h_bytes"] += B * ROWSTATE_INTS * 4
                     if bool(self.state[:B].cpu()[:, 1].all()):   # every row has emitted eos
                         steps = s + 1
                         break
@@ -458,6 +466,7 @@ class WhisperEngine:
                 prompts = torch.tensor([[gen.decoder_start_token_id, langs[b], gen.task_to_id[task]] for b in rows],
                                        dtype=torch.int32)
                 toks = self.decode(n, prompts).cpu().tolist()
+                self.stats["d2h_bytes"] += n * self.max_len * 4
                 if trace is not None:
                     trace.setdefault("iterations", []).append({"rows": list(rows), "seek": [seek[b] for b in rows],
                                                                "tokens": [list(t) for t in toks]})
