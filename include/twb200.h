@@ -94,6 +94,7 @@ typedef struct tw_gemm_args {
     int64_t out_ld;
     int64_t out_batch_rows;
     int32_t out_row_off;
+    int32_t out_mode;       /* 0: row-major as above; 1: head-major out[n/64][b][r][n%64] (K/V for decode attention) */
 } tw_gemm_args;
 int tw_gemm_bf16(const tw_gemm_args* args, void* stream);
 
@@ -136,15 +137,25 @@ typedef struct tw_skinny_args {
     int32_t batch;      /* 1..32 */
     int32_t n;
     int32_t k;          /* multiple of 256 */
+    /* residual epilogue only (tw_dec_linear epilogue 2): when ln_out_bf16 is given, the last CTA to finish
+     * writes LayerNorm(updated fp32 rows; gamma, beta, eps 1e-5) as bf16 [batch, n] (n <= 1280) — the operand of
+     * the next projection — so the decoder needs no separate LayerNorm launches.  ln_counter: zero-initialised
+     * device uint32, re-armed by the kernel. */
+    const float* ln_gamma;
+    const float* ln_beta;
+    void* ln_out_bf16;
+    uint32_t* ln_counter;
 } tw_skinny_args;
 
 typedef struct tw_grammar {
     int32_t eos, pad, no_timestamps, ts_begin, vocab, lang_first, lang_last, max_initial_ts, begin_index;
 } tw_grammar;
 
-/* x[b,:] = tok_emb[tokens[b, pos_b], :] + pos_emb[pos_b, :]   (fp32 residual stream [batch, d_model]) */
+/* x[b,:] = tok_emb[tokens[b, pos_b], :] + pos_emb[pos_b, :]   (fp32 residual stream [batch, d_model]);
+ * optionally also ln_out[b,:] = LayerNorm(x[b,:]; ln_gamma, ln_beta) as bf16 (first layer's self_attn_layer_norm). */
 int tw_dec_embed(const int32_t* tokens, int32_t tokens_ld, const void* row_state, const void* tok_emb_bf16,
-                 const float* pos_emb, float* x, int32_t batch, int32_t d_model, void* stream);
+                 const float* pos_emb, float* x, int32_t batch, int32_t d_model, const float* ln_gamma,
+                 const float* ln_beta, void* ln_out_bf16, void* stream);
 /* out = x W^T + bias with epilogue 0: bf16 [batch, ldo]; 3: GELU -> bf16 [batch, ldo];
  * 2: fp32 residual update in place, out[b, n] += result (out is fp32 [batch, n]). */
 int tw_dec_linear(const tw_skinny_args* args, int32_t epilogue, void* out, int32_t ldo, void* stream);
@@ -154,12 +165,15 @@ int tw_dec_qkv(const tw_skinny_args* args, void* q_out_bf16, void* kv_pool_layer
 int tw_dec_self_attn(const void* q_bf16, void* out_bf16, const void* kv_pool_layer, const int32_t* block_table,
                      int32_t pages_per_row, int32_t n_pages, const void* row_state, int32_t batch, int32_t heads,
                      void* stream);
-/* cross-attention of one query per (row, head) over src_len encoder positions; K/V row j of decode row
- * b at k + (enc_row[b]*src_len + j)*kv_ld (+ head*64); `splits` CTAs per (row, head) with a last-CTA
- * combine (part: fp32 [batch][heads][splits][66], counters: zero-initialised uint32 [batch][heads]). */
-int tw_dec_cross_attn(const void* q_bf16, void* out_bf16, const void* k_bf16, const void* v_bf16, int64_t kv_ld,
-                      const int32_t* enc_row, int32_t src_len, int32_t batch, int32_t heads, int32_t splits,
-                      float* part, uint32_t* counters, void* stream);
+/* cross-attention of one query per (row, head) over src_len encoder positions; K row j of decode row b, head h at
+ * k + enc_row[b]*kv_batch_stride + h*kv_head_stride + j*kv_row_stride (elements; V likewise).  The engine stores
+ * K/V head-major ([head][row][pos][64], tw_gemm_bf16 out_mode 1) so every CTA streams one contiguous block.
+ * `splits` CTAs per (row, head) with a last-CTA combine (part: fp32 [batch][heads][splits][66], counters:
+ * zero-initialised uint32 [batch][heads]). */
+int tw_dec_cross_attn(const void* q_bf16, void* out_bf16, const void* k_bf16, const void* v_bf16,
+                      int64_t kv_row_stride, int64_t kv_batch_stride, int64_t kv_head_stride, const int32_t* enc_row,
+                      int32_t src_len, int32_t batch, int32_t heads, int32_t splits, float* part, uint32_t* counters,
+                      void* stream);
 /* LM head (tied embedding, no bias) + logits processors + per-CTA partial arg-max / log-sum-exp.
  * part_val fp32 [batch][parts][3], part_idx int32 [batch][parts][2], parts = tw_dec_lmhead_parts(vocab).
  * logits_out: optional raw fp32 logits [batch, vocab] (parity tests), else NULL. */

@@ -56,6 +56,13 @@ def hf_model(variant: str):
 
 def main():
     fe = WhisperFeatureExtractor(feature_size=128)
+    if "--pipeline-only" not in sys.argv:
+        part12(fe)
+    part3(fe)
+    print("golden fixtures written")
+
+
+def part12(fe):
     # ---------------------------------------------------------------- 1. log-mel known answers
     A = (0.1 * np.random.default_rng(0).standard_normal(480000)).astype(np.float32)
     t = np.arange(480000) / 16000.0
@@ -91,20 +98,35 @@ def main():
             out[f"{variant}_langs"] = lang.numpy().astype(np.int32)
     np.savez_compressed(os.path.join(HERE, "model_tiny.npz"), **out)
 
+
+
+def part3(fe):
     # ---------------------------------------------------------------- 3. pipeline end to end
     tok = helpers.build_tokenizer()
     asr.ffmpeg_read = lambda b, sr: (np.frombuffer(wave.open(io.BytesIO(b)).readframes(10 ** 9), np.int16)
                                      .astype(np.float32) / 32768.0)
-    long_pcm = np.concatenate([helpers.synth_clip(10 + i, kind="mod" if i % 2 else "noise") for i in range(3)])[:70 * 16000]
-    wav_path = "/tmp/golden_70s.wav"
+    # 71.3 s: with stride 0 the 30 s windows are exactly the three clips of the model fixtures (on which the
+    # "decisive" model's greedy picks all have margins far above the bf16 tolerance)
+    long_pcm = np.concatenate([helpers.synth_clip(0), helpers.synth_clip(1, kind="mod"),
+                               helpers.synth_clip(2, seconds=11.3, kind="mod")])
+    wav_path = "/tmp/golden_71s.wav"
     helpers.write_wav16(wav_path, long_pcm)
     results = {}
+    # decisiveness of the stride-0 windows under PCM16 quantisation, measured with the oracle
+    from oracle import logmel_ref as L
+    q = helpers.quantize_pcm16(long_pcm)
+    wfeats = torch.stack([torch.from_numpy(L.log_mel(q[i * 480000:(i + 1) * 480000])) for i in range(3)])
+    tr = {}
+    R.WhisperRef(R.WhisperDims(**helpers.TINY), helpers.variant_state_dict(R.WhisperDims(**helpers.TINY), "decisive")
+                 ).generate(wfeats.to(torch.bfloat16).float(), trace=tr)
+    results["decisive_30_0_min_margin"] = float(min(min(float(r["margin"].min()), float(r["rule_gap"].min()))
+                                                    for it in tr["iterations"] for r in it["record"]))
     for variant in ("decisive", "varied"):
         model, _ = hf_model(variant)
         pipe = pipeline("automatic-speech-recognition", model=model, tokenizer=tok, feature_extractor=fe, device="cpu",
                         dtype=torch.float32)
         pipe.generation_config.num_beams = 1      # greedy oracle
-        for (cl, st, bs) in ((30, 5, 24), (60, 5, 32), (30, 3, 2)):
+        for (cl, st, bs) in ((30, 0, 24), (30, 5, 24), (60, 5, 32)):
             r = pipe(wav_path, chunk_length_s=cl, stride_length_s=st, batch_size=bs, generate_kwargs={"task": "transcribe"},
                      return_timestamps=True)
             results[f"{variant}_{cl}_{st}_{bs}"] = {"text": r["text"], "chunks": [
@@ -126,7 +148,6 @@ def main():
                 "keys": sorted(res.keys())}
     with open(os.path.join(HERE, "pipeline_tiny.json"), "w") as f:
         json.dump(results, f, indent=1, ensure_ascii=False)
-    print("golden fixtures written")
 
 
 if __name__ == "__main__":

@@ -41,7 +41,7 @@ def test_struct_layouts_match_header():
     from turbo_whisper_workspace_b200 import _lib
     # tw_gemm_args: 20 fields, natural alignment on LP64
     assert C.sizeof(_lib.GemmArgs) == 144
-    assert C.sizeof(_lib.SkinnyArgs) == 48
+    assert C.sizeof(_lib.SkinnyArgs) == 80
     assert C.sizeof(_lib.Grammar) == 36
 
 

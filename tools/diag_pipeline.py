@@ -12,7 +12,7 @@ rd = R.WhisperDims(**helpers.TINY)
 sd = helpers.variant_state_dict(rd, "decisive")
 ref = R.WhisperRef(rd, sd)
 eng = WhisperEngine(WhisperDims(**helpers.TINY), sd, device="cuda:0", max_batch=4)
-for (cl, st) in ((60, 5), (30, 3)):
+for (cl, st) in ((30, 5),):
     wins = P.chunk_windows(len(pcm), cl * 16000, st * 16000, st * 16000)
     clips = [pcm[s:e][:480000] for (s, e, _, _) in wins]
     feats = torch.stack([torch.from_numpy(L.log_mel(c)) for c in clips]).to(torch.bfloat16).float()

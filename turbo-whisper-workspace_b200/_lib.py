@@ -21,13 +21,14 @@ class GemmArgs(C.Structure):
         ("a_row_off", c_void_p), ("w", c_void_p), ("batches", c_int32), ("rows", c_int32),
         ("n", c_int32), ("k", c_int32), ("bias", c_void_p), ("act", c_int32), ("resid", c_void_p),
         ("resid_ld", c_int64), ("resid_batch_rows", c_int64), ("out", c_void_p), ("out_f32", c_int32),
-        ("out_ld", c_int64), ("out_batch_rows", c_int64), ("out_row_off", c_int32),
+        ("out_ld", c_int64), ("out_batch_rows", c_int64), ("out_row_off", c_int32), ("out_mode", c_int32),
     ]
 
 
 class SkinnyArgs(C.Structure):
     _fields_ = [("w", c_void_p), ("x", c_void_p), ("ldx", c_int32), ("bias", c_void_p), ("batch", c_int32),
-                ("n", c_int32), ("k", c_int32)]
+                ("n", c_int32), ("k", c_int32), ("ln_gamma", c_void_p), ("ln_beta", c_void_p), ("ln_out_bf16", c_void_p),
+                ("ln_counter", c_void_p)]
 
 
 class Grammar(C.Structure):
@@ -47,13 +48,14 @@ SIGNATURES = {
     "tw_layernorm": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_float, c_void_p]),
     "tw_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), c_void_p]),
     "tw_attention_enc": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int64, c_void_p]),
-    "tw_dec_embed": (C.c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
+    "tw_dec_embed": (C.c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p,
+                               c_void_p, c_void_p, c_void_p]),
     "tw_dec_linear": (C.c_int, [C.POINTER(SkinnyArgs), c_int32, c_void_p, c_int32, c_void_p]),
     "tw_dec_qkv": (C.c_int, [C.POINTER(SkinnyArgs), c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "tw_dec_self_attn": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_int32, c_int32,
                                    c_void_p]),
-    "tw_dec_cross_attn": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_int32, c_int32,
-                                    c_int32, c_void_p, c_void_p, c_void_p]),
+    "tw_dec_cross_attn": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int32,
+                                    c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "tw_dec_lmhead_parts": (c_int32, [c_int32]),
     "tw_dec_lmhead": (C.c_int, [C.POINTER(SkinnyArgs), C.POINTER(Grammar), c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p]),

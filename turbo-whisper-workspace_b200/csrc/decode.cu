@@ -49,16 +49,58 @@ struct GrammarConst {
 // ------------------------------------------------------------------------------------------------
 // embedding
 // ------------------------------------------------------------------------------------------------
+// also emits LayerNorm(x) (first decoder layer's self_attn_layer_norm) as bf16 when ln_out is given
 __global__ void __launch_bounds__(256) decode_embed_kernel(const int* __restrict__ tokens, int tokens_ld,
                                                           const RowState* __restrict__ st,
                                                           const __nv_bfloat16* __restrict__ tok_emb,
                                                           const float* __restrict__ pos_emb,
-                                                          float* __restrict__ x, int D) {
+                                                          float* __restrict__ x, int D,
+                                                          const float* __restrict__ ln_g,
+                                                          const float* __restrict__ ln_b,
+                                                          __nv_bfloat16* __restrict__ ln_out) {
+    __shared__ float s_red[2][8];
     const int b = blockIdx.x;
     const int pos = st[b].pos;
     const int tok = tokens[b * tokens_ld + pos];
-    for (int i = threadIdx.x; i < D; i += blockDim.x)
-        x[(size_t)b * D + i] = __bfloat162float(tok_emb[(size_t)tok * D + i]) + pos_emb[(size_t)pos * D + i];
+    float v[8];  // D <= 2048
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = threadIdx.x + i * 256;
+        v[i] = 0.f;
+        if (c < D) {
+            v[i] = __bfloat162float(tok_emb[(size_t)tok * D + c]) + pos_emb[(size_t)pos * D + c];
+            x[(size_t)b * D + c] = v[i];
+            sum += v[i];
+        }
+    }
+    if (!ln_out) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    sum = warp_sum(sum);
+    if (lane == 0) s_red[0][warp] = sum;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += s_red[0][w];
+    const float mean = tot / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = threadIdx.x + i * 256;
+        if (c < D) { const float d = v[i] - mean; q += d * d; }
+    }
+    q = warp_sum(q);
+    if (lane == 0) s_red[1][warp] = q;
+    __syncthreads();
+    float qt = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) qt += s_red[1][w];
+    const float rstd = rsqrtf(qt / (float)D + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = threadIdx.x + i * 256;
+        if (c < D) ln_out[(size_t)b * D + c] = __float2bfloat16((v[i] - mean) * rstd * ln_g[c] + ln_b[c]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -70,6 +112,12 @@ struct SkinnyParams {
     const __nv_bfloat16* W;  // [N, K]
     const __nv_bfloat16* X;  // [B, ldx]
     int ldx;
+    // EPI_RESID only: after the in-place residual update the last CTA to finish LayerNorms the updated
+    // fp32 rows into ln_out (the operand of the next projection), so no LayerNorm launch is needed
+    const float* ln_g;
+    const float* ln_b;
+    __nv_bfloat16* ln_out;       // [B, N] or null
+    unsigned int* ln_counter;    // zero-initialised, self re-arming
     const float* bias;       // [N] or null
     int B, N, K;
     int slabs_per_cta;
@@ -118,25 +166,87 @@ TW_DEVINL bool token_allowed(int v, const RowState& s, const GrammarConst& gc, c
     return v >= s.text_lo;
 }
 
-template <int NB, int EPI>
-__global__ void __launch_bounds__(256, 2) skinny_gemm_kernel(const SkinnyParams p) {
-    __shared__ float red[8][NB * 8][17];
+// One warp-row LayerNorm (fp32 two-pass statistics, eps 1e-5) of x[0..K) -> bf16; K <= 1280, K % 128 == 0.
+// LOADCG: read through L2 (rows just written by other CTAs).
+template <bool LOADCG>
+TW_DEVINL void warp_layernorm_row(const float* __restrict__ x, const float* __restrict__ gamma,
+                                  const float* __restrict__ beta, __nv_bfloat16* __restrict__ out, int K, int lane) {
+    const int nvec = K >> 7;
+    const float4* xr = reinterpret_cast<const float4*>(x);
+    float4 v[10];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 10; ++i)
+        if (i < nvec) {
+            v[i] = LOADCG ? __ldcg(xr + lane + i * 32) : xr[lane + i * 32];
+            sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+    const float mean = warp_sum(sum) / (float)K;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 10; ++i)
+        if (i < nvec) {
+            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+            q += (a * a + b * b) + (c * c + d * d);
+        }
+    const float rstd = rsqrtf(warp_sum(q) / (float)K + 1e-5f);
+    uint2* dst = reinterpret_cast<uint2*>(out);
+#pragma unroll
+    for (int i = 0; i < 10; ++i)
+        if (i < nvec) {
+            const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + lane + i * 32);
+            const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + lane + i * 32);
+            uint2 pk;
+            pk.x = pack_bf16x2((v[i].x - mean) * rstd * ga.x + be.x, (v[i].y - mean) * rstd * ga.y + be.y);
+            pk.y = pack_bf16x2((v[i].z - mean) * rstd * ga.z + be.z, (v[i].w - mean) * rstd * ga.w + be.w);
+            dst[lane + i * 32] = pk;
+        }
+}
+
+template <int NB, int EPI, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, (WARPS == 8 && EPI != EPI_LOGITS) ? 2 : 1) skinny_gemm_kernel(const SkinnyParams p) {
+    constexpr int NT = WARPS * 32;
+    __shared__ float red[WARPS][NB * 8][17];
+    __shared__ float tile[NB * 8][17];                       // EPI_LOGITS: reduced logits of the slab
+    __shared__ float s_bt[NB * 8], s_bs[NB * 8], s_sum[NB * 8];  // EPI_LOGITS running partials per row
+    __shared__ int s_it[NB * 8], s_is[NB * 8];
+    __shared__ int s_last;
+
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, tg = lane & 3;
-    const int kw = p.K >> 3;  // K per warp (multiple of 32)
+    const int kw = p.K / WARPS;  // K per warp (multiple of 32)
     const int k_begin = warp * kw;
     const int steps = kw >> 5;
 
-    // EPI_LOGITS running partials (threads 0..B-1 own one batch row each)
-    float best_text = -INFINITY, best_ts = -INFINITY, sum_ts = 0.f;
-    int idx_text = 0x7fffffff, idx_ts = 0x7fffffff;
+    if (EPI == EPI_LOGITS) {
+        for (int i = threadIdx.x; i < NB * 8; i += NT) {
+            s_bt[i] = -INFINITY; s_bs[i] = -INFINITY; s_sum[i] = 0.f; s_it[i] = 0x7fffffff; s_is[i] = 0x7fffffff;
+        }
+    }
+
+    constexpr int UN = 5;  // k-steps per round: their 16-byte fragment loads are all issued before the first mma
+    // weight fragments of the NEXT slab are prefetched while the current slab is reduced / post-processed
+    // (only when one round covers the warp's K range, i.e. steps <= UN: the LM head and every K = 1280 case)
+    const bool can_prefetch = (EPI == EPI_LOGITS) && steps <= UN;  // multi-slab CTAs only exist for the LM head
+    uint4 nlo[EPI == EPI_LOGITS ? UN : 1], nhi[EPI == EPI_LOGITS ? UN : 1];
+    auto w_row = [&](int n0v, int half) { return min(n0v + g + 8 * half, p.N - 1); };
+    if (EPI == EPI_LOGITS && can_prefetch) {
+        const int n0f = blockIdx.x * p.slabs_per_cta * 16;
+        if (n0f < p.N) {
+#pragma unroll
+            for (int u = 0; u < (EPI == EPI_LOGITS ? UN : 1); ++u)
+                if (u < steps) {
+                    nlo[u] = ldg_stream(p.W + (size_t)w_row(n0f, 0) * p.K + k_begin + tg * 8 + u * 32);
+                    nhi[u] = ldg_stream(p.W + (size_t)w_row(n0f, 1) * p.K + k_begin + tg * 8 + u * 32);
+                }
+        }
+    }
 
     for (int sl = 0; sl < p.slabs_per_cta; ++sl) {
         const int n0 = (blockIdx.x * p.slabs_per_cta + sl) * 16;
         if (n0 >= p.N) break;
-        const int ra = min(n0 + g, p.N - 1), rb = min(n0 + g + 8, p.N - 1);
-        const __nv_bfloat16* wa = p.W + (size_t)ra * p.K + k_begin + tg * 8;
-        const __nv_bfloat16* wb = p.W + (size_t)rb * p.K + k_begin + tg * 8;
+        const __nv_bfloat16* wa = p.W + (size_t)w_row(n0, 0) * p.K + k_begin + tg * 8;
+        const __nv_bfloat16* wb = p.W + (size_t)w_row(n0, 1) * p.K + k_begin + tg * 8;
         const __nv_bfloat16* xr[NB];
 #pragma unroll
         for (int j = 0; j < NB; ++j) xr[j] = p.X + (size_t)min(j * 8 + g, p.B - 1) * p.ldx + k_begin + tg * 8;
@@ -144,18 +254,26 @@ __global__ void __launch_bounds__(256, 2) skinny_gemm_kernel(const SkinnyParams 
 #pragma unroll
         for (int j = 0; j < NB; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
 
-        // UN k-steps per round: all 16-byte fragment loads of the round are issued before the first mma,
-        // so one round costs one memory round trip (K = 1280 -> a single round per warp).
-        constexpr int UN = 5;
         for (int s0 = 0; s0 < steps; s0 += UN) {
             uint4 alo[UN], ahi[UN], xb[UN][NB];
 #pragma unroll
             for (int u = 0; u < UN; ++u) {
                 if (s0 + u < steps) {
-                    alo[u] = ldg_stream(wa + (s0 + u) * 32);
-                    ahi[u] = ldg_stream(wb + (s0 + u) * 32);
+                    if (EPI == EPI_LOGITS && can_prefetch) { alo[u] = nlo[u % (EPI == EPI_LOGITS ? UN : 1)]; ahi[u] = nhi[u % (EPI == EPI_LOGITS ? UN : 1)]; }
+                    else { alo[u] = ldg_stream(wa + (s0 + u) * 32); ahi[u] = ldg_stream(wb + (s0 + u) * 32); }
 #pragma unroll
                     for (int j = 0; j < NB; ++j) xb[u][j] = __ldg(reinterpret_cast<const uint4*>(xr[j] + (s0 + u) * 32));
+                }
+            }
+            if (EPI == EPI_LOGITS && can_prefetch && sl + 1 < p.slabs_per_cta) {
+                const int n0n = n0 + 16;
+                if (n0n < p.N) {
+#pragma unroll
+                    for (int u = 0; u < (EPI == EPI_LOGITS ? UN : 1); ++u)
+                        if (u < steps) {
+                            nlo[u] = ldg_stream(p.W + (size_t)w_row(n0n, 0) * p.K + k_begin + tg * 8 + u * 32);
+                            nhi[u] = ldg_stream(p.W + (size_t)w_row(n0n, 1) * p.K + k_begin + tg * 8 + u * 32);
+                        }
                 }
             }
 #pragma unroll
@@ -169,7 +287,7 @@ __global__ void __launch_bounds__(256, 2) skinny_gemm_kernel(const SkinnyParams 
                 }
             }
         }
-        __syncthreads();  // previous slab's reduction buffer fully consumed
+        __syncthreads();  // previous slab's reduction buffers fully consumed
 #pragma unroll
         for (int j = 0; j < NB; ++j) {
             red[warp][j * 8 + 2 * tg][g] = acc[j][0];
@@ -179,71 +297,112 @@ __global__ void __launch_bounds__(256, 2) skinny_gemm_kernel(const SkinnyParams 
         }
         __syncthreads();
 
-        if (EPI != EPI_LOGITS) {
-            for (int o = threadIdx.x; o < NB * 8 * 16; o += 256) {
-                const int bb = o >> 4, rr = o & 15;
-                const int n = n0 + rr;
-                if (bb >= p.B || n >= p.N) continue;
-                float v = 0.f;
+        for (int o = threadIdx.x; o < NB * 8 * 16; o += NT) {
+            const int bb = o >> 4, rr = o & 15;
+            const int n = n0 + rr;
+            float v = 0.f;
 #pragma unroll
-                for (int w = 0; w < 8; ++w) v += red[w][bb][rr];
-                if (p.bias) v += p.bias[n];
-                if (EPI == EPI_BF16) {
-                    p.out_bf16[(size_t)bb * p.ldo + n] = __float2bfloat16(v);
-                } else if (EPI == EPI_GELU_BF16) {
-                    p.out_bf16[(size_t)bb * p.ldo + n] = __float2bfloat16(gelu_erf(v));
-                } else if (EPI == EPI_RESID) {
-                    p.resid[(size_t)bb * p.N + n] += v;
-                } else if (EPI == EPI_QKV) {
-                    const int which = n / p.D, c = n - which * p.D;
-                    if (which == 0) {
-                        p.q_out[(size_t)bb * p.D + c] = __float2bfloat16(v);
-                    } else {
-                        const int pos = p.st[bb].pos;
-                        const int page = p.block_table[bb * p.pages_per_row + pos / PAGE];
-                        __nv_bfloat16* dst = p.kv_pool + ((size_t)(which - 1) * p.n_pages + page) * PAGE * p.D +
-                                             (size_t)(pos % PAGE) * p.D + c;
-                        *dst = __float2bfloat16(v);
-                    }
+            for (int w = 0; w < WARPS; ++w) v += red[w][bb][rr];
+            if (EPI == EPI_LOGITS) {
+                tile[bb][rr] = v;
+                if (p.logits_out && bb < p.B && n < p.N) p.logits_out[(size_t)bb * p.N + n] = v;
+                continue;
+            }
+            if (bb >= p.B || n >= p.N) continue;
+            if (p.bias) v += p.bias[n];
+            if (EPI == EPI_BF16) {
+                p.out_bf16[(size_t)bb * p.ldo + n] = __float2bfloat16(v);
+            } else if (EPI == EPI_GELU_BF16) {
+                p.out_bf16[(size_t)bb * p.ldo + n] = __float2bfloat16(gelu_erf(v));
+            } else if (EPI == EPI_RESID) {
+                p.resid[(size_t)bb * p.N + n] += v;
+            } else if (EPI == EPI_QKV) {
+                const int which = n / p.D, c = n - which * p.D;
+                if (which == 0) {
+                    p.q_out[(size_t)bb * p.D + c] = __float2bfloat16(v);
+                } else {
+                    const int pos = p.st[bb].pos;
+                    const int page = p.block_table[bb * p.pages_per_row + pos / PAGE];
+                    __nv_bfloat16* dst = p.kv_pool + ((size_t)(which - 1) * p.n_pages + page) * PAGE * p.D +
+                                         (size_t)(pos % PAGE) * p.D + c;
+                    *dst = __float2bfloat16(v);
                 }
             }
-        } else {
-            // 16 vocab rows x B batch rows of logits for this slab
-            if (threadIdx.x < p.B) {
-                const int bb = threadIdx.x;
-                const RowState s = p.st[bb];
-#pragma unroll 4
-                for (int rr = 0; rr < 16; ++rr) {
-                    const int n = n0 + rr;
-                    if (n >= p.N) break;
-                    float v = 0.f;
+        }
+        if (EPI == EPI_LOGITS) {
+            __syncthreads();
+            // 16 lanes per batch row: grammar mask, then segmented (half-warp) max / arg-max / sum-exp
+            for (int o = threadIdx.x; o < NB * 8 * 16; o += NT) {  // NB*128 is a multiple of 32: warp-uniform
+                const int bb = o >> 4, rr = o & 15;
+                const int n = n0 + rr;
+                const bool row_ok = bb < p.B;
+                float vt = -INFINITY, vs = -INFINITY;
+                int it = 0x7fffffff, is = 0x7fffffff;
+                if (row_ok && n < p.N) {
+                    const RowState st = p.st[bb];
+                    if (token_allowed(n, st, p.gc, p.suppress_bits, p.begin_suppress_bits)) {
+                        const float v = tile[bb][rr];
+                        if (n >= p.gc.ts_begin && st.mode == 0) { vs = v; is = n; }
+                        else { vt = v; it = n; }
+                    }
+                }
+                float mt = vt, ms = vs;
+                int jt = it, js = is;
 #pragma unroll
-                    for (int w = 0; w < 8; ++w) v += red[w][bb][rr];
-                    if (p.logits_out) p.logits_out[(size_t)bb * p.N + n] = v;
-                    if (!token_allowed(n, s, p.gc, p.suppress_bits, p.begin_suppress_bits)) continue;
-                    if (n >= p.gc.ts_begin && s.mode == 0) {
-                        if (v > best_ts) {
-                            sum_ts = sum_ts * __expf(best_ts - v) + 1.0f;
-                            best_ts = v;
-                            idx_ts = n;
+                for (int d = 1; d < 16; d <<= 1) {
+                    const float ot = __shfl_xor_sync(0xffffffffu, mt, d);
+                    const int oi = __shfl_xor_sync(0xffffffffu, jt, d);
+                    if (ot > mt || (ot == mt && oi < jt)) { mt = ot; jt = oi; }
+                    const float os = __shfl_xor_sync(0xffffffffu, ms, d);
+                    const int oj = __shfl_xor_sync(0xffffffffu, js, d);
+                    if (os > ms || (os == ms && oj < js)) { ms = os; js = oj; }
+                }
+                float e = (vs > -INFINITY) ? __expf(vs - ms) : 0.f;
+#pragma unroll
+                for (int d = 1; d < 16; d <<= 1) e += __shfl_xor_sync(0xffffffffu, e, d);
+                if (rr == 0 && row_ok) {
+                    if (mt > s_bt[bb] || (mt == s_bt[bb] && jt < s_it[bb])) { s_bt[bb] = mt; s_it[bb] = jt; }
+                    if (ms > -INFINITY) {
+                        const float cur = s_bs[bb];
+                        if (ms > cur) {
+                            s_sum[bb] = (cur > -INFINITY ? s_sum[bb] * __expf(cur - ms) : 0.f) + e;
+                            s_bs[bb] = ms;
+                            s_is[bb] = js;
                         } else {
-                            sum_ts += __expf(v - best_ts);
+                            s_sum[bb] += e * __expf(ms - cur);
+                            if (ms == cur && js < s_is[bb]) s_is[bb] = js;
                         }
-                    } else if (v > best_text) {
-                        best_text = v;
-                        idx_text = n;
                     }
                 }
             }
         }
     }
-    if (EPI == EPI_LOGITS && threadIdx.x < p.B) {
-        const size_t o = (size_t)threadIdx.x * gridDim.x + blockIdx.x;
-        p.part_val[o * 3 + 0] = best_text;
-        p.part_val[o * 3 + 1] = best_ts;
-        p.part_val[o * 3 + 2] = sum_ts;
-        p.part_idx[o * 2 + 0] = idx_text;
-        p.part_idx[o * 2 + 1] = idx_ts;
+    if (EPI == EPI_RESID && p.ln_out) {
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned int prev = atomicAdd(p.ln_counter, 1u);
+            s_last = (prev == gridDim.x - 1);
+            if (s_last) *p.ln_counter = 0;  // re-arm for the next launch
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            for (int r = warp; r < p.B; r += WARPS)
+                warp_layernorm_row<true>(p.resid + (size_t)r * p.N, p.ln_g, p.ln_b, p.ln_out + (size_t)r * p.N, p.N, lane);
+        }
+    }
+    if (EPI == EPI_LOGITS) {
+        __syncthreads();
+        if (threadIdx.x < p.B) {
+            const int bb = threadIdx.x;
+            const size_t o = (size_t)bb * gridDim.x + blockIdx.x;
+            p.part_val[o * 3 + 0] = s_bt[bb];
+            p.part_val[o * 3 + 1] = s_bs[bb];
+            p.part_val[o * 3 + 2] = s_sum[bb];
+            p.part_idx[o * 2 + 0] = s_it[bb];
+            p.part_idx[o * 2 + 1] = s_is[bb];
+        }
     }
 }
 
@@ -368,11 +527,11 @@ struct AttnParams {
     const int* block_table;
     int pages_per_row, n_pages;
     const RowState* st;
-    // cross: K at ck + (b*S + j)*ld, V at cv + (b*S + j)*ld
+    // cross: K row j of (row b, head h) at ck + b*batch_stride + h*head_stride + j*row_stride (elements)
     const __nv_bfloat16* ck;
     const __nv_bfloat16* cv;
     const int* enc_row;       // [B] row of the encoder batch this decode row reads (or null = b)
-    long long ld;
+    long long row_stride, batch_stride, head_stride;
     int S, splits;
     float* part;              // [B][H][splits][66]
     unsigned int* counters;   // [B][H]
@@ -413,7 +572,7 @@ __global__ void __launch_bounds__(ATT_THREADS) decode_attn_kernel(const AttnPara
     auto row_ptr = [&](int j, int kv) -> const uint4* {
         const __nv_bfloat16* r;
         if (p.is_cross) {
-            r = (kv ? p.cv : p.ck) + ((size_t)eb * p.S + j) * p.ld + h * 64;
+            r = (kv ? p.cv : p.ck) + (size_t)eb * p.batch_stride + (size_t)h * p.head_stride + (size_t)j * p.row_stride;
         } else {
             const int page = p.block_table[b * p.pages_per_row + j / PAGE];
             r = p.kv_pool + ((size_t)kv * p.n_pages + page) * PAGE * p.D + (size_t)(j % PAGE) * p.D + h * 64;
@@ -526,28 +685,38 @@ using namespace tw::dec;
 
 static_assert(sizeof(RowState) == 32, "RowState layout is part of the ABI (8 x int32)");
 
-template <int EPI>
-static int launch_skinny(const SkinnyParams& p, cudaStream_t st) {
-    const int slabs = (p.N + 15) / 16;
-    const int grid = (slabs + p.slabs_per_cta - 1) / p.slabs_per_cta;
-    const int nb = (p.B + 7) / 8;
-    switch (nb) {
-        case 1: skinny_gemm_kernel<1, EPI><<<grid, 256, 0, st>>>(p); break;
-        case 2: skinny_gemm_kernel<2, EPI><<<grid, 256, 0, st>>>(p); break;
-        case 3: skinny_gemm_kernel<3, EPI><<<grid, 256, 0, st>>>(p); break;
-        case 4: skinny_gemm_kernel<4, EPI><<<grid, 256, 0, st>>>(p); break;
+template <int EPI, int WARPS>
+static int launch_nb(const SkinnyParams& p, int grid, cudaStream_t st) {
+    switch ((p.B + 7) / 8) {
+        case 1: skinny_gemm_kernel<1, EPI, WARPS><<<grid, WARPS * 32, 0, st>>>(p); break;
+        case 2: skinny_gemm_kernel<2, EPI, WARPS><<<grid, WARPS * 32, 0, st>>>(p); break;
+        case 3: skinny_gemm_kernel<3, EPI, WARPS><<<grid, WARPS * 32, 0, st>>>(p); break;
+        case 4: skinny_gemm_kernel<4, EPI, WARPS><<<grid, WARPS * 32, 0, st>>>(p); break;
         default: set_error("skinny gemm: batch %d > %d", p.B, MAXB); return 2;
     }
     TW_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
 
+// the 16-warp K split is used for the long-K residual projection (fc2)
+template <int EPI>
+static int launch_skinny(const SkinnyParams& p, cudaStream_t st) {
+    const int slabs = (p.N + 15) / 16;
+    const int grid = (slabs + p.slabs_per_cta - 1) / p.slabs_per_cta;
+    if (EPI == EPI_RESID && p.K >= 4096 && p.K % 512 == 0) return launch_nb<EPI_RESID, 16>(p, grid, st);
+    return launch_nb<EPI, 8>(p, grid, st);
+}
+
 extern "C" int tw_dec_embed(const int32_t* tokens, int32_t tokens_ld, const void* row_state, const void* tok_emb_bf16,
-                            const float* pos_emb, float* x, int32_t batch, int32_t d_model, void* stream) {
+                            const float* pos_emb, float* x, int32_t batch, int32_t d_model, const float* ln_gamma,
+                            const float* ln_beta, void* ln_out_bf16, void* stream) {
     TW_REQUIRE(tokens && row_state && tok_emb_bf16 && pos_emb && x, "tw_dec_embed: null argument");
+    TW_REQUIRE(d_model <= 2048, "tw_dec_embed: d_model %d > 2048", d_model);
+    TW_REQUIRE(!ln_out_bf16 || (ln_gamma && ln_beta), "tw_dec_embed: LayerNorm output needs gamma and beta");
     if (batch <= 0) return 0;
     decode_embed_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(tokens, tokens_ld, (const RowState*)row_state,
-                                                                (const __nv_bfloat16*)tok_emb_bf16, pos_emb, x, d_model);
+                                                                (const __nv_bfloat16*)tok_emb_bf16, pos_emb, x, d_model,
+                                                                ln_gamma, ln_beta, (__nv_bfloat16*)ln_out_bf16);
     TW_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -580,7 +749,15 @@ extern "C" int tw_dec_linear(const tw_skinny_args* a, int32_t epilogue, void* ou
     fill_common(p, a);
     if (epilogue == 0) { p.out_bf16 = (__nv_bfloat16*)out; p.ldo = ldo; return launch_skinny<EPI_BF16>(p, (cudaStream_t)stream); }
     if (epilogue == 3) { p.out_bf16 = (__nv_bfloat16*)out; p.ldo = ldo; return launch_skinny<EPI_GELU_BF16>(p, (cudaStream_t)stream); }
-    if (epilogue == 2) { p.resid = (float*)out; return launch_skinny<EPI_RESID>(p, (cudaStream_t)stream); }
+    if (epilogue == 2) {
+        p.resid = (float*)out;
+        if (a->ln_out_bf16) {
+            TW_REQUIRE(a->ln_gamma && a->ln_beta && a->ln_counter, "tw_dec_linear: fused LayerNorm needs gamma, beta, counter");
+            TW_REQUIRE(a->n <= 1280 && a->n % 128 == 0, "tw_dec_linear: fused LayerNorm supports n <= 1280, n %% 128 == 0");
+            p.ln_g = a->ln_gamma; p.ln_b = a->ln_beta; p.ln_out = (__nv_bfloat16*)a->ln_out_bf16; p.ln_counter = a->ln_counter;
+        }
+        return launch_skinny<EPI_RESID>(p, (cudaStream_t)stream);
+    }
     set_error("tw_dec_linear: unknown epilogue %d", epilogue);
     return 2;
 }
@@ -660,17 +837,20 @@ extern "C" int tw_dec_self_attn(const void* q_bf16, void* out_bf16, const void* 
 }
 
 extern "C" int tw_dec_cross_attn(const void* q_bf16, void* out_bf16, const void* k_bf16, const void* v_bf16,
-                                 int64_t kv_ld, const int32_t* enc_row, int32_t src_len, int32_t batch, int32_t heads,
+                                 int64_t kv_row_stride, int64_t kv_batch_stride, int64_t kv_head_stride,
+                                 const int32_t* enc_row, int32_t src_len, int32_t batch, int32_t heads,
                                  int32_t splits, float* part, uint32_t* counters, void* stream) {
     TW_REQUIRE(q_bf16 && out_bf16 && k_bf16 && v_bf16, "tw_dec_cross_attn: null argument");
     TW_REQUIRE(splits >= 1 && (src_len + splits - 1) / splits <= ATT_MAXKEYS,
                "tw_dec_cross_attn: %d keys / %d splits exceeds %d per CTA", src_len, splits, ATT_MAXKEYS);
     TW_REQUIRE(splits == 1 || (part && counters), "tw_dec_cross_attn: split needs scratch");
-    TW_REQUIRE(kv_ld % 8 == 0, "tw_dec_cross_attn: kv_ld alignment");
+    TW_REQUIRE(kv_row_stride % 8 == 0 && kv_batch_stride % 8 == 0 && kv_head_stride % 8 == 0,
+               "tw_dec_cross_attn: K/V strides must be multiples of 8 elements");
     if (batch <= 0) return 0;
     AttnParams p{};
     p.q = (const __nv_bfloat16*)q_bf16; p.out = (__nv_bfloat16*)out_bf16; p.D = heads * 64; p.H = heads;
-    p.is_cross = 1; p.ck = (const __nv_bfloat16*)k_bf16; p.cv = (const __nv_bfloat16*)v_bf16; p.ld = kv_ld;
+    p.is_cross = 1; p.ck = (const __nv_bfloat16*)k_bf16; p.cv = (const __nv_bfloat16*)v_bf16;
+    p.row_stride = kv_row_stride; p.batch_stride = kv_batch_stride; p.head_stride = kv_head_stride;
     p.enc_row = enc_row; p.S = src_len; p.splits = splits; p.part = part; p.counters = counters;
     decode_attn_kernel<<<dim3(splits, heads, batch), ATT_THREADS, 0, (cudaStream_t)stream>>>(p);
     TW_CUDA_CHECK(cudaGetLastError());

@@ -42,6 +42,7 @@ struct Params {
     long long out_ld, out_batch_rows;
     int out_row_off;
     int act;
+    int out_mode;  // 0: row-major [.., out_ld]; 1: head-major [N/64][batches][rows][64]
 };
 
 struct TileCoord {
@@ -189,7 +190,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     const int r0 = row_base + rgrp;  // this lane's rows are r0 + 4*i
                     const float* rp = nullptr;
                     if (HAS_RESID) rp = p.resid + ((size_t)t.b * p.resid_batch_rows + r0) * p.resid_ld + n;
-                    const size_t o0 = ((size_t)t.b * p.out_batch_rows + p.out_row_off + r0) * p.out_ld + n;
+                    size_t o0 = ((size_t)t.b * p.out_batch_rows + p.out_row_off + r0) * p.out_ld + n;
+                    size_t out_ld = (size_t)p.out_ld;
+                    if (p.out_mode == 1) {  // element (b, r, n) -> [n / 64][b][r][n % 64]
+                        o0 = (((size_t)(n >> 6) * p.batches + t.b) * p.rows + r0) * 64 + (n & 63);
+                        out_ld = 64;
+                    }
                     float* of = reinterpret_cast<float*>(p.out) + o0;
                     __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(p.out) + o0;
                     const int nrows = p.rows - r0;  // rows r0 + 4*i with 4*i < nrows are valid
@@ -215,12 +221,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         if (HAS_RESID) { f.x += res[i].x; f.y += res[i].y; f.z += res[i].z; f.w += res[i].w; }
                         if (4 * i < nrows) {
                             if (OUT_F32) {
-                                *reinterpret_cast<float4*>(of + (size_t)(4 * i) * p.out_ld) = f;
+                                *reinterpret_cast<float4*>(of + (size_t)(4 * i) * out_ld) = f;
                             } else {
                                 uint2 pk;
                                 pk.x = pack_bf16x2(f.x, f.y);
                                 pk.y = pack_bf16x2(f.z, f.w);
-                                *reinterpret_cast<uint2*>(ob + (size_t)(4 * i) * p.out_ld) = pk;
+                                *reinterpret_cast<uint2*>(ob + (size_t)(4 * i) * out_ld) = pk;
                             }
                         }
                     }
@@ -261,6 +267,8 @@ extern "C" int tw_gemm_bf16(const tw_gemm_args* a, void* stream) {
     TW_REQUIRE(!a->resid || (a->resid_ld % 4 == 0 && ((uintptr_t)a->resid & 15) == 0),
                "tw_gemm_bf16: resid must be 16-byte aligned with ld %% 4 == 0");
     TW_REQUIRE(a->act == 0 || a->act == 1, "tw_gemm_bf16: unknown activation %d", a->act);
+    TW_REQUIRE(a->out_mode == 0 || (a->out_mode == 1 && a->n % 64 == 0 && a->out_row_off == 0),
+               "tw_gemm_bf16: out_mode %d needs N %% 64 == 0 and out_row_off == 0", a->out_mode);
     if (a->batches == 0 || a->rows == 0) return 0;
 
     CUtensorMap tmA, tmB;
@@ -304,6 +312,7 @@ extern "C" int tw_gemm_bf16(const tw_gemm_args* a, void* stream) {
     p.out_batch_rows = a->out_batch_rows;
     p.out_row_off = a->out_row_off;
     p.act = a->act;
+    p.out_mode = a->out_mode;
 
     const int sms = num_sms();
     TW_REQUIRE(sms > 0, "tw_gemm_bf16: no CUDA device");

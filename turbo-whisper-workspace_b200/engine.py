@@ -194,6 +194,7 @@ class WhisperEngine:
             self.part_idx = z(Bm, self.n_parts, 2, dtype=i32)
             self.cross_part = z(Bm, dims.heads, cross_splits, 66, dtype=f32)
             self.cross_cnt = z(Bm, dims.heads, dtype=i32)
+            self.ln_cnt = z(1, dtype=i32)
             self.logits = None   # optional [Bm, vocab] fp32 raw-logit tap for parity tests
             self.choices = None  # optional [Bm, max_len] int32 tap of the un-forced picks
             self.sup_bits = torch.from_numpy(_bitmap(self.gen.suppress_tokens, dims.vocab).view(np.int32)).to(dev)
@@ -205,7 +206,8 @@ class WhisperEngine:
         g.max_initial_ts = self.gen.max_initial_timestamp_index
         g.begin_index = 3
         self.grammar = g
-        self._graphs: Dict[int, torch.cuda.CUDAGraph] = {}
+        self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
+        self._ckv_batch = max_batch
         self.use_graphs = True
         self.finish_check_every = 16
         self.stats = {"enc_windows": 0, "dec_steps": 0, "launches": 0, "h2d_bytes": 0, "d2h_bytes": 0}
@@ -282,18 +284,27 @@ class WhisperEngine:
                 if taps is not None and i in taps.get("layers", ()):
                     taps[f"layer{i}"] = x.clone()
             ops.layernorm(x, w["enc_ln_w"], w["enc_ln_b"], out=xn)
-            ops.gemm(xn, w["ckv_w"], rows=M, bias=w["ckv_b"], out=self.ckv[:M])
+            # cross-attention K/V of every decoder layer in one GEMM, stored head-major
+            # [(layer, k|v, head)][window][position][64] so decode streams contiguous blocks
+            ops.gemm(xn, w["ckv_w"], rows=S, batches=B, a_row_stride=D, a_batch_stride=S * D, a_rows=S,
+                     bias=w["ckv_b"], out=self.ckv, out_mode=1)
+            self._ckv_batch = B
         self.stats["enc_windows"] += B
         self.stats["launches"] += 2 + 7 * d.enc_layers + 2
         return xn
 
     # ------------------------------------------------------------------------------------ decoder
-    def _skinny(self, wname, x, bias, B, k):
+    def _skinny(self, wname, x, bias, B, k, ln=None):
+        """tw_skinny_args for W = self.w[wname].  For residual projections ``ln="dec0.ln2"`` makes the kernel's
+        last CTA write LayerNorm(updated x) into self.dxn (no separate LayerNorm launch)."""
         a = SkinnyArgs()
         wt = self.w[wname]
         a.w, a.x, a.ldx = wt.data_ptr(), x.data_ptr(), x.stride(0)
         a.bias = None if bias is None else self.w[bias].data_ptr()
         a.batch, a.n, a.k = B, wt.shape[0], k
+        if ln is not None:
+            a.ln_gamma, a.ln_beta = self.w[ln + "_w"].data_ptr(), self.w[ln + "_b"].data_ptr()
+            a.ln_out_bf16, a.ln_counter = self.dxn.data_ptr(), self.ln_cnt.data_ptr()
         return a
 
     def _decode_step(self, B: int) -> None:
@@ -303,35 +314,33 @@ class WhisperEngine:
         p = lambda t: C.c_void_p(t.data_ptr())
         S = d.max_source_positions
         check(lib.tw_dec_embed(p(self.tokens), self.max_len, p(self.state), p(w["tok_emb"]), p(w["dec_pos"]), p(self.dx),
-                               B, D, st), "tw_dec_embed")
-        kv_ld = L * 2 * D
+                               B, D, p(w["dec0.ln1_w"]), p(w["dec0.ln1_b"]), p(self.dxn), st), "tw_dec_embed")
+        Bc = self._ckv_batch                 # windows in the encoder batch that produced self.ckv
+        blk = Bc * S * 64                    # elements per (layer, k|v, head) block of the head-major K/V
         for i in range(L):
             q = f"dec{i}."
+            nxt = f"dec{i + 1}.ln1" if i + 1 < L else "dec_ln"   # LayerNorm that follows this layer's fc2
             pool = C.c_void_p(self.kv_pool[i].data_ptr())
-            check(lib.tw_layernorm(p(self.dx), p(w[q + "ln1_w"]), p(w[q + "ln1_b"]), p(self.dxn), B, D, 1e-5, st), "ln1")
             check(lib.tw_dec_qkv(C.byref(self._skinny(q + "qkv_w", self.dxn, q + "qkv_b", B, D)), p(self.dq), pool,
                                  p(self.block_table), self.pages_per_row, self.n_pages, p(self.state), st), "tw_dec_qkv")
             check(lib.tw_dec_self_attn(p(self.dq), p(self.datt), pool, p(self.block_table), self.pages_per_row,
                                        self.n_pages, p(self.state), B, H, st), "tw_dec_self_attn")
-            check(lib.tw_dec_linear(C.byref(self._skinny(q + "out_w", self.datt, q + "out_b", B, D)), 2, p(self.dx), D, st),
-                  "self out_proj")
-            check(lib.tw_layernorm(p(self.dx), p(w[q + "ln2_w"]), p(w[q + "ln2_b"]), p(self.dxn), B, D, 1e-5, st), "ln2")
+            check(lib.tw_dec_linear(C.byref(self._skinny(q + "out_w", self.datt, q + "out_b", B, D, ln=q + "ln2")), 2,
+                                    p(self.dx), D, st), "self out_proj")
             check(lib.tw_dec_linear(C.byref(self._skinny(q + "cq_w", self.dxn, q + "cq_b", B, D)), 0, p(self.dq), D, st),
                   "cross q_proj")
-            kptr = C.c_void_p(self.ckv.data_ptr() + (i * 2 * D) * 2)
-            vptr = C.c_void_p(self.ckv.data_ptr() + (i * 2 * D + D) * 2)
-            check(lib.tw_dec_cross_attn(p(self.dq), p(self.datt), kptr, vptr, kv_ld, None, S, B, H, self.cross_splits,
-                                        p(self.cross_part), p(self.cross_cnt), st), "tw_dec_cross_attn")
-            check(lib.tw_dec_linear(C.byref(self._skinny(q + "cout_w", self.datt, q + "cout_b", B, D)), 2, p(self.dx), D, st),
-                  "cross out_proj")
-            check(lib.tw_layernorm(p(self.dx), p(w[q + "ln3_w"]), p(w[q + "ln3_b"]), p(self.dxn), B, D, 1e-5, st), "ln3")
+            kptr = C.c_void_p(self.ckv.data_ptr() + ((i * 2 + 0) * H) * blk * 2)
+            vptr = C.c_void_p(self.ckv.data_ptr() + ((i * 2 + 1) * H) * blk * 2)
+            check(lib.tw_dec_cross_attn(p(self.dq), p(self.datt), kptr, vptr, 64, S * 64, blk, None, S, B, H,
+                                        self.cross_splits, p(self.cross_part), p(self.cross_cnt), st), "tw_dec_cross_attn")
+            check(lib.tw_dec_linear(C.byref(self._skinny(q + "cout_w", self.datt, q + "cout_b", B, D, ln=q + "ln3")), 2,
+                                    p(self.dx), D, st), "cross out_proj")
             check(lib.tw_dec_linear(C.byref(self._skinny(q + "fc1_w", self.dxn, q + "fc1_b", B, D)), 3, p(self.dhid), F, st),
                   "fc1")
-            check(lib.tw_dec_linear(C.byref(self._skinny(q + "fc2_w", self.dhid, q + "fc2_b", B, F)), 2, p(self.dx), D, st),
-                  "fc2")
-        check(lib.tw_layernorm(p(self.dx), p(w["dec_ln_w"]), p(w["dec_ln_b"]), p(self.dxn), B, D, 1e-5, st), "dec_ln")
-        check(lib.tw_dec_lmhead(C.byref(self._skinny("tok_emb", self.dxn, None, B, D)), C.byref(self.grammar), p(self.state),
-                                p(self.sup_bits), p(self.bsup_bits), p(self.part_val), p(self.part_idx),
+            check(lib.tw_dec_linear(C.byref(self._skinny(q + "fc2_w", self.dhid, q + "fc2_b", B, F, ln=nxt)), 2,
+                                    p(self.dx), D, st), "fc2")
+        check(lib.tw_dec_lmhead(C.byref(self._skinny("tok_emb", self.dxn, None, B, D)), C.byref(self.grammar),
+                                p(self.state), p(self.sup_bits), p(self.bsup_bits), p(self.part_val), p(self.part_idx),
                                 None if self.logits is None else p(self.logits), st), "tw_dec_lmhead")
         check(lib.tw_dec_finalize(p(self.part_val), p(self.part_idx), self.n_parts, p(self.tokens), self.max_len,
                                   p(self.forced), None if self.choices is None else p(self.choices), p(self.state),
@@ -339,10 +348,11 @@ class WhisperEngine:
 
     @property
     def launches_per_step(self) -> int:
-        return 1 + 11 * self.dims.dec_layers + 3
+        return 1 + 8 * self.dims.dec_layers + 2
 
     def _graph_for(self, B: int) -> torch.cuda.CUDAGraph:
-        g = self._graphs.get(B)
+        key = (B, self._ckv_batch)   # the K/V block stride depends on the encoder batch
+        g = self._graphs.get(key)
         if g is None:
             # a warm-up step outside capture (sets kernel attributes); state is re-initialised afterwards
             state_backup = self.state.clone()
@@ -356,7 +366,7 @@ class WhisperEngine:
                 self._decode_step(B)
             self.state.copy_(state_backup)
             self.tokens.copy_(tokens_backup)
-            self._graphs[B] = g
+            self._graphs[key] = g
         return g
 
     def decode(self, B: int, prompts: Optional[torch.Tensor], n_steps: Optional[int] = None,

@@ -100,7 +100,7 @@ def layernorm(x, gamma, beta, out=None, eps: float = 1e-5):
 
 def gemm(a, w, *, rows, batches=1, a_row_stride=None, a_batch_stride=0, a_rows=None, a_row_off=None, bias=None,
          act=0, resid=None, resid_ld=0, resid_batch_rows=0, out=None, out_ld=None, out_batch_rows=0,
-         out_row_off=0, k=None):
+         out_row_off=0, k=None, out_mode=0):
     """K5 GEMM (see include/twb200.h tw_gemm_args).  `a` is any bf16 cuda tensor used as a flat base;
     `w` is bf16 [N, K]."""
     lib = _lib.load()
@@ -123,6 +123,7 @@ def gemm(a, w, *, rows, batches=1, a_row_stride=None, a_batch_stride=0, a_rows=N
     args.out_f32 = 1 if out.dtype == torch.float32 else 0
     args.out_ld = N if out_ld is None else out_ld
     args.out_batch_rows, args.out_row_off = out_batch_rows, out_row_off
+    args.out_mode = out_mode
     with torch.cuda.device(a.device):
         check(lib.tw_gemm_bf16(C.byref(args), _stream()), "tw_gemm_bf16")
     return out

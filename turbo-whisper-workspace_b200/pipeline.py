@@ -148,14 +148,19 @@ class B200WhisperPipeline:
     """Callable with the HF ASR-pipeline signature, backed by one :class:`WhisperEngine` per GPU."""
 
     def __init__(self, state_dict, dims: WhisperDims, tokenizer, generation: Optional[GenerationSettings] = None,
-                 devices: Sequence[Union[str, int]] = ("cuda:0",), max_batch: int = 24, time_precision: float = 0.02):
-        from .scheduler import WindowScheduler
+                 devices: Sequence[Union[str, int]] = ("cuda:0",), max_batch: int = 24, time_precision: float = 0.02,
+                 scheduler=None):
+        """``scheduler``: any object with ``run(clips, task=, language=) -> token rows`` and ``last_stats``;
+        defaults to a :class:`WindowScheduler` with one GPU engine per entry of ``devices``."""
         self.dims = dims
         self.tokenizer = tokenizer
         self.generation = generation or GenerationSettings()
         self.sampling_rate = SAMPLING_RATE
         self.time_precision = time_precision  # chunk_length 30 s / max_source_positions 1500
-        self.scheduler = WindowScheduler(state_dict, dims, self.generation, devices, max_batch)
+        if scheduler is None:
+            from .scheduler import WindowScheduler
+            scheduler = WindowScheduler(state_dict, dims, self.generation, devices, max_batch)
+        self.scheduler = scheduler
         self.last_stats: Dict[str, Any] = {}
 
     @classmethod
