@@ -151,6 +151,9 @@ typedef struct tw_grammar {
     int32_t eos, pad, no_timestamps, ts_begin, vocab, lang_first, lang_last, max_initial_ts, begin_index;
 } tw_grammar;
 
+/* Decode kernels are launched with programmatic dependent launch (each prefetches its weights before waiting for
+ * its predecessor); tw_set_pdl(0) falls back to plain stream ordering (debugging). */
+int tw_set_pdl(int32_t enabled);
 /* x[b,:] = tok_emb[tokens[b, pos_b], :] + pos_emb[pos_b, :]   (fp32 residual stream [batch, d_model]);
  * optionally also ln_out[b,:] = LayerNorm(x[b,:]; ln_gamma, ln_beta) as bf16 (first layer's self_attn_layer_norm). */
 int tw_dec_embed(const int32_t* tokens, int32_t tokens_ld, const void* row_state, const void* tok_emb_bf16,

@@ -52,7 +52,7 @@ def test_error_convention_without_gpu(lib):
     rc = lib.tw_gemm_bf16(None, None)
     assert rc != 0 and b"tw_gemm_bf16" in lib.tw_last_error()
     assert lib.tw_logmel_tables_bytes() > 0 and lib.tw_logmel_scratch_bytes(2) >= 2 * 128 * 3000 * 4
-    assert lib.tw_dec_lmhead_parts(51866) == 811
+    assert lib.tw_dec_lmhead_parts(51866) % 8 == 0
 
 
 def test_product_fails_loudly_without_cuda():

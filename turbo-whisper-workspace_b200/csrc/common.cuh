@@ -93,6 +93,12 @@ TW_DEVINL float gelu_erf_fast(float x) {
 // reference-accuracy variant (decoder path, where cost is irrelevant)
 TW_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
+// Programmatic dependent launch: a kernel lets its successor start early and does its own
+// dependency-free work (weight / encoder K,V prefetch, index math) before waiting for its predecessor.
+// Both instructions are no-ops when the kernel is launched without the PDL attribute.
+TW_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+TW_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------

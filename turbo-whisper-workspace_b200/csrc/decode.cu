@@ -59,6 +59,8 @@ __global__ void __launch_bounds__(256) decode_embed_kernel(const int* __restrict
                                                           const float* __restrict__ ln_b,
                                                           __nv_bfloat16* __restrict__ ln_out) {
     __shared__ float s_red[2][8];
+    pdl_launch_dependents();
+    pdl_wait();
     const int b = blockIdx.x;
     const int pos = st[b].pos;
     const int tok = tokens[b * tokens_ld + pos];
@@ -120,7 +122,6 @@ struct SkinnyParams {
     unsigned int* ln_counter;    // zero-initialised, self re-arming
     const float* bias;       // [N] or null
     int B, N, K;
-    int slabs_per_cta;
     // EPI_BF16 / EPI_GELU_BF16
     __nv_bfloat16* out_bf16;
     int ldo;
@@ -204,12 +205,9 @@ TW_DEVINL void warp_layernorm_row(const float* __restrict__ x, const float* __re
 }
 
 template <int NB, int EPI, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, (WARPS == 8 && EPI != EPI_LOGITS) ? 2 : 1) skinny_gemm_kernel(const SkinnyParams p) {
+__global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 2 : 1) skinny_gemm_kernel(const SkinnyParams p) {
     constexpr int NT = WARPS * 32;
     __shared__ float red[WARPS][NB * 8][17];
-    __shared__ float tile[NB * 8][17];                       // EPI_LOGITS: reduced logits of the slab
-    __shared__ float s_bt[NB * 8], s_bs[NB * 8], s_sum[NB * 8];  // EPI_LOGITS running partials per row
-    __shared__ int s_it[NB * 8], s_is[NB * 8];
     __shared__ int s_last;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -217,163 +215,81 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8 && EPI != EPI_LOGITS) 
     const int kw = p.K / WARPS;  // K per warp (multiple of 32)
     const int k_begin = warp * kw;
     const int steps = kw >> 5;
-
-    if (EPI == EPI_LOGITS) {
-        for (int i = threadIdx.x; i < NB * 8; i += NT) {
-            s_bt[i] = -INFINITY; s_bs[i] = -INFINITY; s_sum[i] = 0.f; s_it[i] = 0x7fffffff; s_is[i] = 0x7fffffff;
-        }
-    }
-
     constexpr int UN = 5;  // k-steps per round: their 16-byte fragment loads are all issued before the first mma
-    // weight fragments of the NEXT slab are prefetched while the current slab is reduced / post-processed
-    // (only when one round covers the warp's K range, i.e. steps <= UN: the LM head and every K = 1280 case)
-    const bool can_prefetch = (EPI == EPI_LOGITS) && steps <= UN;  // multi-slab CTAs only exist for the LM head
-    uint4 nlo[EPI == EPI_LOGITS ? UN : 1], nhi[EPI == EPI_LOGITS ? UN : 1];
-    auto w_row = [&](int n0v, int half) { return min(n0v + g + 8 * half, p.N - 1); };
-    if (EPI == EPI_LOGITS && can_prefetch) {
-        const int n0f = blockIdx.x * p.slabs_per_cta * 16;
-        if (n0f < p.N) {
+
+    const int n0 = blockIdx.x * 16;
+    const int ra = min(n0 + g, p.N - 1), rb = min(n0 + g + 8, p.N - 1);
+    const __nv_bfloat16* wa = p.W + (size_t)ra * p.K + k_begin + tg * 8;
+    const __nv_bfloat16* wb = p.W + (size_t)rb * p.K + k_begin + tg * 8;
+    const __nv_bfloat16* xr[NB];
 #pragma unroll
-            for (int u = 0; u < (EPI == EPI_LOGITS ? UN : 1); ++u)
-                if (u < steps) {
-                    nlo[u] = ldg_stream(p.W + (size_t)w_row(n0f, 0) * p.K + k_begin + tg * 8 + u * 32);
-                    nhi[u] = ldg_stream(p.W + (size_t)w_row(n0f, 1) * p.K + k_begin + tg * 8 + u * 32);
+    for (int j = 0; j < NB; ++j) xr[j] = p.X + (size_t)min(j * 8 + g, p.B - 1) * p.ldx + k_begin + tg * 8;
+    float acc[NB][4];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+
+    // the weights do not depend on the previous kernel: the first round of weight fragments is requested
+    // before the programmatic-dependency wait, so the stream overlaps the predecessor's tail
+    pdl_launch_dependents();
+    uint4 alo[UN], ahi[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u)
+        if (u < steps) { alo[u] = ldg_stream(wa + u * 32); ahi[u] = ldg_stream(wb + u * 32); }
+    pdl_wait();
+    for (int s0 = 0; s0 < steps; s0 += UN) {
+        uint4 xb[UN][NB];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            if (s0 + u < steps) {
+                if (s0 > 0) { alo[u] = ldg_stream(wa + (s0 + u) * 32); ahi[u] = ldg_stream(wb + (s0 + u) * 32); }
+#pragma unroll
+                for (int j = 0; j < NB; ++j) xb[u][j] = __ldg(reinterpret_cast<const uint4*>(xr[j] + (s0 + u) * 32));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            if (s0 + u < steps) {
+#pragma unroll
+                for (int j = 0; j < NB; ++j) {
+                    mma_bf16_16816(acc[j], alo[u].x, ahi[u].x, alo[u].y, ahi[u].y, xb[u][j].x, xb[u][j].y);
+                    mma_bf16_16816(acc[j], alo[u].z, ahi[u].z, alo[u].w, ahi[u].w, xb[u][j].z, xb[u][j].w);
                 }
+            }
         }
     }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+        red[warp][j * 8 + 2 * tg][g] = acc[j][0];
+        red[warp][j * 8 + 2 * tg + 1][g] = acc[j][1];
+        red[warp][j * 8 + 2 * tg][g + 8] = acc[j][2];
+        red[warp][j * 8 + 2 * tg + 1][g + 8] = acc[j][3];
+    }
+    __syncthreads();
 
-    for (int sl = 0; sl < p.slabs_per_cta; ++sl) {
-        const int n0 = (blockIdx.x * p.slabs_per_cta + sl) * 16;
-        if (n0 >= p.N) break;
-        const __nv_bfloat16* wa = p.W + (size_t)w_row(n0, 0) * p.K + k_begin + tg * 8;
-        const __nv_bfloat16* wb = p.W + (size_t)w_row(n0, 1) * p.K + k_begin + tg * 8;
-        const __nv_bfloat16* xr[NB];
+    for (int o = threadIdx.x; o < NB * 8 * 16; o += NT) {
+        const int bb = o >> 4, rr = o & 15;
+        const int n = n0 + rr;
+        if (bb >= p.B || n >= p.N) continue;
+        float v = 0.f;
 #pragma unroll
-        for (int j = 0; j < NB; ++j) xr[j] = p.X + (size_t)min(j * 8 + g, p.B - 1) * p.ldx + k_begin + tg * 8;
-        float acc[NB][4];
-#pragma unroll
-        for (int j = 0; j < NB; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-
-        for (int s0 = 0; s0 < steps; s0 += UN) {
-            uint4 alo[UN], ahi[UN], xb[UN][NB];
-#pragma unroll
-            for (int u = 0; u < UN; ++u) {
-                if (s0 + u < steps) {
-                    if (EPI == EPI_LOGITS && can_prefetch) { alo[u] = nlo[u % (EPI == EPI_LOGITS ? UN : 1)]; ahi[u] = nhi[u % (EPI == EPI_LOGITS ? UN : 1)]; }
-                    else { alo[u] = ldg_stream(wa + (s0 + u) * 32); ahi[u] = ldg_stream(wb + (s0 + u) * 32); }
-#pragma unroll
-                    for (int j = 0; j < NB; ++j) xb[u][j] = __ldg(reinterpret_cast<const uint4*>(xr[j] + (s0 + u) * 32));
-                }
-            }
-            if (EPI == EPI_LOGITS && can_prefetch && sl + 1 < p.slabs_per_cta) {
-                const int n0n = n0 + 16;
-                if (n0n < p.N) {
-#pragma unroll
-                    for (int u = 0; u < (EPI == EPI_LOGITS ? UN : 1); ++u)
-                        if (u < steps) {
-                            nlo[u] = ldg_stream(p.W + (size_t)w_row(n0n, 0) * p.K + k_begin + tg * 8 + u * 32);
-                            nhi[u] = ldg_stream(p.W + (size_t)w_row(n0n, 1) * p.K + k_begin + tg * 8 + u * 32);
-                        }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < UN; ++u) {
-                if (s0 + u < steps) {
-#pragma unroll
-                    for (int j = 0; j < NB; ++j) {
-                        mma_bf16_16816(acc[j], alo[u].x, ahi[u].x, alo[u].y, ahi[u].y, xb[u][j].x, xb[u][j].y);
-                        mma_bf16_16816(acc[j], alo[u].z, ahi[u].z, alo[u].w, ahi[u].w, xb[u][j].z, xb[u][j].w);
-                    }
-                }
-            }
-        }
-        __syncthreads();  // previous slab's reduction buffers fully consumed
-#pragma unroll
-        for (int j = 0; j < NB; ++j) {
-            red[warp][j * 8 + 2 * tg][g] = acc[j][0];
-            red[warp][j * 8 + 2 * tg + 1][g] = acc[j][1];
-            red[warp][j * 8 + 2 * tg][g + 8] = acc[j][2];
-            red[warp][j * 8 + 2 * tg + 1][g + 8] = acc[j][3];
-        }
-        __syncthreads();
-
-        for (int o = threadIdx.x; o < NB * 8 * 16; o += NT) {
-            const int bb = o >> 4, rr = o & 15;
-            const int n = n0 + rr;
-            float v = 0.f;
-#pragma unroll
-            for (int w = 0; w < WARPS; ++w) v += red[w][bb][rr];
-            if (EPI == EPI_LOGITS) {
-                tile[bb][rr] = v;
-                if (p.logits_out && bb < p.B && n < p.N) p.logits_out[(size_t)bb * p.N + n] = v;
-                continue;
-            }
-            if (bb >= p.B || n >= p.N) continue;
-            if (p.bias) v += p.bias[n];
-            if (EPI == EPI_BF16) {
-                p.out_bf16[(size_t)bb * p.ldo + n] = __float2bfloat16(v);
-            } else if (EPI == EPI_GELU_BF16) {
-                p.out_bf16[(size_t)bb * p.ldo + n] = __float2bfloat16(gelu_erf(v));
-            } else if (EPI == EPI_RESID) {
-                p.resid[(size_t)bb * p.N + n] += v;
-            } else if (EPI == EPI_QKV) {
-                const int which = n / p.D, c = n - which * p.D;
-                if (which == 0) {
-                    p.q_out[(size_t)bb * p.D + c] = __float2bfloat16(v);
-                } else {
-                    const int pos = p.st[bb].pos;
-                    const int page = p.block_table[bb * p.pages_per_row + pos / PAGE];
-                    __nv_bfloat16* dst = p.kv_pool + ((size_t)(which - 1) * p.n_pages + page) * PAGE * p.D +
-                                         (size_t)(pos % PAGE) * p.D + c;
-                    *dst = __float2bfloat16(v);
-                }
-            }
-        }
-        if (EPI == EPI_LOGITS) {
-            __syncthreads();
-            // 16 lanes per batch row: grammar mask, then segmented (half-warp) max / arg-max / sum-exp
-            for (int o = threadIdx.x; o < NB * 8 * 16; o += NT) {  // NB*128 is a multiple of 32: warp-uniform
-                const int bb = o >> 4, rr = o & 15;
-                const int n = n0 + rr;
-                const bool row_ok = bb < p.B;
-                float vt = -INFINITY, vs = -INFINITY;
-                int it = 0x7fffffff, is = 0x7fffffff;
-                if (row_ok && n < p.N) {
-                    const RowState st = p.st[bb];
-                    if (token_allowed(n, st, p.gc, p.suppress_bits, p.begin_suppress_bits)) {
-                        const float v = tile[bb][rr];
-                        if (n >= p.gc.ts_begin && st.mode == 0) { vs = v; is = n; }
-                        else { vt = v; it = n; }
-                    }
-                }
-                float mt = vt, ms = vs;
-                int jt = it, js = is;
-#pragma unroll
-                for (int d = 1; d < 16; d <<= 1) {
-                    const float ot = __shfl_xor_sync(0xffffffffu, mt, d);
-                    const int oi = __shfl_xor_sync(0xffffffffu, jt, d);
-                    if (ot > mt || (ot == mt && oi < jt)) { mt = ot; jt = oi; }
-                    const float os = __shfl_xor_sync(0xffffffffu, ms, d);
-                    const int oj = __shfl_xor_sync(0xffffffffu, js, d);
-                    if (os > ms || (os == ms && oj < js)) { ms = os; js = oj; }
-                }
-                float e = (vs > -INFINITY) ? __expf(vs - ms) : 0.f;
-#pragma unroll
-                for (int d = 1; d < 16; d <<= 1) e += __shfl_xor_sync(0xffffffffu, e, d);
-                if (rr == 0 && row_ok) {
-                    if (mt > s_bt[bb] || (mt == s_bt[bb] && jt < s_it[bb])) { s_bt[bb] = mt; s_it[bb] = jt; }
-                    if (ms > -INFINITY) {
-                        const float cur = s_bs[bb];
-                        if (ms > cur) {
-                            s_sum[bb] = (cur > -INFINITY ? s_sum[bb] * __expf(cur - ms) : 0.f) + e;
-                            s_bs[bb] = ms;
-                            s_is[bb] = js;
-                        } else {
-                            s_sum[bb] += e * __expf(ms - cur);
-                            if (ms == cur && js < s_is[bb]) s_is[bb] = js;
-                        }
-                    }
-                }
+        for (int w = 0; w < WARPS; ++w) v += red[w][bb][rr];
+        if (p.bias) v += p.bias[n];
+        if (EPI == EPI_BF16) {
+            p.out_bf16[(size_t)bb * p.ldo + n] = __float2bfloat16(v);
+        } else if (EPI == EPI_GELU_BF16) {
+            p.out_bf16[(size_t)bb * p.ldo + n] = __float2bfloat16(gelu_erf(v));
+        } else if (EPI == EPI_RESID) {
+            p.resid[(size_t)bb * p.N + n] += v;
+        } else if (EPI == EPI_QKV) {
+            const int which = n / p.D, c = n - which * p.D;
+            if (which == 0) {
+                p.q_out[(size_t)bb * p.D + c] = __float2bfloat16(v);
+            } else {
+                const int pos = p.st[bb].pos;
+                const int page = p.block_table[bb * p.pages_per_row + pos / PAGE];
+                __nv_bfloat16* dst = p.kv_pool + ((size_t)(which - 1) * p.n_pages + page) * PAGE * p.D +
+                                     (size_t)(pos % PAGE) * p.D + c;
+                *dst = __float2bfloat16(v);
             }
         }
     }
@@ -392,16 +308,148 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8 && EPI != EPI_LOGITS) 
                 warp_layernorm_row<true>(p.resid + (size_t)r * p.N, p.ln_g, p.ln_b, p.ln_out + (size_t)r * p.N, p.N, lane);
         }
     }
-    if (EPI == EPI_LOGITS) {
-        __syncthreads();
-        if (threadIdx.x < p.B) {
-            const int bb = threadIdx.x;
-            const size_t o = (size_t)bb * gridDim.x + blockIdx.x;
-            p.part_val[o * 3 + 0] = s_bt[bb];
-            p.part_val[o * 3 + 1] = s_bs[bb];
-            p.part_val[o * 3 + 2] = s_sum[bb];
-            p.part_idx[o * 2 + 0] = s_it[bb];
-            p.part_idx[o * 2 + 1] = s_is[bb];
+}
+
+// ------------------------------------------------------------------------------------------------
+// LM head: logits = x W^T over the tied embedding (51866 x 1280) + logits processors + partial arg-max /
+// log-sum-exp.  Persistent grid, one 16-row slab per WARP and the full K per warp: no block-level
+// synchronisation in the streaming loop, weight fragments double-buffered in registers (the next round of
+// 16-byte loads is in flight while the current round's mma run).  The mma accumulator layout already has
+// every (vocab row, batch row) logit in a known lane, so masks and reductions are warp shuffles.
+// ------------------------------------------------------------------------------------------------
+template <int NB>
+__global__ void __launch_bounds__(256, 1) lmhead_kernel(const SkinnyParams p) {
+    constexpr int UN = 4;  // k-steps (of 32) per round
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, tg = lane & 3;
+    const int gwarp = blockIdx.x * 8 + warp, nwarps = gridDim.x * 8;
+    const int n_slabs = (p.N + 15) >> 4;
+    const int rounds = p.K / (32 * UN);  // K % 128 == 0
+
+    pdl_launch_dependents();
+    uint4 alo[2][UN], ahi[2][UN];
+    if (gwarp < n_slabs) {  // first round of this warp's first slab: independent of the previous kernel
+        const __nv_bfloat16* wa0 = p.W + (size_t)min(gwarp * 16 + g, p.N - 1) * p.K + tg * 8;
+        const __nv_bfloat16* wb0 = p.W + (size_t)min(gwarp * 16 + g + 8, p.N - 1) * p.K + tg * 8;
+#pragma unroll
+        for (int u = 0; u < UN; ++u) { alo[0][u] = ldg_stream(wa0 + u * 32); ahi[0][u] = ldg_stream(wb0 + u * 32); }
+    }
+    pdl_wait();
+    // per-thread running partials for its 2*NB batch columns (j*8 + 2*tg + e)
+    float bt[NB * 2], bs[NB * 2], sm[NB * 2];
+    int it[NB * 2], is[NB * 2];
+    RowState st[NB * 2];
+#pragma unroll
+    for (int c = 0; c < NB * 2; ++c) {
+        bt[c] = -INFINITY; bs[c] = -INFINITY; sm[c] = 0.f; it[c] = 0x7fffffff; is[c] = 0x7fffffff;
+        const int bb = (c >> 1) * 8 + 2 * tg + (c & 1);
+        st[c] = p.st[min(bb, p.B - 1)];
+    }
+    const __nv_bfloat16* xr[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) xr[j] = p.X + (size_t)min(j * 8 + g, p.B - 1) * p.ldx + tg * 8;
+
+    for (int slab = gwarp; slab < n_slabs; slab += nwarps) {
+        const int n0 = slab * 16;
+        const __nv_bfloat16* wa = p.W + (size_t)min(n0 + g, p.N - 1) * p.K + tg * 8;
+        const __nv_bfloat16* wb = p.W + (size_t)min(n0 + g + 8, p.N - 1) * p.K + tg * 8;
+        float acc[NB][4];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+        if (slab != gwarp) {
+#pragma unroll
+            for (int u = 0; u < UN; ++u) { alo[0][u] = ldg_stream(wa + u * 32); ahi[0][u] = ldg_stream(wb + u * 32); }
+        }
+#pragma unroll 2
+        for (int r = 0; r < rounds; ++r) {
+            const int cur = r & 1;
+            if (r + 1 < rounds) {
+#pragma unroll
+                for (int u = 0; u < UN; ++u) {
+                    alo[cur ^ 1][u] = ldg_stream(wa + ((r + 1) * UN + u) * 32);
+                    ahi[cur ^ 1][u] = ldg_stream(wb + ((r + 1) * UN + u) * 32);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+#pragma unroll
+                for (int j = 0; j < NB; ++j) {
+                    const uint4 xb = __ldg(reinterpret_cast<const uint4*>(xr[j] + (r * UN + u) * 32));
+                    mma_bf16_16816(acc[j], alo[cur][u].x, ahi[cur][u].x, alo[cur][u].y, ahi[cur][u].y, xb.x, xb.y);
+                    mma_bf16_16816(acc[j], alo[cur][u].z, ahi[cur][u].z, alo[cur][u].w, ahi[cur][u].w, xb.z, xb.w);
+                }
+            }
+        }
+        // acc[j][e]: vocab row n0+g (e<2) / n0+g+8 (e>=2), batch row j*8 + 2*tg + (e&1)
+#pragma unroll
+        for (int c = 0; c < NB * 2; ++c) {
+            const int j = c >> 1, e = c & 1;
+            const int bb = j * 8 + 2 * tg + e;
+            float vt = -INFINITY, vs = -INFINITY;
+            int jt = 0x7fffffff, js = 0x7fffffff;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int n = n0 + g + 8 * h;
+                const float v = acc[j][e + 2 * h];
+                if (bb < p.B && n < p.N) {
+                    if (p.logits_out) p.logits_out[(size_t)bb * p.N + n] = v;
+                    if (token_allowed(n, st[c], p.gc, p.suppress_bits, p.begin_suppress_bits)) {
+                        if (n >= p.gc.ts_begin && st[c].mode == 0) {
+                            if (v > vs) { vs = v; js = n; }   // rows ascend with h: ties keep the lower id
+                        } else if (v > vt) { vt = v; jt = n; }
+                    }
+                }
+            }
+            // reduce over the 8 lanes that share tg (vocab rows g = 0..7): xor 4, 8, 16
+            float ms = vs;
+            int ks = js;
+#pragma unroll
+            for (int d = 4; d < 32; d <<= 1) {
+                const float ot = __shfl_xor_sync(0xffffffffu, vt, d);
+                const int oi = __shfl_xor_sync(0xffffffffu, jt, d);
+                if (ot > vt || (ot == vt && oi < jt)) { vt = ot; jt = oi; }
+                const float os = __shfl_xor_sync(0xffffffffu, ms, d);
+                const int oj = __shfl_xor_sync(0xffffffffu, ks, d);
+                if (os > ms || (os == ms && oj < ks)) { ms = os; ks = oj; }
+            }
+            // sum of exp(ts logit - slab max) over this thread's (up to 2) timestamp entries, then over lanes
+            float ex = 0.f;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int n = n0 + g + 8 * h;
+                const float v = acc[j][e + 2 * h];
+                if (bb < p.B && n < p.N && n >= p.gc.ts_begin && st[c].mode == 0 &&
+                    token_allowed(n, st[c], p.gc, p.suppress_bits, p.begin_suppress_bits))
+                    ex += __expf(v - ms);
+            }
+#pragma unroll
+            for (int d = 4; d < 32; d <<= 1) ex += __shfl_xor_sync(0xffffffffu, ex, d);
+            if (vt > bt[c] || (vt == bt[c] && jt < it[c])) { bt[c] = vt; it[c] = jt; }
+            if (ms > -INFINITY) {
+                if (ms > bs[c]) {
+                    sm[c] = (bs[c] > -INFINITY ? sm[c] * __expf(bs[c] - ms) : 0.f) + ex;
+                    bs[c] = ms;
+                    is[c] = ks;
+                } else {
+                    sm[c] += ex * __expf(ms - bs[c]);
+                    if (ms == bs[c] && ks < is[c]) is[c] = ks;
+                }
+            }
+        }
+    }
+    // one partial per (batch row, warp): lanes g == 0 hold the reduced values of their 2*NB columns
+    if (g == 0) {
+#pragma unroll
+        for (int c = 0; c < NB * 2; ++c) {
+            const int bb = (c >> 1) * 8 + 2 * tg + (c & 1);
+            if (bb < p.B) {
+                const size_t o = (size_t)bb * nwarps + gwarp;
+                p.part_val[o * 3 + 0] = bt[c];
+                p.part_val[o * 3 + 1] = bs[c];
+                p.part_val[o * 3 + 2] = sm[c];
+                p.part_idx[o * 2 + 0] = it[c];
+                p.part_idx[o * 2 + 1] = is[c];
+            }
         }
     }
 }
@@ -426,6 +474,8 @@ __global__ void __launch_bounds__(128) decode_finalize_kernel(const FinalizePara
     __shared__ float s_text[128], s_ts[128], s_sum[128];
     __shared__ int s_itext[128], s_its[128];
     const int b = blockIdx.x, tid = threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
     float bt = -INFINITY, bs = -INFINITY, sm = 0.f;
     int it = 0x7fffffff, is = 0x7fffffff;
     for (int i = tid; i < p.n_parts; i += 128) {
@@ -443,23 +493,35 @@ __global__ void __launch_bounds__(128) decode_finalize_kernel(const FinalizePara
             }
         }
     }
-    s_text[tid] = bt; s_ts[tid] = bs; s_sum[tid] = sm; s_itext[tid] = it; s_its[tid] = is;
-    __syncthreads();
-    if (tid == 0) {
-        for (int i = 1; i < 128; ++i) {
-            const float vt = s_text[i], vs = s_ts[i], ss = s_sum[i];
-            const int xt = s_itext[i], xs = s_its[i];
-            if (vt > bt || (vt == bt && xt < it)) { bt = vt; it = xt; }
-            if (vs > -INFINITY) {
-                if (vs > bs || (vs == bs && xs < is)) {
-                    sm = (bs > -INFINITY ? sm * __expf(bs - vs) : 0.f) + ss;
-                    bs = vs;
-                    is = xs;
-                } else {
-                    sm += ss * __expf(vs - bs);
-                }
+    // combine the 128 per-thread partials: shuffles within each warp, then 4 warp results through smem
+    auto merge = [&](float vt, int xt, float vs, int xs, float ss) {
+        if (vt > bt || (vt == bt && xt < it)) { bt = vt; it = xt; }
+        if (vs > -INFINITY) {
+            if (vs > bs || (vs == bs && xs < is)) {
+                sm = (bs > -INFINITY ? sm * __expf(bs - vs) : 0.f) + ss;
+                bs = vs;
+                is = xs;
+            } else {
+                sm += ss * __expf(vs - bs);
             }
         }
+    };
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const float vt = __shfl_xor_sync(0xffffffffu, bt, d);
+        const int xt = __shfl_xor_sync(0xffffffffu, it, d);
+        const float vs = __shfl_xor_sync(0xffffffffu, bs, d);
+        const int xs = __shfl_xor_sync(0xffffffffu, is, d);
+        const float ss = __shfl_xor_sync(0xffffffffu, sm, d);
+        merge(vt, xt, vs, xs, ss);
+    }
+    if ((tid & 31) == 0) {
+        const int w = tid >> 5;
+        s_text[w] = bt; s_ts[w] = bs; s_sum[w] = sm; s_itext[w] = it; s_its[w] = is;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < 4; ++w) merge(s_text[w], s_itext[w], s_ts[w], s_its[w], s_sum[w]);
         RowState s = p.st[b];
         const GrammarConst& gc = p.gc;
         int tok;
@@ -555,6 +617,8 @@ __global__ void __launch_bounds__(ATT_THREADS) decode_attn_kernel(const AttnPara
     __shared__ int s_last;
     const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int tid = threadIdx.x, grp = tid >> 3, l8 = tid & 7;
+    pdl_launch_dependents();
+    pdl_wait();
 
     int j0, j1;
     if (p.is_cross) {
@@ -683,15 +747,35 @@ __global__ void __launch_bounds__(ATT_THREADS) decode_attn_kernel(const AttnPara
 using namespace tw;
 using namespace tw::dec;
 
+static int g_use_pdl = 1;
+extern "C" int tw_set_pdl(int32_t enabled) { g_use_pdl = enabled ? 1 : 0; return 0; }
+
+// launch with the programmatic-stream-serialization attribute (the kernel's own griddepcontrol.wait orders it
+// after its predecessor); captured into CUDA graphs as a programmatic dependency edge
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_use_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 static_assert(sizeof(RowState) == 32, "RowState layout is part of the ABI (8 x int32)");
 
 template <int EPI, int WARPS>
 static int launch_nb(const SkinnyParams& p, int grid, cudaStream_t st) {
     switch ((p.B + 7) / 8) {
-        case 1: skinny_gemm_kernel<1, EPI, WARPS><<<grid, WARPS * 32, 0, st>>>(p); break;
-        case 2: skinny_gemm_kernel<2, EPI, WARPS><<<grid, WARPS * 32, 0, st>>>(p); break;
-        case 3: skinny_gemm_kernel<3, EPI, WARPS><<<grid, WARPS * 32, 0, st>>>(p); break;
-        case 4: skinny_gemm_kernel<4, EPI, WARPS><<<grid, WARPS * 32, 0, st>>>(p); break;
+        case 1: TW_CUDA_CHECK(launch_pdl(skinny_gemm_kernel<1, EPI, WARPS>, dim3(grid), dim3(WARPS * 32), 0, st, p)); break;
+        case 2: TW_CUDA_CHECK(launch_pdl(skinny_gemm_kernel<2, EPI, WARPS>, dim3(grid), dim3(WARPS * 32), 0, st, p)); break;
+        case 3: TW_CUDA_CHECK(launch_pdl(skinny_gemm_kernel<3, EPI, WARPS>, dim3(grid), dim3(WARPS * 32), 0, st, p)); break;
+        case 4: TW_CUDA_CHECK(launch_pdl(skinny_gemm_kernel<4, EPI, WARPS>, dim3(grid), dim3(WARPS * 32), 0, st, p)); break;
         default: set_error("skinny gemm: batch %d > %d", p.B, MAXB); return 2;
     }
     TW_CUDA_CHECK(cudaGetLastError());
@@ -701,8 +785,7 @@ static int launch_nb(const SkinnyParams& p, int grid, cudaStream_t st) {
 // the 16-warp K split is used for the long-K residual projection (fc2)
 template <int EPI>
 static int launch_skinny(const SkinnyParams& p, cudaStream_t st) {
-    const int slabs = (p.N + 15) / 16;
-    const int grid = (slabs + p.slabs_per_cta - 1) / p.slabs_per_cta;
+    const int grid = (p.N + 15) / 16;
     if (EPI == EPI_RESID && p.K >= 4096 && p.K % 512 == 0) return launch_nb<EPI_RESID, 16>(p, grid, st);
     return launch_nb<EPI, 8>(p, grid, st);
 }
@@ -714,9 +797,9 @@ extern "C" int tw_dec_embed(const int32_t* tokens, int32_t tokens_ld, const void
     TW_REQUIRE(d_model <= 2048, "tw_dec_embed: d_model %d > 2048", d_model);
     TW_REQUIRE(!ln_out_bf16 || (ln_gamma && ln_beta), "tw_dec_embed: LayerNorm output needs gamma and beta");
     if (batch <= 0) return 0;
-    decode_embed_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(tokens, tokens_ld, (const RowState*)row_state,
-                                                                (const __nv_bfloat16*)tok_emb_bf16, pos_emb, x, d_model,
-                                                                ln_gamma, ln_beta, (__nv_bfloat16*)ln_out_bf16);
+    TW_CUDA_CHECK(launch_pdl(decode_embed_kernel, dim3(batch), dim3(256), 0, (cudaStream_t)stream, tokens, (int)tokens_ld,
+                             (const RowState*)row_state, (const __nv_bfloat16*)tok_emb_bf16, pos_emb, x, (int)d_model,
+                             ln_gamma, ln_beta, (__nv_bfloat16*)ln_out_bf16));
     TW_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -739,7 +822,6 @@ static void fill_common(SkinnyParams& p, const tw_skinny_args* a) {
     p.B = a->batch;
     p.N = a->n;
     p.K = a->k;
-    p.slabs_per_cta = 1;
 }
 
 extern "C" int tw_dec_linear(const tw_skinny_args* a, int32_t epilogue, void* out, int32_t ldo, void* stream) {
@@ -787,7 +869,12 @@ static GrammarConst to_gc(const tw_grammar* g) {
     return gc;
 }
 
-extern "C" int32_t tw_dec_lmhead_parts(int32_t vocab) { return ((vocab + 15) / 16 + 3) / 4; }
+// number of partial records per batch row = warps of the persistent LM-head grid (one CTA per SM)
+static int lmhead_grid() { int n = num_sms(); return n > 0 ? n : 148; }
+extern "C" int32_t tw_dec_lmhead_parts(int32_t vocab) {
+    (void)vocab;
+    return lmhead_grid() * 8;
+}
 
 extern "C" int tw_dec_lmhead(const tw_skinny_args* a, const tw_grammar* g, const void* row_state,
                              const uint32_t* suppress_bits, const uint32_t* begin_suppress_bits, float* part_val,
@@ -797,7 +884,6 @@ extern "C" int tw_dec_lmhead(const tw_skinny_args* a, const tw_grammar* g, const
     TW_REQUIRE(a->n == g->vocab, "tw_dec_lmhead: N (%d) != vocab (%d)", a->n, g->vocab);
     SkinnyParams p;
     fill_common(p, a);
-    p.slabs_per_cta = 4;
     p.st = (const RowState*)row_state;
     p.suppress_bits = suppress_bits;
     p.begin_suppress_bits = begin_suppress_bits;
@@ -805,7 +891,17 @@ extern "C" int tw_dec_lmhead(const tw_skinny_args* a, const tw_grammar* g, const
     p.part_val = part_val;
     p.part_idx = part_idx;
     p.logits_out = logits_out;
-    return launch_skinny<EPI_LOGITS>(p, (cudaStream_t)stream);
+    const int grid = lmhead_grid();
+    cudaStream_t st = (cudaStream_t)stream;
+    switch ((p.B + 7) / 8) {
+        case 1: TW_CUDA_CHECK(launch_pdl(lmhead_kernel<1>, dim3(grid), dim3(256), 0, st, p)); break;
+        case 2: TW_CUDA_CHECK(launch_pdl(lmhead_kernel<2>, dim3(grid), dim3(256), 0, st, p)); break;
+        case 3: TW_CUDA_CHECK(launch_pdl(lmhead_kernel<3>, dim3(grid), dim3(256), 0, st, p)); break;
+        case 4: TW_CUDA_CHECK(launch_pdl(lmhead_kernel<4>, dim3(grid), dim3(256), 0, st, p)); break;
+        default: set_error("tw_dec_lmhead: batch %d > %d", p.B, MAXB); return 2;
+    }
+    TW_CUDA_CHECK(cudaGetLastError());
+    return 0;
 }
 
 extern "C" int tw_dec_finalize(const float* part_val, const int32_t* part_idx, int32_t n_parts, int32_t* tokens,
@@ -816,7 +912,7 @@ extern "C" int tw_dec_finalize(const float* part_val, const int32_t* part_idx, i
     FinalizeParams p;
     p.part_val = part_val; p.part_idx = part_idx; p.n_parts = n_parts; p.tokens = tokens; p.tokens_ld = tokens_ld;
     p.forced = forced; p.choices = choices; p.st = (RowState*)row_state; p.gc = to_gc(g); p.max_len = tokens_ld;
-    decode_finalize_kernel<<<batch, 128, 0, (cudaStream_t)stream>>>(p);
+    TW_CUDA_CHECK(launch_pdl(decode_finalize_kernel, dim3(batch), dim3(128), 0, (cudaStream_t)stream, p));
     TW_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -831,7 +927,7 @@ extern "C" int tw_dec_self_attn(const void* q_bf16, void* out_bf16, const void* 
     p.q = (const __nv_bfloat16*)q_bf16; p.out = (__nv_bfloat16*)out_bf16; p.D = heads * 64; p.H = heads;
     p.is_cross = 0; p.kv_pool = (const __nv_bfloat16*)kv_pool_layer; p.block_table = block_table;
     p.pages_per_row = pages_per_row; p.n_pages = n_pages; p.st = (const RowState*)row_state; p.splits = 1;
-    decode_attn_kernel<<<dim3(1, heads, batch), ATT_THREADS, 0, (cudaStream_t)stream>>>(p);
+    TW_CUDA_CHECK(launch_pdl(decode_attn_kernel, dim3(1, heads, batch), dim3(ATT_THREADS), 0, (cudaStream_t)stream, p));
     TW_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -852,7 +948,7 @@ extern "C" int tw_dec_cross_attn(const void* q_bf16, void* out_bf16, const void*
     p.is_cross = 1; p.ck = (const __nv_bfloat16*)k_bf16; p.cv = (const __nv_bfloat16*)v_bf16;
     p.row_stride = kv_row_stride; p.batch_stride = kv_batch_stride; p.head_stride = kv_head_stride;
     p.enc_row = enc_row; p.S = src_len; p.splits = splits; p.part = part; p.counters = counters;
-    decode_attn_kernel<<<dim3(splits, heads, batch), ATT_THREADS, 0, (cudaStream_t)stream>>>(p);
+    TW_CUDA_CHECK(launch_pdl(decode_attn_kernel, dim3(splits, heads, batch), dim3(ATT_THREADS), 0, (cudaStream_t)stream, p));
     TW_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
