@@ -191,37 +191,6 @@ int tw_dec_finalize(const float* part_val, const int32_t* part_idx, int32_t n_pa
                     int32_t tokens_ld, const int32_t* forced, int32_t* choices, void* row_state,
                     const tw_grammar* g, int32_t batch, void* stream);
 
-/* ------------------------------------------------------------------------------------------------
- * Fused decode step: the whole greedy step above as ONE persistent cooperative kernel (grid = #SMs, grid-wide
- * barriers between phases, weight / encoder-K,V prefetch across the barriers).  Same arithmetic, same buffers and
- * the same row_state / partial formats as the per-kernel entry points.
- * layers_dev: DEVICE array of n_layers tw_dec_layer records.  barrier: zero-initialised device uint32[2].
- * n_parts must be >= 8 * (number of SMs) (= tw_dec_lmhead_parts()).
- * ---------------------------------------------------------------------------------------------- */
-typedef struct tw_dec_layer {
-    const void *qkv_w, *out_w, *cq_w, *cout_w, *fc1_w, *fc2_w;                 /* bf16 [out, in] */
-    const float *qkv_b, *out_b, *cq_b, *cout_b, *fc1_b, *fc2_b;                /* fp32 */
-    const float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *ln3_g, *ln3_b;                /* self / cross / final LayerNorm */
-    void* kv_pool;                                                             /* paged self K/V of this layer */
-    const void *cross_k, *cross_v;                                             /* encoder K / V of this layer */
-} tw_dec_layer;
-
-typedef struct tw_dec_step_args {
-    int32_t batch, d_model, ffn, heads, n_layers, src_len, vocab;
-    const tw_dec_layer* layers_dev;
-    int32_t* tokens; int32_t tokens_ld; const int32_t* forced; int32_t* choices; void* row_state;
-    const void* tok_emb_bf16; const float* pos_emb; const float* final_ln_gamma; const float* final_ln_beta;
-    float* x; void* xn_bf16; void* q_bf16; void* att_bf16; void* hid_bf16;
-    const int32_t* block_table; int32_t pages_per_row; int32_t n_pages;
-    int64_t kv_row_stride, kv_batch_stride, kv_head_stride;
-    int32_t splits; float* cross_part; uint32_t* cross_counters;
-    const tw_grammar* grammar; const uint32_t* suppress_bits; const uint32_t* begin_suppress_bits;
-    float* part_val; int32_t* part_idx; int32_t n_parts; float* logits_out;
-    uint32_t* barrier;
-    uint64_t* timing;   /* optional device uint64[128]: ns timestamps after every grid barrier (profiling), or NULL */
-} tw_dec_step_args;
-int tw_dec_step_fused(const tw_dec_step_args* args, void* stream);
-
 #ifdef __cplusplus
 }
 #endif

@@ -36,28 +36,6 @@ class Grammar(C.Structure):
                                        "max_initial_ts", "begin_index")]
 
 
-class DecLayer(C.Structure):
-    _fields_ = [(n, c_void_p) for n in (
-        "qkv_w", "out_w", "cq_w", "cout_w", "fc1_w", "fc2_w", "qkv_b", "out_b", "cq_b", "cout_b", "fc1_b", "fc2_b",
-        "ln1_g", "ln1_b", "ln2_g", "ln2_b", "ln3_g", "ln3_b", "kv_pool", "cross_k", "cross_v")]
-
-
-class DecStepArgs(C.Structure):
-    _fields_ = [
-        ("batch", c_int32), ("d_model", c_int32), ("ffn", c_int32), ("heads", c_int32), ("n_layers", c_int32),
-        ("src_len", c_int32), ("vocab", c_int32), ("layers_dev", c_void_p),
-        ("tokens", c_void_p), ("tokens_ld", c_int32), ("forced", c_void_p), ("choices", c_void_p), ("row_state", c_void_p),
-        ("tok_emb_bf16", c_void_p), ("pos_emb", c_void_p), ("final_ln_gamma", c_void_p), ("final_ln_beta", c_void_p),
-        ("x", c_void_p), ("xn_bf16", c_void_p), ("q_bf16", c_void_p), ("att_bf16", c_void_p), ("hid_bf16", c_void_p),
-        ("block_table", c_void_p), ("pages_per_row", c_int32), ("n_pages", c_int32),
-        ("kv_row_stride", c_int64), ("kv_batch_stride", c_int64), ("kv_head_stride", c_int64),
-        ("splits", c_int32), ("cross_part", c_void_p), ("cross_counters", c_void_p),
-        ("grammar", C.POINTER(Grammar)), ("suppress_bits", c_void_p), ("begin_suppress_bits", c_void_p),
-        ("part_val", c_void_p), ("part_idx", c_void_p), ("n_parts", c_int32), ("logits_out", c_void_p),
-        ("barrier", c_void_p), ("timing", c_void_p),
-    ]
-
-
 # name -> (restype, argtypes); mirrors include/twb200.h one to one (tests/test_abi.py checks it)
 SIGNATURES = {
     "tw_last_error": (C.c_char_p, []),
@@ -84,7 +62,6 @@ SIGNATURES = {
                                 c_void_p, c_void_p, c_void_p]),
     "tw_dec_finalize": (C.c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_void_p,
                                   C.POINTER(Grammar), c_int32, c_void_p]),
-    "tw_dec_step_fused": (C.c_int, [C.POINTER(DecStepArgs), c_void_p]),
     "tw_shift_frames": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int64,
                                   c_int32, c_void_p]),
 }

@@ -738,607 +738,6 @@ __global__ void __launch_bounds__(ATT_THREADS) decode_attn_kernel(const AttnPara
     }
 }
 
-
-// ================================================================================================
-// Fused decode step: ONE persistent cooperative kernel (grid = #SMs) runs the whole greedy step
-//   embed+LN -> L x { QKV, self-attn, out-proj(+res), LN, cross-q, cross-attn, out-proj(+res), LN,
-//                     fc1+GELU, fc2(+res), LN } -> LM head + grammar -> finalize
-// with grid-wide barriers between the phases instead of 34 dependent launches.  Each phase requests
-// its dependency-free operands (weight fragments, encoder K/V rows) BEFORE the barrier, so the HBM
-// latency of phase k+1 overlaps the barrier that ends phase k.  Activations produced inside the
-// kernel are re-read through L2 (ld.global.cg): L1 is not coherent across SMs within a launch.
-// ================================================================================================
-struct LayerPtrs {  // device-resident table, one entry per decoder layer (mirrors tw_dec_layer)
-    const __nv_bfloat16 *qkv_w, *out_w, *cq_w, *cout_w, *fc1_w, *fc2_w;
-    const float *qkv_b, *out_b, *cq_b, *cout_b, *fc1_b, *fc2_b;
-    const float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *ln3_g, *ln3_b;
-    __nv_bfloat16* kv_pool;            // [2][n_pages][PAGE][D]
-    const __nv_bfloat16 *cross_k, *cross_v;
-};
-
-struct MegaArgs {
-    int B, D, F, H, L, S, V;
-    const LayerPtrs* layers;
-    int* tokens; int tokens_ld; const int* forced; int* choices; RowState* st;
-    const __nv_bfloat16* tok_emb; const float* pos_emb; const float* fln_g; const float* fln_b;
-    float* x; __nv_bfloat16* xn; __nv_bfloat16* q; __nv_bfloat16* att; __nv_bfloat16* hid;
-    const int* block_table; int pages_per_row, n_pages;
-    long long ck_row, ck_batch, ck_head;
-    int splits; float* cross_part; unsigned int* cross_cnt;
-    GrammarConst gc; const uint32_t* sup; const uint32_t* bsup;
-    float* part_val; int* part_idx; int n_parts; float* logits_out;
-    unsigned int* bar;  // [2] grid barrier state (count, generation), zero-initialised
-    unsigned long long* timing;  // optional [128] ns timestamps of CTA 0 after every grid barrier (profiling)
-};
-
-TW_DEVINL uint4 ldcg16(const void* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
-
-// grid-wide barrier (all CTAs co-resident: cooperative launch).  Sense-reversing on a generation word.
-TW_DEVINL void grid_barrier(unsigned int* bar, unsigned int& gen) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned int arrived = atomicAdd(&bar[0], 1u);
-        if (arrived == gridDim.x - 1) {
-            bar[0] = 0;
-            __threadfence();
-            atomicAdd(&bar[1], 1u);
-        } else {
-            while (*reinterpret_cast<volatile unsigned int*>(&bar[1]) == gen) { __nanosleep(20); }
-        }
-        __threadfence();
-    }
-    gen += 1;
-    __syncthreads();
-}
-TW_DEVINL void stamp(const unsigned long long* base_, unsigned long long* t, unsigned int gen0, unsigned int gen) {
-    (void)base_;
-    if (t && blockIdx.x == 0 && threadIdx.x == 0) {
-        unsigned long long ns;
-        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
-        const unsigned int i = gen - gen0;
-        if (i < 128) t[i] = ns;
-    }
-}
-
-__shared__ unsigned int g_gen0;
-
-struct MegaSmem {
-    float red[8][MAXB][17];
-    float att_m[2][ATT_GROUPS], att_l[2][ATT_GROUPS];
-    float att_o[2][ATT_GROUPS][64];
-    int att_last[2];
-    float fin_f[3][8];
-    int fin_i[2][8];
-    float emb_red[2][8];
-    unsigned int gen0;
-    RowState rows[MAXB];            // LM head: row states (shared, read with broadcast LDS)
-    float lm_f[8][MAXB][3];         // LM head: per-warp running partials (best text, best ts, sum exp ts)
-    int lm_i[8][MAXB][2];
-};
-
-enum { G_BF16 = 0, G_QKV = 1, G_RESID = 2, G_GELU = 3 };
-
-// One GEMV phase: out = X W^T (+bias, epilogue); slabs of 16 output features strided over the grid, K split
-// over the 8 warps.  The first slab's first round of weight fragments is requested before the barrier.
-template <int NB, int EPI>
-__device__ __noinline__ void mega_gemv(const MegaArgs& a, MegaSmem& sm, unsigned int& gen, const __nv_bfloat16* W, const float* bias,
-                         const __nv_bfloat16* X, int ldx, int N, int K, __nv_bfloat16* out_bf16, int ldo,
-                         __nv_bfloat16* kv_pool) {
-    constexpr int UN = 5;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = lane >> 2, tg = lane & 3;
-    const int kw = K >> 3, k_begin = warp * kw, steps = kw >> 5;
-    const int n_slabs = (N + 15) >> 4;
-    uint4 alo[UN], ahi[UN];
-    {
-        const int n0 = blockIdx.x * 16;
-        if (n0 < N) {
-            const __nv_bfloat16* wa = W + (size_t)min(n0 + g, N - 1) * K + k_begin + tg * 8;
-            const __nv_bfloat16* wb = W + (size_t)min(n0 + g + 8, N - 1) * K + k_begin + tg * 8;
-#pragma unroll
-            for (int u = 0; u < UN; ++u)
-                if (u < steps) { alo[u] = ldg_stream(wa + u * 32); ahi[u] = ldg_stream(wb + u * 32); }
-        }
-    }
-    grid_barrier(a.bar, gen); stamp(nullptr, a.timing, g_gen0, gen);
-    for (int slab = blockIdx.x; slab < n_slabs; slab += gridDim.x) {
-        const int n0 = slab * 16;
-        const __nv_bfloat16* wa = W + (size_t)min(n0 + g, N - 1) * K + k_begin + tg * 8;
-        const __nv_bfloat16* wb = W + (size_t)min(n0 + g + 8, N - 1) * K + k_begin + tg * 8;
-        const __nv_bfloat16* xr[NB];
-#pragma unroll
-        for (int j = 0; j < NB; ++j) xr[j] = X + (size_t)min(j * 8 + g, a.B - 1) * ldx + k_begin + tg * 8;
-        float acc[NB][4];
-#pragma unroll
-        for (int j = 0; j < NB; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-        for (int s0 = 0; s0 < steps; s0 += UN) {
-            uint4 xb[UN][NB];
-#pragma unroll
-            for (int u = 0; u < UN; ++u) {
-                if (s0 + u < steps) {
-                    if (s0 > 0 || slab != (int)blockIdx.x) {
-                        alo[u] = ldg_stream(wa + (s0 + u) * 32);
-                        ahi[u] = ldg_stream(wb + (s0 + u) * 32);
-                    }
-#pragma unroll
-                    for (int j = 0; j < NB; ++j) xb[u][j] = ldcg16(xr[j] + (s0 + u) * 32);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < UN; ++u) {
-                if (s0 + u < steps) {
-#pragma unroll
-                    for (int j = 0; j < NB; ++j) {
-                        mma_bf16_16816(acc[j], alo[u].x, ahi[u].x, alo[u].y, ahi[u].y, xb[u][j].x, xb[u][j].y);
-                        mma_bf16_16816(acc[j], alo[u].z, ahi[u].z, alo[u].w, ahi[u].w, xb[u][j].z, xb[u][j].w);
-                    }
-                }
-            }
-        }
-        __syncthreads();  // previous slab's reduction buffer consumed
-#pragma unroll
-        for (int j = 0; j < NB; ++j) {
-            sm.red[warp][j * 8 + 2 * tg][g] = acc[j][0];
-            sm.red[warp][j * 8 + 2 * tg + 1][g] = acc[j][1];
-            sm.red[warp][j * 8 + 2 * tg][g + 8] = acc[j][2];
-            sm.red[warp][j * 8 + 2 * tg + 1][g + 8] = acc[j][3];
-        }
-        __syncthreads();
-        for (int o = threadIdx.x; o < NB * 8 * 16; o += 256) {
-            const int bb = o >> 4, rr = o & 15;
-            const int n = n0 + rr;
-            if (bb >= a.B || n >= N) continue;
-            float v = 0.f;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) v += sm.red[w][bb][rr];
-            if (bias) v += bias[n];
-            if (EPI == G_BF16) {
-                out_bf16[(size_t)bb * ldo + n] = __float2bfloat16(v);
-            } else if (EPI == G_GELU) {
-                out_bf16[(size_t)bb * ldo + n] = __float2bfloat16(gelu_erf(v));
-            } else if (EPI == G_RESID) {
-                float* xp = a.x + (size_t)bb * N + n;
-                *xp = __ldcg(xp) + v;
-            } else {  // G_QKV
-                const int which = n / a.D, c = n - which * a.D;
-                if (which == 0) {
-                    a.q[(size_t)bb * a.D + c] = __float2bfloat16(v);
-                } else {
-                    const int pos = __ldcg(&a.st[bb].pos);
-                    const int page = a.block_table[bb * a.pages_per_row + pos / PAGE];
-                    kv_pool[((size_t)(which - 1) * a.n_pages + page) * PAGE * a.D + (size_t)(pos % PAGE) * a.D + c] =
-                        __float2bfloat16(v);
-                }
-            }
-        }
-    }
-}
-
-// LayerNorm phase: x (fp32) -> xn (bf16), one warp per row over the whole grid
-__device__ __noinline__ void mega_ln(const MegaArgs& a, unsigned int& gen, const float* g, const float* b) {
-    grid_barrier(a.bar, gen); stamp(nullptr, a.timing, g_gen0, gen);
-    const int gw = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (gw < a.B) warp_layernorm_row<true>(a.x + (size_t)gw * a.D, g, b, a.xn + (size_t)gw * a.D, a.D, threadIdx.x & 31);
-}
-
-// attention phase: units (split, head, row); two units per CTA at a time (128 threads each)
-template <bool CROSS>
-__device__ __noinline__ void mega_attn(const MegaArgs& a, MegaSmem& sm, unsigned int& gen, const LayerPtrs& lp) {
-    const int half = threadIdx.x >> 7, tid = threadIdx.x & 127;
-    const int grp = tid >> 3, l8 = tid & 7;
-    const int splits = CROSS ? a.splits : 1;
-    const int n_units = a.B * a.H * splits;
-    const int per = CROSS ? (a.S + splits - 1) / splits : 0;
-    grid_barrier(a.bar, gen); stamp(nullptr, a.timing, g_gen0, gen);
-    // every thread of a half runs the same number of iterations (the named barrier below needs all 128)
-    for (int u0 = blockIdx.x * 2; u0 < n_units; u0 += gridDim.x * 2) {
-        const int u = u0 + half;
-        const bool live = u < n_units;
-        const int uu = live ? u : n_units - 1;
-        const int split = uu % splits, h = (uu / splits) % a.H, b = uu / (splits * a.H);
-        int j0 = 0, j1;
-        if (CROSS) { j0 = split * per; j1 = min(a.S, j0 + per); }
-        else j1 = __ldcg(&a.st[b].pos) + 1;
-        float q[8];
-        bf16x8_to_f32(ldcg16(a.q + (size_t)b * a.D + h * 64 + l8 * 8), q);
-        auto row_ptr = [&](int j, int kv) -> const uint4* {
-            const __nv_bfloat16* r;
-            if (CROSS) {
-                r = (kv ? lp.cross_v : lp.cross_k) + (size_t)b * a.ck_batch + (size_t)h * a.ck_head + (size_t)j * a.ck_row;
-            } else {
-                const int page = a.block_table[b * a.pages_per_row + j / PAGE];
-                r = lp.kv_pool + ((size_t)kv * a.n_pages + page) * PAGE * a.D + (size_t)(j % PAGE) * a.D + h * 64;
-            }
-            return reinterpret_cast<const uint4*>(r) + l8;
-        };
-        float m = -INFINITY, l = 0.f, o[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = 0.f;
-        for (int base = j0; base < j1; base += ATT_GROUPS * ATT_KU) {
-            const int jb = base + grp;
-            uint4 kr[ATT_KU], vr[ATT_KU];
-#pragma unroll
-            for (int t = 0; t < ATT_KU; ++t) {
-                const int j = min(jb + t * ATT_GROUPS, j1 - 1);
-                kr[t] = CROSS ? ldg_stream(row_ptr(j, 0)) : __ldcg(row_ptr(j, 0));
-                vr[t] = CROSS ? ldg_stream(row_ptr(j, 1)) : __ldcg(row_ptr(j, 1));
-            }
-            float sc[ATT_KU];
-            float mx = m;
-#pragma unroll
-            for (int t = 0; t < ATT_KU; ++t) {
-                float f[8];
-                bf16x8_to_f32(kr[t], f);
-                float d = 0.f;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) d = fmaf(q[i], f[i], d);
-                d += __shfl_xor_sync(0xffffffffu, d, 1);
-                d += __shfl_xor_sync(0xffffffffu, d, 2);
-                d += __shfl_xor_sync(0xffffffffu, d, 4);
-                sc[t] = (jb + t * ATT_GROUPS < j1) ? d : -INFINITY;
-                mx = fmaxf(mx, sc[t]);
-            }
-            if (mx == -INFINITY) continue;
-            const float alpha = (m == -INFINITY) ? 0.f : __expf(m - mx);
-            l *= alpha;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] *= alpha;
-#pragma unroll
-            for (int t = 0; t < ATT_KU; ++t) {
-                const float pj = __expf(sc[t] - mx);
-                l += pj;
-                float f[8];
-                bf16x8_to_f32(vr[t], f);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) o[i] = fmaf(pj, f[i], o[i]);
-            }
-            m = mx;
-        }
-        if (l8 == 0) { sm.att_m[half][grp] = m; sm.att_l[half][grp] = l; }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) sm.att_o[half][grp][l8 * 8 + i] = o[i];
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
-        float M = -INFINITY, Ls = 0.f, O = 0.f;
-        if (tid < 64) {
-#pragma unroll
-            for (int gq = 0; gq < ATT_GROUPS; ++gq) M = fmaxf(M, sm.att_m[half][gq]);
-#pragma unroll
-            for (int gq = 0; gq < ATT_GROUPS; ++gq) {
-                const float w = (sm.att_m[half][gq] == -INFINITY) ? 0.f : __expf(sm.att_m[half][gq] - M);
-                Ls = fmaf(sm.att_l[half][gq], w, Ls);
-                O = fmaf(sm.att_o[half][gq][tid], w, O);
-            }
-        }
-        if (!CROSS || splits == 1) {
-            if (tid < 64 && live) a.att[(size_t)b * a.D + h * 64 + tid] = __float2bfloat16(O / Ls);
-        } else {
-            float* my = a.cross_part + (((size_t)b * a.H + h) * splits + split) * 66;
-            if (live) {
-                if (tid < 64) my[2 + tid] = O;
-                if (tid == 0) { my[0] = M; my[1] = Ls; }
-            }
-            __threadfence();
-            asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
-            if (tid == 0) {
-                int last = 0;
-                if (live) {
-                    const unsigned int prev = atomicAdd(&a.cross_cnt[b * a.H + h], 1u);
-                    last = (prev == (unsigned)splits - 1);
-                    if (last) a.cross_cnt[b * a.H + h] = 0;
-                }
-                sm.att_last[half] = last;
-            }
-            asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
-            if (sm.att_last[half] && tid < 64) {
-                __threadfence();
-                const float* base = a.cross_part + ((size_t)b * a.H + h) * splits * 66;
-                float Mg = -INFINITY;
-                for (int s2 = 0; s2 < splits; ++s2) Mg = fmaxf(Mg, __ldcg(base + s2 * 66));
-                float Lg = 0.f, Og = 0.f;
-                for (int s2 = 0; s2 < splits; ++s2) {
-                    const float w = __expf(__ldcg(base + s2 * 66) - Mg);
-                    Lg = fmaf(__ldcg(base + s2 * 66 + 1), w, Lg);
-                    Og = fmaf(__ldcg(base + s2 * 66 + 2 + tid), w, Og);
-                }
-                a.att[(size_t)b * a.D + h * 64 + tid] = __float2bfloat16(Og / Lg);
-            }
-        }
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");  // smem of this half is reused next iteration
-    }
-}
-
-// LM head phase: warp per 16-row slab, full K, double-buffered weight fragments (see lmhead_kernel)
-template <int NB>
-__device__ __noinline__ void mega_lmhead(const MegaArgs& a, MegaSmem& sm, unsigned int& gen) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = lane >> 2, tg = lane & 3;
-
-        constexpr int UN = 4;
-        const int gwarp = blockIdx.x * 8 + warp, nwarps = gridDim.x * 8;
-        const int n_slabs = (a.V + 15) >> 4;
-        const int K = a.D, rounds = K / (32 * UN);
-        const __nv_bfloat16* W = a.tok_emb;
-        uint4 alo[2][UN], ahi[2][UN];
-        if (gwarp < n_slabs) {
-            const __nv_bfloat16* wa0 = W + (size_t)min(gwarp * 16 + g, a.V - 1) * K + tg * 8;
-            const __nv_bfloat16* wb0 = W + (size_t)min(gwarp * 16 + g + 8, a.V - 1) * K + tg * 8;
-#pragma unroll
-            for (int u = 0; u < UN; ++u) { alo[0][u] = ldg_stream(wa0 + u * 32); ahi[0][u] = ldg_stream(wb0 + u * 32); }
-        }
-        grid_barrier(a.bar, gen); stamp(nullptr, a.timing, g_gen0, gen);
-        // row states and running partials live in shared memory (registers are needed for the fragment double buffer)
-        if (threadIdx.x < a.B) sm.rows[threadIdx.x] = a.st[threadIdx.x];
-        for (int i = lane; i < MAXB; i += 32) {
-            sm.lm_f[warp][i][0] = -INFINITY; sm.lm_f[warp][i][1] = -INFINITY; sm.lm_f[warp][i][2] = 0.f;
-            sm.lm_i[warp][i][0] = 0x7fffffff; sm.lm_i[warp][i][1] = 0x7fffffff;
-        }
-        __syncthreads();
-        const __nv_bfloat16* xr[NB];
-#pragma unroll
-        for (int j = 0; j < NB; ++j) xr[j] = a.xn + (size_t)min(j * 8 + g, a.B - 1) * K + tg * 8;
-        for (int slab = gwarp; slab < n_slabs; slab += nwarps) {
-            const int n0 = slab * 16;
-            const __nv_bfloat16* wa = W + (size_t)min(n0 + g, a.V - 1) * K + tg * 8;
-            const __nv_bfloat16* wb = W + (size_t)min(n0 + g + 8, a.V - 1) * K + tg * 8;
-            float acc[NB][4];
-#pragma unroll
-            for (int j = 0; j < NB; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-            if (slab != gwarp) {
-#pragma unroll
-                for (int u = 0; u < UN; ++u) { alo[0][u] = ldg_stream(wa + u * 32); ahi[0][u] = ldg_stream(wb + u * 32); }
-            }
-#pragma unroll 2
-            for (int r = 0; r < rounds; ++r) {
-                const int cur = r & 1;
-                if (r + 1 < rounds) {
-#pragma unroll
-                    for (int u = 0; u < UN; ++u) {
-                        alo[cur ^ 1][u] = ldg_stream(wa + ((r + 1) * UN + u) * 32);
-                        ahi[cur ^ 1][u] = ldg_stream(wb + ((r + 1) * UN + u) * 32);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < UN; ++u) {
-#pragma unroll
-                    for (int j = 0; j < NB; ++j) {
-                        const uint4 xb = ldcg16(xr[j] + (r * UN + u) * 32);
-                        mma_bf16_16816(acc[j], alo[cur][u].x, ahi[cur][u].x, alo[cur][u].y, ahi[cur][u].y, xb.x, xb.y);
-                        mma_bf16_16816(acc[j], alo[cur][u].z, ahi[cur][u].z, alo[cur][u].w, ahi[cur][u].w, xb.z, xb.w);
-                    }
-                }
-            }
-#pragma unroll 1
-            for (int c = 0; c < NB * 2; ++c) {
-                const int j = c >> 1, e = c & 1;
-                const int bb = j * 8 + 2 * tg + e;
-                const RowState& rs = sm.rows[min(bb, a.B - 1)];
-                const float v0 = (e == 0) ? acc[j][0] : acc[j][1];
-                const float v1 = (e == 0) ? acc[j][2] : acc[j][3];
-                float vt = -INFINITY, vs = -INFINITY;
-                int jt = 0x7fffffff, js = 0x7fffffff;
-                bool ts_ok[2];
-#pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    const int n = n0 + g + 8 * hh;
-                    const float v = hh ? v1 : v0;
-                    ts_ok[hh] = false;
-                    if (bb < a.B && n < a.V) {
-                        if (a.logits_out) a.logits_out[(size_t)bb * a.V + n] = v;
-                        if (token_allowed(n, rs, a.gc, a.sup, a.bsup)) {
-                            if (n >= a.gc.ts_begin && rs.mode == 0) {
-                                ts_ok[hh] = true;
-                                if (v > vs) { vs = v; js = n; }
-                            } else if (v > vt) { vt = v; jt = n; }
-                        }
-                    }
-                }
-                float ms = vs;
-                int ks = js;
-#pragma unroll
-                for (int d = 4; d < 32; d <<= 1) {
-                    const float ot = __shfl_xor_sync(0xffffffffu, vt, d);
-                    const int oi = __shfl_xor_sync(0xffffffffu, jt, d);
-                    if (ot > vt || (ot == vt && oi < jt)) { vt = ot; jt = oi; }
-                    const float os = __shfl_xor_sync(0xffffffffu, ms, d);
-                    const int oj = __shfl_xor_sync(0xffffffffu, ks, d);
-                    if (os > ms || (os == ms && oj < ks)) { ms = os; ks = oj; }
-                }
-                float ex = (ts_ok[0] ? __expf(v0 - ms) : 0.f) + (ts_ok[1] ? __expf(v1 - ms) : 0.f);
-#pragma unroll
-                for (int d = 4; d < 32; d <<= 1) ex += __shfl_xor_sync(0xffffffffu, ex, d);
-                if (g == 0 && bb < a.B) {   // one lane per batch column owns the warp's running partial
-                    float* pf = sm.lm_f[warp][bb];
-                    int* pi = sm.lm_i[warp][bb];
-                    if (vt > pf[0] || (vt == pf[0] && jt < pi[0])) { pf[0] = vt; pi[0] = jt; }
-                    if (ms > -INFINITY) {
-                        const float cur = pf[1];
-                        if (ms > cur) {
-                            pf[2] = (cur > -INFINITY ? pf[2] * __expf(cur - ms) : 0.f) + ex;
-                            pf[1] = ms;
-                            pi[1] = ks;
-                        } else {
-                            pf[2] += ex * __expf(ms - cur);
-                            if (ms == cur && ks < pi[1]) pi[1] = ks;
-                        }
-                    }
-                }
-            }
-        }
-        __syncwarp();
-        for (int bb = lane; bb < a.B; bb += 32) {
-            const size_t o = (size_t)bb * a.n_parts + gwarp;
-            a.part_val[o * 3 + 0] = sm.lm_f[warp][bb][0];
-            a.part_val[o * 3 + 1] = sm.lm_f[warp][bb][1];
-            a.part_val[o * 3 + 2] = sm.lm_f[warp][bb][2];
-            a.part_idx[o * 2 + 0] = sm.lm_i[warp][bb][0];
-            a.part_idx[o * 2 + 1] = sm.lm_i[warp][bb][1];
-        }
-    }
-
-template <int NB>
-__global__ void __launch_bounds__(256, 1) decode_step_mega_kernel(const MegaArgs a) {
-    __shared__ MegaSmem sm;
-    unsigned int gen = *reinterpret_cast<volatile unsigned int*>(&a.bar[1]);  // stable until every CTA arrives
-    if (threadIdx.x == 0) { g_gen0 = gen; stamp(nullptr, a.timing, gen, gen); }
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = lane >> 2, tg = lane & 3;
-
-    // ---------------- embed + first LayerNorm (rows by the first B CTAs) ----------------
-    if ((int)blockIdx.x < a.B) {
-        const int b = blockIdx.x;
-        const int pos = a.st[b].pos;
-        const int tok = a.tokens[b * a.tokens_ld + pos];
-        const LayerPtrs& l0 = a.layers[0];
-        float v[8];
-        float sum = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int c = threadIdx.x + i * 256;
-            v[i] = 0.f;
-            if (c < a.D) {
-                v[i] = __bfloat162float(a.tok_emb[(size_t)tok * a.D + c]) + a.pos_emb[(size_t)pos * a.D + c];
-                a.x[(size_t)b * a.D + c] = v[i];
-                sum += v[i];
-            }
-        }
-        sum = warp_sum(sum);
-        if (lane == 0) sm.emb_red[0][warp] = sum;
-        __syncthreads();
-        float tot = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) tot += sm.emb_red[0][w];
-        const float mean = tot / (float)a.D;
-        float qv = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int c = threadIdx.x + i * 256;
-            if (c < a.D) { const float d = v[i] - mean; qv += d * d; }
-        }
-        qv = warp_sum(qv);
-        if (lane == 0) sm.emb_red[1][warp] = qv;
-        __syncthreads();
-        float qt = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) qt += sm.emb_red[1][w];
-        const float rstd = rsqrtf(qt / (float)a.D + 1e-5f);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int c = threadIdx.x + i * 256;
-            if (c < a.D) a.xn[(size_t)b * a.D + c] = __float2bfloat16((v[i] - mean) * rstd * l0.ln1_g[c] + l0.ln1_b[c]);
-        }
-    }
-
-    // ---------------- decoder layers ----------------
-    for (int li = 0; li < a.L; ++li) {
-        const LayerPtrs& lp = a.layers[li];
-        mega_gemv<NB, G_QKV>(a, sm, gen, lp.qkv_w, lp.qkv_b, a.xn, a.D, 3 * a.D, a.D, nullptr, 0, lp.kv_pool);
-        mega_attn<false>(a, sm, gen, lp);
-        mega_gemv<NB, G_RESID>(a, sm, gen, lp.out_w, lp.out_b, a.att, a.D, a.D, a.D, nullptr, 0, nullptr);
-        mega_ln(a, gen, lp.ln2_g, lp.ln2_b);
-        mega_gemv<NB, G_BF16>(a, sm, gen, lp.cq_w, lp.cq_b, a.xn, a.D, a.D, a.D, a.q, a.D, nullptr);
-        mega_attn<true>(a, sm, gen, lp);
-        mega_gemv<NB, G_RESID>(a, sm, gen, lp.cout_w, lp.cout_b, a.att, a.D, a.D, a.D, nullptr, 0, nullptr);
-        mega_ln(a, gen, lp.ln3_g, lp.ln3_b);
-        mega_gemv<NB, G_GELU>(a, sm, gen, lp.fc1_w, lp.fc1_b, a.xn, a.D, a.F, a.D, a.hid, a.F, nullptr);
-        mega_gemv<NB, G_RESID>(a, sm, gen, lp.fc2_w, lp.fc2_b, a.hid, a.F, a.D, a.F, nullptr, 0, nullptr);
-        if (li + 1 < a.L) mega_ln(a, gen, a.layers[li + 1].ln1_g, a.layers[li + 1].ln1_b);
-        else mega_ln(a, gen, a.fln_g, a.fln_b);
-    }
-
-    mega_lmhead<NB>(a, sm, gen);
-
-    // ---------------- finalize (rows by the first B CTAs) ----------------
-    grid_barrier(a.bar, gen); stamp(nullptr, a.timing, g_gen0, gen);
-    if ((int)blockIdx.x < a.B) {
-        const int b = blockIdx.x, tid = threadIdx.x;
-        float bt = -INFINITY, bs = -INFINITY, sme = 0.f;
-        int it = 0x7fffffff, is = 0x7fffffff;
-        auto merge = [&](float vt, int xt, float vs, int xs, float ss) {
-            if (vt > bt || (vt == bt && xt < it)) { bt = vt; it = xt; }
-            if (vs > -INFINITY) {
-                if (vs > bs || (vs == bs && xs < is)) {
-                    sme = (bs > -INFINITY ? sme * __expf(bs - vs) : 0.f) + ss;
-                    bs = vs;
-                    is = xs;
-                } else {
-                    sme += ss * __expf(vs - bs);
-                }
-            }
-        };
-        const int used = min(a.n_parts, gridDim.x * 8);
-        for (int i = tid; i < used; i += 256) {
-            const size_t o = (size_t)b * a.n_parts + i;
-            merge(__ldcg(&a.part_val[o * 3 + 0]), __ldcg(&a.part_idx[o * 2 + 0]), __ldcg(&a.part_val[o * 3 + 1]),
-                  __ldcg(&a.part_idx[o * 2 + 1]), __ldcg(&a.part_val[o * 3 + 2]));
-        }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            const float vt = __shfl_xor_sync(0xffffffffu, bt, d);
-            const int xt = __shfl_xor_sync(0xffffffffu, it, d);
-            const float vs = __shfl_xor_sync(0xffffffffu, bs, d);
-            const int xs = __shfl_xor_sync(0xffffffffu, is, d);
-            const float ss = __shfl_xor_sync(0xffffffffu, sme, d);
-            merge(vt, xt, vs, xs, ss);
-        }
-        if (lane == 0) {
-            sm.fin_f[0][warp] = bt; sm.fin_f[1][warp] = bs; sm.fin_f[2][warp] = sme;
-            sm.fin_i[0][warp] = it; sm.fin_i[1][warp] = is;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            for (int w = 1; w < 8; ++w) merge(sm.fin_f[0][w], sm.fin_i[0][w], sm.fin_f[1][w], sm.fin_i[1][w], sm.fin_f[2][w]);
-            RowState s = a.st[b];
-            const GrammarConst& gc = a.gc;
-            int tok;
-            if (s.mode == 1) {
-                tok = it;
-            } else {
-                const float lse_ts = (bs > -INFINITY) ? bs + logf(sme) : -INFINITY;
-                if (lse_ts > bt) tok = is;
-                else tok = (bs > bt) ? is : it;
-            }
-            const int wi = s.pos + 1;
-            if (s.finished) tok = gc.pad;
-            if (a.choices && wi < a.tokens_ld) a.choices[b * a.tokens_ld + wi] = tok;
-            const int f = (wi < a.tokens_ld) ? a.forced[b * a.tokens_ld + wi] : -1;
-            if (f >= 0) tok = f;
-            if (wi < a.tokens_ld) a.tokens[b * a.tokens_ld + wi] = tok;
-            const int gen_before = wi - gc.begin_index;
-            if (gen_before >= 0 && tok == gc.eos) s.finished = 1;
-            s.pos = wi;
-            s.mode = 0;
-            const int gen_now = gen_before + 1;
-            if (gen_now <= 0) {
-                s.last_ts = -1;
-                s.begin = (gen_now == 0);
-                s.text_lo = gc.ts_begin;
-                s.ts_lo = gc.ts_begin;
-                s.ts_hi = gc.ts_begin + gc.max_initial_ts;
-            } else {
-                const int prev = (gen_now >= 2) ? a.tokens[b * a.tokens_ld + wi - 1] : -1;
-                const bool last_is_ts = tok >= gc.ts_begin;
-                const bool pen_is_ts = (gen_now < 2) || prev >= gc.ts_begin;
-                if (last_is_ts) s.last_ts = tok;
-                s.begin = 0;
-                s.text_lo = 0;
-                s.ts_lo = gc.ts_begin;
-                s.ts_hi = gc.vocab - 1;
-                if (last_is_ts) {
-                    if (pen_is_ts) s.ts_hi = gc.ts_begin - 1;
-                    else s.text_lo = gc.eos;
-                }
-                if (s.last_ts >= 0) {
-                    const int bound = (last_is_ts && !pen_is_ts) ? s.last_ts : s.last_ts + 1;
-                    if (bound > s.ts_lo) s.ts_lo = bound;
-                }
-            }
-            a.st[b] = s;
-        }
-    }
-}
-
 }  // namespace dec
 }  // namespace tw
 
@@ -1551,51 +950,5 @@ extern "C" int tw_dec_cross_attn(const void* q_bf16, void* out_bf16, const void*
     p.enc_row = enc_row; p.S = src_len; p.splits = splits; p.part = part; p.counters = counters;
     TW_CUDA_CHECK(launch_pdl(decode_attn_kernel, dim3(splits, heads, batch), dim3(ATT_THREADS), 0, (cudaStream_t)stream, p));
     TW_CUDA_CHECK(cudaGetLastError());
-    return 0;
-}
-
-static_assert(sizeof(LayerPtrs) == sizeof(tw_dec_layer), "tw_dec_layer mirrors LayerPtrs");
-
-extern "C" int tw_dec_step_fused(const tw_dec_step_args* a, void* stream) {
-    TW_REQUIRE(a && a->layers_dev && a->tokens && a->forced && a->row_state && a->tok_emb_bf16 && a->pos_emb && a->x &&
-                   a->xn_bf16 && a->q_bf16 && a->att_bf16 && a->hid_bf16 && a->block_table && a->cross_part &&
-                   a->cross_counters && a->grammar && a->suppress_bits && a->begin_suppress_bits && a->part_val &&
-                   a->part_idx && a->barrier && a->final_ln_gamma && a->final_ln_beta,
-               "tw_dec_step_fused: null argument");
-    TW_REQUIRE(a->batch >= 1 && a->batch <= MAXB, "tw_dec_step_fused: batch %d not in [1,%d]", a->batch, MAXB);
-    TW_REQUIRE(a->d_model % 256 == 0 && a->d_model <= 1280 && a->ffn % 256 == 0 && a->d_model == a->heads * 64,
-               "tw_dec_step_fused: unsupported dims");
-    TW_REQUIRE(a->splits >= 1 && (a->src_len + a->splits - 1) / a->splits <= ATT_MAXKEYS * 4, "tw_dec_step_fused: splits");
-    MegaArgs m{};
-    m.B = a->batch; m.D = a->d_model; m.F = a->ffn; m.H = a->heads; m.L = a->n_layers; m.S = a->src_len; m.V = a->vocab;
-    m.layers = (const LayerPtrs*)a->layers_dev;
-    m.tokens = a->tokens; m.tokens_ld = a->tokens_ld; m.forced = a->forced; m.choices = a->choices;
-    m.st = (RowState*)a->row_state;
-    m.tok_emb = (const __nv_bfloat16*)a->tok_emb_bf16; m.pos_emb = a->pos_emb;
-    m.fln_g = a->final_ln_gamma; m.fln_b = a->final_ln_beta;
-    m.x = a->x; m.xn = (__nv_bfloat16*)a->xn_bf16; m.q = (__nv_bfloat16*)a->q_bf16; m.att = (__nv_bfloat16*)a->att_bf16;
-    m.hid = (__nv_bfloat16*)a->hid_bf16;
-    m.block_table = a->block_table; m.pages_per_row = a->pages_per_row; m.n_pages = a->n_pages;
-    m.ck_row = a->kv_row_stride; m.ck_batch = a->kv_batch_stride; m.ck_head = a->kv_head_stride;
-    m.splits = a->splits; m.cross_part = a->cross_part; m.cross_cnt = a->cross_counters;
-    m.gc = to_gc(a->grammar); m.sup = a->suppress_bits; m.bsup = a->begin_suppress_bits;
-    m.part_val = a->part_val; m.part_idx = a->part_idx; m.n_parts = a->n_parts; m.logits_out = a->logits_out;
-    m.bar = a->barrier;
-    m.timing = (unsigned long long*)a->timing;
-    const int sms = num_sms();
-    TW_REQUIRE(sms > 0, "tw_dec_step_fused: no CUDA device");
-    TW_REQUIRE(a->n_parts >= sms * 8, "tw_dec_step_fused: n_parts %d < %d", a->n_parts, sms * 8);
-    void* kern = nullptr;
-    switch ((m.B + 7) / 8) {
-        case 1: kern = (void*)decode_step_mega_kernel<1>; break;
-        case 2: kern = (void*)decode_step_mega_kernel<2>; break;
-        case 3: kern = (void*)decode_step_mega_kernel<3>; break;
-        default: kern = (void*)decode_step_mega_kernel<4>; break;
-    }
-    int per_sm = 0;
-    TW_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));
-    TW_REQUIRE(per_sm >= 1, "tw_dec_step_fused: kernel does not fit on an SM");
-    void* args[] = {(void*)&m};
-    TW_CUDA_CHECK(cudaLaunchCooperativeKernel(kern, dim3(sms), dim3(256), args, 0, (cudaStream_t)stream));
     return 0;
 }

@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from . import _lib, ops
-from ._lib import DecLayer, DecStepArgs, Grammar, SkinnyArgs, check
+from ._lib import Grammar, SkinnyArgs, check
 from .config import N_FRAMES, N_SAMPLES, GenerationSettings, WhisperDims
 
 MAX_DECODE_BATCH = 32
@@ -155,7 +155,6 @@ class WhisperEngine:
         self.device = torch.device(device)
         self.max_batch = max_batch
         self.cross_splits = cross_splits
-        self.fused_splits = 3      # 3 x 500 keys: 24*20*3 units = 4.86 rounds of 2 units x 148 CTAs
         D, F, L, Bm = dims.d_model, dims.ffn, dims.dec_layers, max_batch
         S, T = dims.max_source_positions, N_FRAMES
         dev = self.device
@@ -193,11 +192,9 @@ class WhisperEngine:
             self.n_parts = int(_lib.load().tw_dec_lmhead_parts(dims.vocab))
             self.part_val = z(Bm, self.n_parts, 3, dtype=f32)
             self.part_idx = z(Bm, self.n_parts, 2, dtype=i32)
-            self.cross_part = z(Bm, dims.heads, max(cross_splits, 4), 66, dtype=f32)
+            self.cross_part = z(Bm, dims.heads, cross_splits, 66, dtype=f32)
             self.cross_cnt = z(Bm, dims.heads, dtype=i32)
             self.ln_cnt = z(1, dtype=i32)
-            self.grid_bar = z(2, dtype=i32)            # grid barrier state of the fused decode-step kernel
-            self.layer_table = z(L * C.sizeof(DecLayer), dtype=torch.uint8)
             self.logits = None   # optional [Bm, vocab] fp32 raw-logit tap for parity tests
             self.choices = None  # optional [Bm, max_len] int32 tap of the un-forced picks
             self.sup_bits = torch.from_numpy(_bitmap(self.gen.suppress_tokens, dims.vocab).view(np.int32)).to(dev)
@@ -212,9 +209,6 @@ class WhisperEngine:
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
         self._ckv_batch = max_batch
         self.use_graphs = True
-        self.fused_step = True     # one persistent cooperative kernel per decode step (else 34 launches / CUDA graph)
-        self._layer_table_key = None
-        self.step_timing = None    # optional int64[128] device tensor: per-phase timestamps of the fused step
         self.finish_check_every = 16
         self.stats = {"enc_windows": 0, "dec_steps": 0, "launches": 0, "h2d_bytes": 0, "d2h_bytes": 0}
         self._pcm_host = torch.zeros(Bm, N_SAMPLES, dtype=torch.float32).pin_memory()
@@ -352,53 +346,9 @@ class WhisperEngine:
                                   p(self.forced), None if self.choices is None else p(self.choices), p(self.state),
                                   C.byref(self.grammar), B, st), "tw_dec_finalize")
 
-    def _decode_step_fused(self, B: int) -> None:
-        """The same step as ONE persistent cooperative kernel (tw_dec_step_fused)."""
-        lib, d, w = _lib.load(), self.dims, self.w
-        D, F, L, H, S = d.d_model, d.ffn, d.dec_layers, d.heads, d.max_source_positions
-        Bc = self._ckv_batch
-        blk = Bc * S * 64
-        if self._layer_table_key != Bc:      # cross K/V block addresses depend on the encoder batch
-            tab = (DecLayer * L)()
-            for i in range(L):
-                q = f"dec{i}."
-                t = tab[i]
-                for f_, k_ in (("qkv_w", "qkv_w"), ("out_w", "out_w"), ("cq_w", "cq_w"), ("cout_w", "cout_w"),
-                               ("fc1_w", "fc1_w"), ("fc2_w", "fc2_w"), ("qkv_b", "qkv_b"), ("out_b", "out_b"),
-                               ("cq_b", "cq_b"), ("cout_b", "cout_b"), ("fc1_b", "fc1_b"), ("fc2_b", "fc2_b"),
-                               ("ln1_g", "ln1_w"), ("ln1_b", "ln1_b"), ("ln2_g", "ln2_w"), ("ln2_b", "ln2_b"),
-                               ("ln3_g", "ln3_w"), ("ln3_b", "ln3_b")):
-                    setattr(t, f_, w[q + k_].data_ptr())
-                t.kv_pool = self.kv_pool[i].data_ptr()
-                t.cross_k = self.ckv.data_ptr() + ((i * 2 + 0) * H) * blk * 2
-                t.cross_v = self.ckv.data_ptr() + ((i * 2 + 1) * H) * blk * 2
-            host = torch.frombuffer(bytearray(bytes(tab)), dtype=torch.uint8)
-            self.layer_table.copy_(host)
-            self._layer_table_key = Bc
-        p = lambda t: t.data_ptr()
-        a = DecStepArgs()
-        a.batch, a.d_model, a.ffn, a.heads, a.n_layers, a.src_len, a.vocab = B, D, F, H, L, S, d.vocab
-        a.layers_dev = p(self.layer_table)
-        a.tokens, a.tokens_ld, a.forced = p(self.tokens), self.max_len, p(self.forced)
-        a.choices = None if self.choices is None else p(self.choices)
-        a.row_state = p(self.state)
-        a.tok_emb_bf16, a.pos_emb = p(w["tok_emb"]), p(w["dec_pos"])
-        a.final_ln_gamma, a.final_ln_beta = p(w["dec_ln_w"]), p(w["dec_ln_b"])
-        a.x, a.xn_bf16, a.q_bf16, a.att_bf16, a.hid_bf16 = p(self.dx), p(self.dxn), p(self.dq), p(self.datt), p(self.dhid)
-        a.block_table, a.pages_per_row, a.n_pages = p(self.block_table), self.pages_per_row, self.n_pages
-        a.kv_row_stride, a.kv_batch_stride, a.kv_head_stride = 64, S * 64, blk
-        a.splits, a.cross_part, a.cross_counters = self.fused_splits, p(self.cross_part), p(self.cross_cnt)
-        a.grammar = C.pointer(self.grammar)
-        a.suppress_bits, a.begin_suppress_bits = p(self.sup_bits), p(self.bsup_bits)
-        a.part_val, a.part_idx, a.n_parts = p(self.part_val), p(self.part_idx), self.n_parts
-        a.logits_out = None if self.logits is None else p(self.logits)
-        a.barrier = p(self.grid_bar)
-        a.timing = None if self.step_timing is None else p(self.step_timing)
-        check(lib.tw_dec_step_fused(C.byref(a), self._stream()), "tw_dec_step_fused")
-
     @property
     def launches_per_step(self) -> int:
-        return 1 if self.fused_step else 1 + 8 * self.dims.dec_layers + 2
+        return 1 + 8 * self.dims.dec_layers + 2
 
     def _graph_for(self, B: int) -> torch.cuda.CUDAGraph:
         key = (B, self._ckv_batch)   # the K/V block stride depends on the encoder batch
@@ -447,11 +397,9 @@ class WhisperEngine:
             self.state[:B].copy_(st0.to(dev))
             self.stats["h2d_bytes"] += 2 * B * max_len * 4 + B * ROWSTATE_INTS * 4
             steps = (max_len - 1) if n_steps is None else min(n_steps, max_len - 1)
-            graph = self._graph_for(B) if (self.use_graphs and not self.fused_step) else None
+            graph = self._graph_for(B) if self.use_graphs else None
             for s in range(steps):
-                if self.fused_step:
-                    self._decode_step_fused(B)
-                elif graph is not None:
+                if graph is not None:
                     graph.replay()
                 else:
                     self._decode_step(B)
