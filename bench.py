@@ -211,7 +211,39 @@ def gemm_roofline_probe(eng, B, iters=5):
     return ms, flops
 
 
+def cross_attn_roofline_probe(eng, B, iters=20):
+    """Average launch duration of the decode cross-attention kernel (largest single kernel of a step by time) on
+    the engine's own head-major K/V, CUDA events on the launching stream.  Algorithmic bytes per launch =
+    B * 2 (K,V) * 1500 * 1280 * 2 B (7.68 MB per sequence-layer)."""
+    import ctypes as C
+    from turbo_whisper_workspace_b200 import _lib
+    lib = _lib.load()
+    d = eng.dims
+    D, H, S = d.d_model, d.heads, d.max_source_positions
+    blk = eng._ckv_batch * S * 64
+    p = lambda t: C.c_void_p(t.data_ptr())
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    L = d.dec_layers
+
+    def launch(i):
+        kptr = C.c_void_p(eng.ckv.data_ptr() + ((i * 2 + 0) * H) * blk * 2)
+        vptr = C.c_void_p(eng.ckv.data_ptr() + ((i * 2 + 1) * H) * blk * 2)
+        _lib.check(lib.tw_dec_cross_attn(p(eng.dq), p(eng.datt), kptr, vptr, 64, S * 64, blk, None, S, B, H,
+                                         eng.cross_splits, p(eng.cross_part), p(eng.cross_cnt), st), "cross_attn")
+    for i in range(L):
+        launch(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for it in range(iters):
+        launch(it % L)          # rotate layers: 4 x 184 MB > L2
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters, B * 2.0 * S * D * 2
+
+
 def run_own(args, rank, world, local_rank):
+    import threading
     import torch.distributed as dist
     import helpers
     from turbo_whisper_workspace_b200.config import WhisperDims
@@ -227,11 +259,12 @@ def run_own(args, rank, world, local_rank):
     dims = WhisperDims.large_v3_turbo()
     sd = helpers.random_state_dict(dims, 0, "hf")
     tok = helpers.build_tokenizer()
-    pipe = B200WhisperPipeline(sd, dims, tok, devices=[dev], max_batch=B)
+    pipe = B200WhisperPipeline(sd, dims, tok, devices=[dev], max_batch=B, contexts_per_device=args.contexts)
     del sd
-    eng = pipe.scheduler.engines[0]
+    engines = pipe.scheduler.flat_engines
+    K = args.steps
     clips = [helpers.synth_clip(rank * B + i) for i in range(B)]
-    audio = np.concatenate(clips)                      # 720 s host PCM for the e2e call
+    audio = np.concatenate(clips * K)                  # K x 720 s host PCM for the e2e call (K micro-batches)
     kw = dict(chunk_length_s=30, stride_length_s=0, batch_size=B, generate_kwargs={"task": "transcribe"},
               return_timestamps=True)
 
@@ -241,77 +274,113 @@ def run_own(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_resident():
-        eng.features(B)
-        return eng.generate(B)
+    def stats_sum(key):
+        return sum(e.stats.get(key, 0) for e in engines)
+
+    def run_resident(n_steps):
+        """n_steps passes over the PCM already resident in each context's HBM buffer; the contexts of the GPU
+        take the steps round-robin on their own streams.  Returns per-context end events."""
+        ends, errs = [None] * len(engines), []
+
+        def work(ci):
+            try:
+                eng = engines[ci]
+                with torch.cuda.stream(eng.stream) if eng.stream is not None else torch.cuda.stream(torch.cuda.current_stream()):
+                    for s_ in range(ci, n_steps, len(engines)):
+                        eng.features(B)
+                        work.rows = eng.generate(B)
+                    ev = torch.cuda.Event(enable_timing=True)
+                    ev.record()
+                    ends[ci] = ev
+            except BaseException as ex:
+                errs.append(ex)
+        ths = [threading.Thread(target=work, args=(ci,)) for ci in range(len(engines))]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        if errs:
+            raise errs[0]
+        return ends, getattr(work, "rows", None)
 
     # ---- device-resident leg ("value")
-    eng.load_pcm(clips)
-    for _ in range(args.warmup):
-        step_resident()
+    for eng in engines:
+        if eng.stream is not None:
+            with torch.cuda.stream(eng.stream):
+                eng.load_pcm(clips)
+        else:
+            eng.load_pcm(clips)
+    torch.cuda.synchronize()
+    run_resident(max(args.warmup, len(engines)))
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    l0 = dict(eng.stats)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0, d0, w0 = stats_sum("launches"), stats_sum("dec_steps"), stats_sum("enc_windows")
+    e0 = torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        rows = step_resident()
-    e1.record()
+    torch.cuda.synchronize()      # every context stream starts after e0
+    ends, rows = run_resident(K)
     barrier()
-    t_dev = e0.elapsed_time(e1) / 1e3
-    launches = eng.stats["launches"] - l0["launches"]
-    dec_steps = eng.stats["dec_steps"] - l0["dec_steps"]
-    enc_windows = eng.stats["enc_windows"] - l0["enc_windows"]
+    t_dev = max(e0.elapsed_time(ev) for ev in ends if ev is not None) / 1e3
+    launches = stats_sum("launches") - l0
+    dec_steps = stats_sum("dec_steps") - d0
+    enc_windows = stats_sum("enc_windows") - w0
 
     # ---- end-to-end leg through the reference-facing callable
-    for _ in range(min(args.warmup, 1)):
-        pipe(audio, **kw)
+    pipe(audio[:B * 480000 * min(K, len(engines))], **kw)      # warm-up of the call path
     barrier()
-    b0 = dict(eng.stats)
+    h0, dd0 = stats_sum("h2d_bytes"), stats_sum("d2h_bytes")
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        result = pipe(audio, **kw)
+    result = pipe(audio, **kw)
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
     clocks = sampler.stop()
-    h2d = (eng.stats.get("h2d_bytes", 0) - b0.get("h2d_bytes", 0)) // max(args.steps, 1)
-    d2h = (eng.stats.get("d2h_bytes", 0) - b0.get("d2h_bytes", 0)) // max(args.steps, 1)
+    h2d = (stats_sum("h2d_bytes") - h0) // max(K, 1)
+    d2h = (stats_sum("d2h_bytes") - dd0) // max(K, 1)
 
-    # ---- roofline of the dominant encoder kernel, measured live
+    # ---- rooflines of the two dominant kernels, measured live
     pk = peaks()
-    gemm_ms, gemm_flops = gemm_roofline_probe(eng, B)
+    eng0 = engines[0]
+    ca_ms, ca_bytes = cross_attn_roofline_probe(eng0, B)
+    gemm_ms, gemm_flops = gemm_roofline_probe(eng0, B)
 
     t = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     t_dev, t_e2e = float(t[0]), float(t[1])
-    audio_s = WINDOW_S * B * world * args.steps
+    audio_s = WINDOW_S * B * world * K
     if rank == 0:
-        achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
+        ca_gbs = ca_bytes / (ca_ms * 1e-3) / 1e9
+        gemm_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12
         line = {
             "metric": "RTFx (audio s / wall s), large-v3-turbo bf16", "value": audio_s / t_dev, "unit": "x realtime",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3,
+            "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": t_dev / K * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "whisper-large-v3-turbo bf16, 24 x 30 s windows per GPU per step (BASELINE.json "
                                    "configs[1]); random-init weights (HF init, seed 0), 0.1*N(0,1) audio; greedy, "
                                    "timestamps, HF short-form seek loop",
                        "windows_per_gpu": B, "parallelism": f"window-sharded x{world}, no data-path collective",
+                       "contexts_per_gpu": len(engines),
                        "l2": "working set (1.6 GB weights + >2 GB activations per step) exceeds the 126 MB L2",
-                       "decoder_steps_per_step": dec_steps // args.steps,
-                       "encoder_windows_per_step": enc_windows // args.steps},
+                       "decoder_steps_per_step": dec_steps // K, "encoder_windows_per_step": enc_windows // K},
             "e2e": {"value": audio_s / t_e2e, "unit": "x realtime", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": t_e2e / args.steps * 1e3,
-                    "api": "B200WhisperPipeline.__call__(np.ndarray, chunk_length_s=30, stride_length_s=0, "
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": t_e2e / K * 1e3,
+                    "api": "B200WhisperPipeline.__call__(np.ndarray[steps*720 s], chunk_length_s=30, stride_length_s=0, "
                            "batch_size=24, return_timestamps=True)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05, encoder qkv/out/fc1/fc2 shapes)",
-                         "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                         "frac": achieved / pk["bf16_tflops"], "traffic": None, "peak_source": pk["source"] + " burst",
-                         "flops_per_launch": gemm_flops, "ms_per_launch": gemm_ms},
-            "output_check": {"windows": len(result["chunks"]) if isinstance(result, dict) else None,
-                             "tokens_first_row": len(rows[0])},
+            "roofline": {"bound": "hbm", "kernel": "decode_attn_kernel (cross-attention over the encoder K/V; largest "
+                                                   "single kernel of a step by time)",
+                         "achieved": ca_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ca_gbs / pk["hbm_gbs"],
+                         "traffic": None, "peak_source": pk["source"], "bytes_per_launch": ca_bytes,
+                         "ms_per_launch": ca_ms},
+            "roofline_encoder_gemm": {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05; encoder qkv/out/fc1/fc2 "
+                                      "shapes, fused bias/GELU/residual)", "achieved": gemm_tf,
+                                      "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": gemm_tf / pk["bf16_tflops"],
+                                      "traffic": None, "peak_source": pk["source"] + " burst",
+                                      "flops_per_launch": gemm_flops, "ms_per_launch": gemm_ms},
+            "output_check": {"chunks": len(result["chunks"]) if isinstance(result, dict) else None,
+                             "tokens_first_row": len(rows[0]) if rows else None},
         }
         if world == 1 and not args.no_cpu_baseline:
             from transformers import WhisperFeatureExtractor
@@ -338,6 +407,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--contexts", type=int, default=2, help="engine contexts (streams) per GPU sharing one weight copy")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -71,8 +71,13 @@ def test_window_scheduler_orders_and_microbatches():
     sch = S.WindowScheduler(None, None, None, devices=["d0", "d1", "d2"], engine_factory=lambda d: FakeEngine(d, 4))
     rows = sch.run(clips)
     assert rows == [[(100 + i) % 1000, i] for i in range(23)]
-    assert [sum(e.calls) for e in sch.engines] == [8, 8, 7]
-    assert all(max(e.calls) <= 4 for e in sch.engines)
+    assert [sum(e.calls) for e in sch.flat_engines] == [8, 8, 7]
+    assert all(max(e.calls) <= 4 for e in sch.flat_engines)
+    # two contexts per device share the device's micro-batch queue; order of the results is unchanged
+    sch2 = S.WindowScheduler(None, None, None, devices=["d0", "d1"], engine_factory=lambda d: FakeEngine(d, 4),
+                             contexts_per_device=2)
+    assert sch2.run(clips) == rows
+    assert sum(sum(e.calls) for e in sch2.flat_engines) == 23 and len(sch2.flat_engines) == 4
     assert S.WindowScheduler(None, None, None, devices=["d0"], engine_factory=lambda d: FakeEngine(d)).run([]) == []
 
 

@@ -12,6 +12,7 @@ on the data path (tensor allocation, H2D / D2H copies and int bookkeeping only).
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
@@ -22,6 +23,7 @@ from ._lib import Grammar, SkinnyArgs, check
 from .config import N_FRAMES, N_SAMPLES, GenerationSettings, WhisperDims
 
 MAX_DECODE_BATCH = 32
+_CAPTURE_LOCK = threading.Lock()   # CUDA-graph capture is serialised across the engine contexts of a process
 PAGE = 64
 ROWSTATE_INTS = 8
 
@@ -143,8 +145,12 @@ def retrieve_segment(seq: List[int], seek_num_frames: int, ts_begin: int):
 class WhisperEngine:
     """One engine per GPU.  ``max_batch`` bounds the number of 30 s windows processed together."""
 
-    def __init__(self, dims: WhisperDims, state_dict: Dict[str, torch.Tensor], device="cuda:0",
-                 gen: Optional[GenerationSettings] = None, max_batch: int = 24, cross_splits: int = 4):
+    def __init__(self, dims: WhisperDims, state_dict: Optional[Dict[str, torch.Tensor]], device="cuda:0",
+                 gen: Optional[GenerationSettings] = None, max_batch: int = 24, cross_splits: int = 4,
+                 shared_weights: Optional[Dict[str, torch.Tensor]] = None, own_stream: bool = False):
+        """``shared_weights``: the packed weights (``.w``) of another engine on the same device — several engine
+        contexts (each with its own workspaces, KV pool and stream) then serve one GPU from one copy of the model,
+        so that one context's latency-bound decode overlaps another's tensor-bound encoder."""
         dims.validate()
         _lib.load()
         if not torch.cuda.is_available():
@@ -159,7 +165,8 @@ class WhisperEngine:
         S, T = dims.max_source_positions, N_FRAMES
         dev = self.device
         with torch.cuda.device(dev):
-            self.w = pack_weights(state_dict, dims, dev)
+            self.w = shared_weights if shared_weights is not None else pack_weights(state_dict, dims, dev)
+            self.stream = torch.cuda.Stream(device=dev) if own_stream else None
             bf, f32, i32 = torch.bfloat16, torch.float32, torch.int32
             z = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, device=dev)
             self.logmel = ops.LogMel(dev, Bm)
@@ -358,12 +365,13 @@ class WhisperEngine:
             state_backup = self.state.clone()
             tokens_backup = self.tokens.clone()
             self._decode_step(B)
-            torch.cuda.synchronize(self.device)
+            torch.cuda.current_stream(self.device).synchronize()
             self.state.copy_(state_backup)
             self.tokens.copy_(tokens_backup)
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._decode_step(B)
+            with _CAPTURE_LOCK:
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    self._decode_step(B)
             self.state.copy_(state_backup)
             self.tokens.copy_(tokens_backup)
             self._graphs[key] = g
@@ -419,6 +427,11 @@ class WhisperEngine:
                           language: Optional[str] = None) -> List[List[int]]:
         """PCM windows (<= 30 s each) -> generated token ids per window (segments concatenated), the
         output contract of ``WhisperGenerationMixin.generate(..., return_timestamps=True)`` minus padding."""
+        if self.stream is not None:
+            with torch.cuda.stream(self.stream):
+                B = self.load_pcm(clips)
+                self.features(B)
+                return self.generate(B, task=task, language=language)
         B = self.load_pcm(clips)
         self.features(B)
         return self.generate(B, task=task, language=language)

@@ -149,7 +149,7 @@ class B200WhisperPipeline:
 
     def __init__(self, state_dict, dims: WhisperDims, tokenizer, generation: Optional[GenerationSettings] = None,
                  devices: Sequence[Union[str, int]] = ("cuda:0",), max_batch: int = 24, time_precision: float = 0.02,
-                 scheduler=None):
+                 scheduler=None, contexts_per_device: int = 2):
         """``scheduler``: any object with ``run(clips, task=, language=) -> token rows`` and ``last_stats``;
         defaults to a :class:`WindowScheduler` with one GPU engine per entry of ``devices``."""
         self.dims = dims
@@ -159,16 +159,18 @@ class B200WhisperPipeline:
         self.time_precision = time_precision  # chunk_length 30 s / max_source_positions 1500
         if scheduler is None:
             from .scheduler import WindowScheduler
-            scheduler = WindowScheduler(state_dict, dims, self.generation, devices, max_batch)
+            scheduler = WindowScheduler(state_dict, dims, self.generation, devices, max_batch,
+                                        contexts_per_device=contexts_per_device)
         self.scheduler = scheduler
         self.last_stats: Dict[str, Any] = {}
 
     @classmethod
-    def from_hf_model(cls, model, tokenizer, devices=("cuda:0",), max_batch: int = 24) -> "B200WhisperPipeline":
+    def from_hf_model(cls, model, tokenizer, devices=("cuda:0",), max_batch: int = 24,
+                      contexts_per_device: int = 2) -> "B200WhisperPipeline":
         """Build from a ``transformers.WhisperForConditionalGeneration`` (weights, config, generation_config)."""
         dims = WhisperDims.from_hf_config(model.config)
         gen = GenerationSettings.from_hf(model.generation_config)
-        return cls(model.state_dict(), dims, tokenizer, gen, devices, max_batch)
+        return cls(model.state_dict(), dims, tokenizer, gen, devices, max_batch, contexts_per_device=contexts_per_device)
 
     # -------------------------------------------------------------------------------- call
     def __call__(self, inputs, chunk_length_s: float = 0, stride_length_s=None, batch_size: Optional[int] = None,

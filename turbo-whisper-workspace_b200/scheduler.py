@@ -43,48 +43,75 @@ def run_in_microbatches(engine, clips: Sequence[np.ndarray], task: str, language
 
 
 class WindowScheduler:
-    def __init__(self, state_dict, dims, generation, devices: Sequence[Any] = ("cuda:0",), max_batch: int = 24,
-                 engine_factory: Optional[Callable[..., Any]] = None):
-        if engine_factory is None:
-            from .engine import WhisperEngine
+    """One process; ``contexts_per_device`` engine contexts per local GPU, each driven by its own host thread and
+    CUDA stream and sharing one copy of the weights.  Work is handed out as micro-batches of ``max_batch``
+    consecutive windows from one queue per device, so that a context's latency-bound decode overlaps another
+    context's tensor-bound encoder (and another decode) on the same GPU."""
 
-            def engine_factory(device):
-                return WhisperEngine(dims, state_dict, device=device, gen=generation, max_batch=max_batch)
+    def __init__(self, state_dict, dims, generation, devices: Sequence[Any] = ("cuda:0",), max_batch: int = 24,
+                 engine_factory: Optional[Callable[..., Any]] = None, contexts_per_device: int = 1):
         self.devices = list(devices)
-        self.engines = [engine_factory(d) for d in self.devices]
+        self.contexts_per_device = max(1, int(contexts_per_device))
+        self.engines: List[List[Any]] = []      # [device][context]
+        for d in self.devices:
+            ctxs = []
+            for c in range(self.contexts_per_device):
+                if engine_factory is not None:
+                    ctxs.append(engine_factory(d))
+                else:
+                    from .engine import WhisperEngine
+                    shared = ctxs[0].w if ctxs else None
+                    ctxs.append(WhisperEngine(dims, state_dict if shared is None else None, device=d, gen=generation,
+                                              max_batch=max_batch, shared_weights=shared,
+                                              own_stream=self.contexts_per_device > 1))
+            self.engines.append(ctxs)
         self.last_stats: Dict[str, Any] = {}
+
+    @property
+    def flat_engines(self) -> List[Any]:
+        return [e for ctxs in self.engines for e in ctxs]
 
     def run(self, clips: Sequence[np.ndarray], task: str = "transcribe", language: Optional[str] = None
             ) -> List[List[int]]:
         t0 = time.perf_counter()
         n = len(clips)
-        ranges = partition(n, len(self.engines))
-        results: List[Optional[List[List[int]]]] = [None] * len(self.engines)
-        errors: List[Optional[BaseException]] = [None] * len(self.engines)
+        ranges = partition(n, len(self.devices))
+        results: List[Optional[List[int]]] = [None] * n
+        errors: List[BaseException] = []
+        lock = threading.Lock()
+        threads = []
+        for di, (s, e) in enumerate(ranges):
+            ctxs = self.engines[di]
+            mb = ctxs[0].max_batch
+            queue = [(i, min(i + mb, e)) for i in range(s, e, mb)]   # micro-batches of this device, in order
 
-        def work(i):
-            s, e = ranges[i]
-            try:
-                results[i] = run_in_microbatches(self.engines[i], clips[s:e], task, language) if e > s else []
-            except BaseException as ex:  # surfaced on the calling thread
-                errors[i] = ex
+            def work(engine, queue=queue):
+                try:
+                    while True:
+                        with lock:
+                            if not queue or errors:
+                                return
+                            a, b = queue.pop(0)
+                        rows = engine.generate_from_pcm(clips[a:b], task=task, language=language)
+                        results[a:b] = rows
+                except BaseException as ex:  # surfaced on the calling thread
+                    with lock:
+                        errors.append(ex)
 
-        if len(self.engines) == 1:
-            work(0)
+            for eng in ctxs:
+                threads.append(threading.Thread(target=work, args=(eng,), daemon=True))
+        if len(threads) == 1:
+            threads[0].run()
         else:
-            threads = [threading.Thread(target=work, args=(i,), daemon=True) for i in range(len(self.engines))]
             for t in threads:
                 t.start()
             for t in threads:
                 t.join()
-        for ex in errors:
-            if ex is not None:
-                raise ex
-        rows: List[List[int]] = []
-        for r in results:
-            rows.extend(r or [])
-        self.last_stats = {"workers": len(self.engines), "ranges": ranges, "seconds": time.perf_counter() - t0}
-        return rows
+        if errors:
+            raise errors[0]
+        self.last_stats = {"workers": len(self.devices), "contexts_per_device": self.contexts_per_device,
+                           "ranges": ranges, "seconds": time.perf_counter() - t0}
+        return [r for r in results]
 
     def close(self):
         self.engines = []
