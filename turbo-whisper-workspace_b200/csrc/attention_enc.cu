@@ -6,74 +6,104 @@
 // which is exact for a power of two).
 //
 // Input is the fused QKV projection output [B*T, 3*D] bf16 (q | k | v, head h at columns 64h..).
-// One CTA = one (batch, head, 128-query tile).  192 threads: warp 0 TMA producer, warp 1 MMA
-// issuer, warps 2-5 softmax / accumulation (one query row per thread, no shuffles).
+// One CTA = one (batch, head) and TWO 128-query tiles (A, B) that ping-pong on the tensor pipe.  320 threads:
+// warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 / 6-9 softmax + accumulation of tile A / B (one query row
+// per thread, no shuffles).  While the threads of A run the softmax of kv-tile j, the tensor core computes
+// S_B(j), P_B V(j-1) ... : MMA order S_A(0) S_B(0) | PV_A(j) S_A(j+1) PV_B(j) S_B(j+1) | ...
 //   S  = Q K_j^T      tcgen05.mma 128x128x64  -> TMEM cols [0,128)
 //   P  = exp2(S - m)  softmax threads, written to smem as the bf16 K-major SW128 A-operand
 //   O_j = P V_j       tcgen05.mma 128x64x128 (V consumed MN-major straight from its TMA tile)
 //                     -> TMEM cols [128,192); threads fold it into fp32 registers with the usual
 //                     online-softmax rescale.
-// 96 KB smem and 256 TMEM columns per CTA so two CTAs share an SM and overlap each other's
-// softmax and MMA phases.
+// K/V tiles are shared by both query tiles (half the smem / L2 traffic per query); 160 KB smem and 384 of the 512
+// TMEM columns per CTA (S_A, S_B, O_A, O_B).
 #include "common.cuh"
 #include "twb200_internal.h"
 
 namespace tw {
 namespace attn {
 
-constexpr int BQ = 128;   // query rows per CTA
+constexpr int BQ = 128;   // query rows per tile; a CTA owns two tiles (A, B) that ping-pong
 constexpr int BKV = 128;  // keys per iteration
 constexpr int DH = 64;
-constexpr int NUM_THREADS = 192;
-constexpr int TILE_BYTES = 128 * DH * 2;  // 16 KB: Q, K, V tiles and each half of P
-constexpr int TMEM_COLS = 256;
-constexpr int S_COL = 0;
-constexpr int O_COL = 128;
-constexpr int SMEM_BYTES = 6 * TILE_BYTES + 1024 + 128;  // Q, K0, K1, V, P_lo, P_hi
+constexpr int NUM_THREADS = 320;           // warp 0 TMA, warp 1 MMA, warps 2-5 softmax A, warps 6-9 softmax B
+constexpr int TILE_BYTES = 128 * DH * 2;   // 16 KB: Q, K, V tiles and each half of P
+constexpr int TMEM_COLS = 512;
+constexpr int S_COL = 0;                   // S_A [0,128)   S_B [128,256)
+constexpr int O_N = 80;                    // 64 output columns + 16 row-sum columns (V is extended by a block of ones)
+constexpr int O_COL = 256;                 // O_A [256,336) O_B [336,416); row sums at O_COL + 64
+constexpr int ONES_BYTES = 2048;           // 16 key rows x 128 B of bf16 1.0: second MN atom of the PV B operand
+// smem tiles: Q_A Q_B | K0 K1 | V0 V1 | ones.  P never touches shared memory: the softmax threads store it (bf16,
+// two keys per 32-bit column) into the first 64 TMEM columns of their own S tile and tcgen05.mma reads the A
+// operand from tensor memory.
+constexpr int SMEM_BYTES = 6 * TILE_BYTES + ONES_BYTES + 1024 + 256;
 constexpr float LOG2E = 1.4426950408889634f;
+
+// single-instruction exp2 (MUFU.EX2, flush-to-zero): arguments here are <= 0, so the slow path of exp2f()
+// (denormal-input scaling, 4 extra instructions per element) is never needed
+// two exponentials per MUFU op on bf16 pairs: the result is directly the packed bf16 P operand.  The argument
+// is rounded to bf16 first (|error| <= 2^-9 |x| in the exponent, below the bf16 rounding of P itself for the
+// entries that carry weight).
+TW_DEVINL uint32_t ex2_bf16x2(uint32_t x) {
+    uint32_t y;
+    asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(y) : "r"(x));
+    return y;
+}
+TW_DEVINL float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 struct Params {
     int T, H, D;        // sequence length, heads, model width (H*64)
     long long out_ld;   // elements
     __nv_bfloat16* out;
+    long long* dbg;   // optional clock64 trace of CTA (0,0,0): [0..63] MMA thread, [64..] softmax A row 0
 };
 
-__global__ void __launch_bounds__(NUM_THREADS, 2)
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 attention_enc_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;
-    uint8_t* sK = smem + TILE_BYTES;       // 2 stages
-    uint8_t* sV = smem + 3 * TILE_BYTES;
-    uint8_t* sP = smem + 4 * TILE_BYTES;   // 2 halves (keys 0-63, 64-127)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * TILE_BYTES);
+    uint8_t* sQ = smem;                       // 2 tiles
+    uint8_t* sK = smem + 2 * TILE_BYTES;      // 2 stages
+    uint8_t* sV = smem + 4 * TILE_BYTES;      // 2 stages
+    uint8_t* sOnes = smem + 6 * TILE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * TILE_BYTES + ONES_BYTES);
     uint64_t* q_full = bars + 0;
     uint64_t* k_full = bars + 1;   // [2]
     uint64_t* k_empty = bars + 3;  // [2]
-    uint64_t* v_full = bars + 5;
-    uint64_t* v_empty = bars + 6;
-    uint64_t* s_full = bars + 7;
-    uint64_t* p_full = bars + 8;
-    uint64_t* o_full = bars + 9;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 10);
+    uint64_t* v_full = bars + 5;   // [2]
+    uint64_t* v_empty = bars + 7;  // [2]
+    uint64_t* s_full = bars + 9;   // [2] per group
+    uint64_t* p_full = bars + 11;  // [2] per group
+    uint64_t* o_full = bars + 13;  // [2] per group
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 15);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
+    const int q0 = blockIdx.x * (2 * BQ), h = blockIdx.y, b = blockIdx.z;
     const int nkv = (p.T + BKV - 1) / BKV;
+    const bool trace = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+    int ti = 0;
+#define TRACE(base) do { if (trace && ti < 60) p.dbg[(base) + ti++] = clock64(); } while (0)
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQKV);
         mbar_init(q_full, 1);
-        mbar_init(&k_full[0], 1); mbar_init(&k_full[1], 1);
-        mbar_init(&k_empty[0], 1); mbar_init(&k_empty[1], 1);
-        mbar_init(v_full, 1); mbar_init(v_empty, 1);
-        mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(o_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
+            mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+            mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&o_full[i], 1);
+        }
         fence_barrier_init();
     }
     if (warp == 1) {
         tmem_alloc(tmem_ptr_smem, TMEM_COLS);
         tmem_relinquish();
     }
+    for (int i = threadIdx.x; i < ONES_BYTES / 4; i += NUM_THREADS) reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3F803F80u;  // bf16 1.0 pairs
+    fence_proxy_async_smem();
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
@@ -81,142 +111,212 @@ attention_enc_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
 
     if (warp == 0) {
         if (lane == 0) {
-            mbar_arrive_expect_tx(q_full, TILE_BYTES);
+            mbar_arrive_expect_tx(q_full, 2 * TILE_BYTES);
             tma_load_3d(&tmQKV, q_full, sQ, h * DH, q0, b);
+            tma_load_3d(&tmQKV, q_full, sQ + TILE_BYTES, h * DH, q0 + BQ, b);
             for (int j = 0; j < nkv; ++j) {
                 const int s = j & 1;
-                const uint32_t kph = (j >> 1) & 1;
-                mbar_wait(&k_empty[s], kph ^ 1);
+                const uint32_t ph = (j >> 1) & 1;
+                mbar_wait(&k_empty[s], ph ^ 1);
                 mbar_arrive_expect_tx(&k_full[s], TILE_BYTES);
                 tma_load_3d(&tmQKV, &k_full[s], sK + s * TILE_BYTES, p.D + h * DH, j * BKV, b);
-                mbar_wait(v_empty, (j & 1) ^ 1);
-                mbar_arrive_expect_tx(v_full, TILE_BYTES);
-                tma_load_3d(&tmQKV, v_full, sV, 2 * p.D + h * DH, j * BKV, b);
+                mbar_wait(&v_empty[s], ph ^ 1);
+                mbar_arrive_expect_tx(&v_full[s], TILE_BYTES);
+                tma_load_3d(&tmQKV, &v_full[s], sV + s * TILE_BYTES, 2 * p.D + h * DH, j * BKV, b);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc_s = umma_idesc_bf16(BQ, BKV, 0, 0);
-            constexpr uint32_t idesc_o = umma_idesc_bf16(BQ, DH, 0, 1);  // B (= V) is MN-major
-            const uint32_t q_addr = smem_u32(sQ), v_addr = smem_u32(sV), p_addr = smem_u32(sP);
-            mbar_wait(q_full, 0);
-            for (int j = 0; j < nkv; ++j) {
-                const int s = j & 1;
-                const uint32_t ph = j & 1;
-                mbar_wait(&k_full[s], (j >> 1) & 1);
-                tcgen05_fence_after();
-                const uint32_t k_addr = smem_u32(sK + s * TILE_BYTES);
+            constexpr uint32_t idesc_o = umma_idesc_bf16(BQ, O_N, 0, 1);  // B = [V | ones] is MN-major, N = 80
+            // Every descriptor is loop-invariant: build them once.  The single issuing thread must spend ~2
+            // instructions per tcgen05.mma, not ~30, because these MMAs only last 32-64 cycles each.
+            uint64_t dq[2][DH / 16], dk[2][DH / 16], dv[2][BKV / 16];
+#pragma unroll
+            for (int k = 0; k < DH / 16; ++k) {
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    dq[g][k] = umma_desc_sw128(smem_u32(sQ) + g * TILE_BYTES + k * 32, 16, 1024);
+                    dk[g][k] = umma_desc_sw128(smem_u32(sK) + g * TILE_BYTES + k * 32, 16, 1024);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < BKV / 16; ++k) {
+#pragma unroll
+                for (int st = 0; st < 2; ++st) {
+                    const uint32_t va = smem_u32(sV) + st * TILE_BYTES + k * 2048;
+                    // MN atom 0 = the 64 head-dim columns of V (16 key rows x 128 B); atom 1 (LBO away) = ones
+                    dv[st][k] = umma_desc_sw128(va, smem_u32(sOnes) - va, 1024);
+                }
+            }
+            auto issue_s = [&](int g, int j) {   // S_g = Q_g K_j^T
+                const int st = j & 1;
 #pragma unroll
                 for (int k = 0; k < DH / 16; ++k)
-                    tcgen05_mma_f16(tmem_base + S_COL, umma_desc_sw128(q_addr + k * 32, 16, 1024),
-                                    umma_desc_sw128(k_addr + k * 32, 16, 1024), idesc_s, k != 0);
-                tcgen05_commit(s_full);
-                tcgen05_commit(&k_empty[s]);
-                mbar_wait(p_full, ph);
-                mbar_wait(v_full, ph);
-                tcgen05_fence_after();
+                    tcgen05_mma_f16(tmem_base + S_COL + g * BKV, dq[g][k], dk[st][k], idesc_s, k != 0);
+                tcgen05_commit(&s_full[g]);
+            };
+            auto issue_pv = [&](int g, int j) {  // [O_g | rowsum_g] += P_g [V_j | 1]   (A = P from TMEM)
+                const int st = j & 1;
+                const uint32_t p_tmem = tmem_base + S_COL + g * BKV;   // P aliases the first 64 columns of S_g
+                const uint32_t acc0 = j != 0;
 #pragma unroll
                 for (int k = 0; k < BKV / 16; ++k)
-                    tcgen05_mma_f16(tmem_base + O_COL,
-                                    umma_desc_sw128(p_addr + (k >> 2) * TILE_BYTES + (k & 3) * 32, 16, 1024),
-                                    umma_desc_sw128(v_addr + k * 2048, 16, 1024), idesc_o, k != 0);
-                tcgen05_commit(o_full);
-                tcgen05_commit(v_empty);
+                    tcgen05_mma_f16_ts(tmem_base + O_COL + g * O_N, p_tmem + k * 8, dv[st][k], idesc_o, k != 0 ? 1u : acc0);
+                tcgen05_commit(&o_full[g]);
+            };
+            TRACE(0);
+            mbar_wait(q_full, 0);
+            mbar_wait(&k_full[0], 0);
+            TRACE(0);
+            tcgen05_fence_after();
+            issue_s(0, 0);
+            issue_s(1, 0);
+            tcgen05_commit(&k_empty[0]);
+            for (int j = 0; j < nkv; ++j) {
+                const uint32_t ph = j & 1;
+                const bool more = j + 1 < nkv;
+                mbar_wait(&p_full[0], ph);
+                TRACE(0);
+                mbar_wait(&v_full[j & 1], (j >> 1) & 1);
+                tcgen05_fence_after();
+                issue_pv(0, j);
+                if (more) {
+                    mbar_wait(&k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+                    tcgen05_fence_after();
+                    issue_s(0, j + 1);
+                }
+                mbar_wait(&p_full[1], ph);
+                TRACE(0);
+                tcgen05_fence_after();
+                issue_pv(1, j);
+                tcgen05_commit(&v_empty[j & 1]);
+                if (more) {
+                    issue_s(1, j + 1);
+                    tcgen05_commit(&k_empty[(j + 1) & 1]);
+                }
             }
         }
     } else {
-        const int quarter = warp & 3;
+        const int grp = (warp - 2) >> 2;    // 0: tile A, 1: tile B
+        const int quarter = warp & 3;       // TMEM lane quarter this warp may access
         const int r = quarter * 32 + lane;  // query row within the tile == TMEM lane
         const uint32_t t_lane = (uint32_t)(quarter * 32) << 16;
-        float m = -INFINITY, l = 0.f;
-        float acc[DH];
-#pragma unroll
-        for (int i = 0; i < DH; ++i) acc[i] = 0.f;
-        uint8_t* p_row = sP + r * 128;
-        const int sw = r & 7;
+        const uint32_t s_col = S_COL + grp * BKV, o_col = O_COL + grp * O_N, l_col = o_col + DH;
+        // O and the row sums accumulate in TMEM across kv tiles (tcgen05.mma accumulate); S is read from TMEM
+        // exactly once per tile (TMEM read bandwidth is the scarce resource).  The softmax reference point
+        // m_used only moves when the running maximum grows by more than RESCALE_LOG2 (lazy rescaling: P <= 2^8,
+        // mathematically identical after the final O / rowsum division); a move rescales O and rowsum in TMEM.
+        constexpr float RESCALE_LOG2 = 8.0f;
+        float m_used = -INFINITY;   // in log2 units (score * log2e)
 
         for (int j = 0; j < nkv; ++j) {
             const uint32_t ph = j & 1;
             const int kvalid = p.T - j * BKV;  // keys >= kvalid are padding (TMA zero-fill)
-            mbar_wait(s_full, ph);
+            const bool full = kvalid >= BKV;
+            if (grp == 0 && r == 0) TRACE(64);
+            mbar_wait(&s_full[grp], ph);
+            if (j > 0) mbar_wait(&o_full[grp], (j - 1) & 1);
+            if (grp == 0 && r == 0) TRACE(64);  // PV(j-1) done (implied by S(j) done; keeps phases in step)
             tcgen05_fence_after();
-            // pass 1: row max
-            float mx = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < BKV / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(tmem_base + t_lane + S_COL + c * 32, v);
-                tmem_ld_wait();
-                if (c * 32 + 32 <= kvalid) {
+            uint32_t v[BKV];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+            for (int c = 0; c < BKV / 32; ++c)
+                tmem_ld_32x32b_x32(tmem_base + t_lane + s_col + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
+            tmem_ld_wait();
+            if (grp == 0 && r == 0) TRACE(64);
+            float mx = -INFINITY;
+            if (full) {
+                float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // independent chains
+#pragma unroll
+                for (int i = 0; i < BKV; i += 4) {
+                    m4[0] = fmaxf(m4[0], __uint_as_float(v[i]));
+                    m4[1] = fmaxf(m4[1], __uint_as_float(v[i + 1]));
+                    m4[2] = fmaxf(m4[2], __uint_as_float(v[i + 2]));
+                    m4[3] = fmaxf(m4[3], __uint_as_float(v[i + 3]));
+                }
+                mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+            } else {
+#pragma unroll
+                for (int i = 0; i < BKV; ++i)
+                    if (i < kvalid) mx = fmaxf(mx, __uint_as_float(v[i]));
+            }
+            const float mx2 = mx * LOG2E;
+            const bool move = mx2 > m_used + RESCALE_LOG2;   // always true on the first tile (m_used = -inf)
+            const float alpha = move ? ex2_approx(m_used - mx2) : 1.0f;   // first tile: exp2(-inf) = 0, O is overwritten
+            if (move) m_used = mx2;
+            const float mb = m_used;
+#pragma unroll
+            for (int c = 0; c < BKV / 32; ++c) {
+                uint32_t pk[16];
+                if (full || c * 32 + 32 <= kvalid) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        pk[i] = ex2_bf16x2(pack_bf16x2(fmaf(__uint_as_float(v[c * 32 + 2 * i]), LOG2E, -mb),
+                                                       fmaf(__uint_as_float(v[c * 32 + 2 * i + 1]), LOG2E, -mb)));
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (c * 32 + i < kvalid) mx = fmaxf(mx, __uint_as_float(v[i]));
+                    for (int i = 0; i < 16; ++i) {
+                        const float a0 = (c * 32 + 2 * i < kvalid) ? fmaf(__uint_as_float(v[c * 32 + 2 * i]), LOG2E, -mb) : -INFINITY;
+                        const float a1 = (c * 32 + 2 * i + 1 < kvalid) ? fmaf(__uint_as_float(v[c * 32 + 2 * i + 1]), LOG2E, -mb) : -INFINITY;
+                        pk[i] = ex2_bf16x2(pack_bf16x2(a0, a1));
+                    }
                 }
+                // keys [32c, 32c+32) of this row -> TMEM columns [16c, 16c+16) of the P tile (aliases S_g, already in registers)
+                asm volatile(
+                    "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+                    "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                    :
+                    : "r"(tmem_base + t_lane + s_col + c * 16), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]),
+                      "r"(pk[5]), "r"(pk[6]), "r"(pk[7]), "r"(pk[8]), "r"(pk[9]), "r"(pk[10]), "r"(pk[11]), "r"(pk[12]),
+                      "r"(pk[13]), "r"(pk[14]), "r"(pk[15])
+                    : "memory");
             }
-            const float m_new = fmaxf(m, mx);
-            const float alpha = exp2f((m - m_new) * LOG2E);  // m = -inf on the first tile -> 0
-            const float mb = m_new * LOG2E;
-            m = m_new;
-            // pass 2: P = exp2(s*log2e - m*log2e), row sum, bf16 pack into the swizzled A tile
-            float rs = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < BKV / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(tmem_base + t_lane + S_COL + c * 32, v);
-                tmem_ld_wait();
-                float e[32];
+            // rescale the TMEM accumulators of this row when its reference point moved (warp-collective ld/st)
+            if (j > 0 && __any_sync(0xffffffffu, move)) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float x = exp2f(fmaf(__uint_as_float(v[i]), LOG2E, -mb));
-                    e[i] = (c * 32 + i < kvalid) ? x : 0.f;
-                    rs += e[i];
+                for (int c = 0; c < DH / 32; ++c) {
+                    uint32_t o[32];
+                    tmem_ld_32x32b_x32(tmem_base + t_lane + o_col + c * 32, o);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                    tmem_st_32x32b_x32(tmem_base + t_lane + o_col + c * 32, o);
                 }
-                uint8_t* dst = p_row + (c >> 1) * TILE_BYTES;
+                const uint32_t ls = tmem_ld_32x32b_x1(tmem_base + t_lane + l_col);
+                tmem_ld_wait();
+                tmem_st_32x32b_x1(tmem_base + t_lane + l_col, __float_as_uint(__uint_as_float(ls) * alpha));
+            }
+            tmem_st_wait();
+            if (grp == 0 && r == 0) TRACE(64);
+            tcgen05_fence_before();
+            mbar_arrive(&p_full[grp]);
+        }
+        mbar_wait(&o_full[grp], (nkv - 1) & 1);
+        tcgen05_fence_after();
+        const int q = q0 + grp * BQ + r;
+        const uint32_t ls = tmem_ld_32x32b_x1(tmem_base + t_lane + l_col);
+        tmem_ld_wait();
+        const float inv = 1.0f / __uint_as_float(ls);
+        __nv_bfloat16* o = p.out + ((size_t)b * p.T + q) * p.out_ld + h * DH;
+#pragma unroll
+        for (int c = 0; c < DH / 32; ++c) {
+            uint32_t acc[32];
+            tmem_ld_32x32b_x32(tmem_base + t_lane + o_col + c * 32, acc);
+            tmem_ld_wait();
+            if (q < p.T) {
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
-                    const int chunk = (c & 1) * 4 + g;  // 16-byte chunk within the 128-byte row
                     uint4 pk;
-                    pk.x = pack_bf16x2(e[g * 8 + 0], e[g * 8 + 1]);
-                    pk.y = pack_bf16x2(e[g * 8 + 2], e[g * 8 + 3]);
-                    pk.z = pack_bf16x2(e[g * 8 + 4], e[g * 8 + 5]);
-                    pk.w = pack_bf16x2(e[g * 8 + 6], e[g * 8 + 7]);
-                    *reinterpret_cast<uint4*>(dst + ((chunk ^ sw) << 4)) = pk;
+                    pk.x = pack_bf16x2(__uint_as_float(acc[g * 8 + 0]) * inv, __uint_as_float(acc[g * 8 + 1]) * inv);
+                    pk.y = pack_bf16x2(__uint_as_float(acc[g * 8 + 2]) * inv, __uint_as_float(acc[g * 8 + 3]) * inv);
+                    pk.z = pack_bf16x2(__uint_as_float(acc[g * 8 + 4]) * inv, __uint_as_float(acc[g * 8 + 5]) * inv);
+                    pk.w = pack_bf16x2(__uint_as_float(acc[g * 8 + 6]) * inv, __uint_as_float(acc[g * 8 + 7]) * inv);
+                    reinterpret_cast<uint4*>(o)[c * 4 + g] = pk;
                 }
             }
-            l = l * alpha + rs;
-            fence_proxy_async_smem();  // make the generic-proxy smem writes visible to tcgen05.mma
-            tcgen05_fence_before();
-            mbar_arrive(p_full);
-            // fold O_j into the running output
-            mbar_wait(o_full, ph);
-            tcgen05_fence_after();
-#pragma unroll
-            for (int c = 0; c < DH / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(tmem_base + t_lane + O_COL + c * 32, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) acc[c * 32 + i] = fmaf(acc[c * 32 + i], alpha, __uint_as_float(v[i]));
-            }
-            tcgen05_fence_before();
         }
-        const int q = q0 + r;
-        if (q < p.T) {
-            const float inv = 1.0f / l;
-            __nv_bfloat16* o = p.out + ((size_t)b * p.T + q) * p.out_ld + h * DH;
-#pragma unroll
-            for (int g = 0; g < DH / 8; ++g) {
-                uint4 pk;
-                pk.x = pack_bf16x2(acc[g * 8 + 0] * inv, acc[g * 8 + 1] * inv);
-                pk.y = pack_bf16x2(acc[g * 8 + 2] * inv, acc[g * 8 + 3] * inv);
-                pk.z = pack_bf16x2(acc[g * 8 + 4] * inv, acc[g * 8 + 5] * inv);
-                pk.w = pack_bf16x2(acc[g * 8 + 6] * inv, acc[g * 8 + 7] * inv);
-                reinterpret_cast<uint4*>(o)[g] = pk;
-            }
-        }
+        tcgen05_fence_before();
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -228,6 +328,9 @@ attention_enc_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
 
 }  // namespace attn
 }  // namespace tw
+
+static long long* g_attn_dbg = nullptr;
+extern "C" int tw_attention_enc_set_trace(void* dev_buf_int64_x192) { g_attn_dbg = (long long*)dev_buf_int64_x192; return 0; }
 
 extern "C" int tw_attention_enc(const void* qkv_bf16, void* out_bf16, int32_t batch, int32_t seq,
                                 int32_t heads, int64_t out_ld, void* stream) {
@@ -248,13 +351,13 @@ extern "C" int tw_attention_enc(const void* qkv_bf16, void* out_bf16, int32_t ba
                           CU_TENSOR_MAP_SWIZZLE_128B))
         return 1;
     Params p;
-    p.T = seq; p.H = heads; p.D = D; p.out_ld = out_ld; p.out = (__nv_bfloat16*)out_bf16;
+    p.T = seq; p.H = heads; p.D = D; p.out_ld = out_ld; p.out = (__nv_bfloat16*)out_bf16; p.dbg = g_attn_dbg;
     static bool attr_set = false;
     if (!attr_set) {
         TW_CUDA_CHECK(cudaFuncSetAttribute(attention_enc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_set = true;
     }
-    dim3 grid((seq + BQ - 1) / BQ, heads, batch);
+    dim3 grid((seq + 2 * BQ - 1) / (2 * BQ), heads, batch);
     attention_enc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tm, p);
     TW_CUDA_CHECK(cudaGetLastError());
     return 0;

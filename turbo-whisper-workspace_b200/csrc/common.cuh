@@ -204,6 +204,18 @@ TW_DEVINL void tcgen05_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc
         : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (128 lanes x K, two bf16 per 32-bit column) is read from tensor memory
+TW_DEVINL void tcgen05_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n"
+        :
+        : "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 TW_DEVINL void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // 32 lanes x 32 consecutive fp32 columns: thread t of the warp receives row (lane base + t)
@@ -221,6 +233,29 @@ TW_DEVINL void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
         : "memory");
 }
 
+TW_DEVINL void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        :
+        : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+          "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+          "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+TW_DEVINL void tmem_st_32x32b_x1(uint32_t taddr, uint32_t r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(r) : "memory");
+}
+TW_DEVINL void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// 32 lanes x 1 fp32 column
+TW_DEVINL uint32_t tmem_ld_32x32b_x1(uint32_t taddr) {
+    uint32_t r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+    return r;
+}
+
 // ---- UMMA shared-memory matrix descriptor (sm_100 format, version 1) --------------------------
 // bits [0,14)  start address >> 4        bits [16,30) leading-dim byte offset >> 4
 // bits [32,46) stride-dim byte offset >> 4   bits [46,48) version = 1
@@ -235,6 +270,15 @@ TW_DEVINL uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t 
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)2 << 61;
+    return d;
+}
+// no-swizzle K-major descriptor (8x16-byte core matrices; LBO = K-direction, SBO = MN-direction core stride)
+TW_DEVINL uint64_t umma_desc_noswizzle(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
     return d;
 }
 // ---- UMMA instruction descriptor, kind::f16, bf16 x bf16 -> fp32 -------------------------------
