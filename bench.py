@@ -164,12 +164,16 @@ def run_reference(args, rank, world):
               "generate(max_new_tokens=4 and 20), extrapolated to the 3 encoder + 891 decoder forwards the full "
               f"reference call runs per 30 s window; t_enc={samples[-1]['t_enc']:.2f}s t_dec_step="
               f"{samples[-1]['t_dec_step'] * 1e3:.1f}ms")
-    line = {"impl": "reference", "metric": "RTFx (audio s / wall s), large-v3-turbo, CPU fp32 reference path",
+    line = {"impl": "reference", "metric": "RTFx (audio s / wall s), large-v3-turbo bf16",
             "value": rtfx, "unit": "x realtime", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t * 1e3 * WINDOWS_PER_GPU, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "whisper-large-v3-turbo, 24 x 30 s windows per GPU (configs[1]); reference arm runs "
-                                   "its own CPU path window by window", "windows_per_gpu": WINDOWS_PER_GPU},
+            "config": {"workload": "whisper-large-v3-turbo bf16, 24 x 30 s windows per GPU per step (BASELINE.json "
+                                   "configs[1]); random-init weights (HF init, seed 0), 0.1*N(0,1) audio; greedy, "
+                                   "timestamps, HF short-form seek loop",
+                       "windows_per_gpu": WINDOWS_PER_GPU,
+                       "reference_arm": "the reference's own CPU implementation of the path (transformers Whisper "
+                                        "classes, fp32, greedy), rank 0 only, one bounded window sample per step"},
             "cpu_baseline": {"value": rtfx, "unit": "x realtime", "cores": torch.get_num_threads(), "kind": "port",
                              "sample": sample},
             "e2e": {"value": rtfx, "unit": "x realtime", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -372,12 +376,13 @@ def run_own(args, rank, world, local_rank):
             "roofline": {"bound": "hbm", "kernel": "decode_attn_kernel (cross-attention over the encoder K/V; largest "
                                                    "single kernel of a step by time)",
                          "achieved": ca_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ca_gbs / pk["hbm_gbs"],
-                         "traffic": None, "peak_source": pk["source"], "bytes_per_launch": ca_bytes,
-                         "ms_per_launch": ca_ms},
+                         "traffic": 189.84e6 if B == 24 else None,   # dram read+write per launch, ncu --set full (profiles/r1e_summary.md)
+                         "peak_source": pk["source"], "bytes_per_launch": ca_bytes, "ms_per_launch": ca_ms},
             "roofline_encoder_gemm": {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05; encoder qkv/out/fc1/fc2 "
                                       "shapes, fused bias/GELU/residual)", "achieved": gemm_tf,
                                       "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": gemm_tf / pk["bf16_tflops"],
-                                      "traffic": None, "peak_source": pk["source"] + " burst",
+                                      "traffic": 332.7e6 if B == 24 else None,   # qkv-shape launch, ncu (profiles/r1e_summary.md)
+                                      "peak_source": pk["source"] + " burst",
                                       "flops_per_launch": gemm_flops, "ms_per_launch": gemm_ms},
             "output_check": {"chunks": len(result["chunks"]) if isinstance(result, dict) else None,
                              "tokens_first_row": len(rows[0]) if rows else None},
