@@ -117,7 +117,7 @@ class WhisperRef:
         s = q @ k.transpose(-1, -2)
         if causal and T > 1:
             S = k.shape[2]
-            mask = torch.ones(T, S, dtype=torch.bool).tril(diagonal=S - T)
+            mask = torch.ones(T, S, dtype=torch.bool, device=s.device).tril(diagonal=S - T)
             s = s.masked_fill(~mask, float("-inf"))
         p = torch.softmax(s, dim=-1)
         o = (p @ v).transpose(1, 2).reshape(B, T, H * dh)
