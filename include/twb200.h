@@ -107,6 +107,9 @@ int tw_gemm_bf16(const tw_gemm_args* args, void* stream);
  * ---------------------------------------------------------------------------------------------- */
 int tw_attention_enc(const void* qkv_bf16, void* out_bf16, int32_t batch, int32_t seq, int32_t heads,
                      int64_t out_ld, void* stream);
+/* profiling hook: device int64[192] that CTA (0,0,0) fills with clock64() stamps of its MMA thread ([0,64)) and of
+ * query row 0's softmax thread ([64,128)); NULL disables (default). */
+int tw_attention_enc_set_trace(void* dev_buf_int64_x192);
 
 /* Gather a seek-shifted 30 s window of time-major features (WhisperGenerationMixin._get_input_segment,
  * $TF/models/whisper/generation_whisper.py:1831-1850): dst[b, row_off + t, :] =

@@ -62,6 +62,7 @@ SIGNATURES = {
                                 c_void_p, c_void_p, c_void_p]),
     "tw_dec_finalize": (C.c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_void_p,
                                   C.POINTER(Grammar), c_int32, c_void_p]),
+    "tw_attention_enc_set_trace": (C.c_int, [c_void_p]),
     "tw_shift_frames": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int64,
                                   c_int32, c_void_p]),
 }

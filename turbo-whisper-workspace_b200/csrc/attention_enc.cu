@@ -173,27 +173,27 @@ attention_enc_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
             issue_s(0, 0);
             issue_s(1, 0);
             tcgen05_commit(&k_empty[0]);
-            for (int j = 0; j < nkv; ++j) {
-                const uint32_t ph = j & 1;
-                const bool more = j + 1 < nkv;
-                mbar_wait(&p_full[0], ph);
-                TRACE(0);
-                mbar_wait(&v_full[j & 1], (j >> 1) & 1);
-                tcgen05_fence_after();
-                issue_pv(0, j);
-                if (more) {
-                    mbar_wait(&k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+            // The two query tiles are served in whatever order their P tiles become ready (non-blocking polls), so a
+            // slow softmax of one tile never delays the MMAs of the other.  K/V stages are released once both tiles
+            // have issued the MMAs that read them; a tile can therefore run at most one kv tile ahead of the other.
+            int jg[2] = {0, 0};          // next PV index per tile
+            while (jg[0] < nkv || jg[1] < nkv) {
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    const int j = jg[g];
+                    if (j >= nkv) continue;
+                    if (!mbar_try_wait(&p_full[g], j & 1)) continue;
+                    mbar_wait(&v_full[j & 1], (j >> 1) & 1);
                     tcgen05_fence_after();
-                    issue_s(0, j + 1);
-                }
-                mbar_wait(&p_full[1], ph);
-                TRACE(0);
-                tcgen05_fence_after();
-                issue_pv(1, j);
-                tcgen05_commit(&v_empty[j & 1]);
-                if (more) {
-                    issue_s(1, j + 1);
-                    tcgen05_commit(&k_empty[(j + 1) & 1]);
+                    issue_pv(g, j);
+                    if (jg[g ^ 1] > j) tcgen05_commit(&v_empty[j & 1]);          // second reader of V_j
+                    if (j + 1 < nkv) {
+                        mbar_wait(&k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+                        tcgen05_fence_after();
+                        issue_s(g, j + 1);
+                        if (jg[g ^ 1] > j) tcgen05_commit(&k_empty[(j + 1) & 1]);  // second reader of K_{j+1}
+                    }
+                    jg[g] = j + 1;
                 }
             }
         }
