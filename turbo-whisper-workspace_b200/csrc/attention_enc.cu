@@ -337,6 +337,7 @@ extern "C" int tw_attention_enc(const void* qkv_bf16, void* out_bf16, int32_t ba
     using namespace tw;
     using namespace tw::attn;
     TW_REQUIRE(qkv_bf16 && out_bf16, "tw_attention_enc: null argument");
+    if (tw::ensure_device(qkv_bf16)) return 1;
     TW_REQUIRE(batch >= 0 && seq > 0 && heads > 0, "tw_attention_enc: bad shape");
     TW_REQUIRE(batch <= 65535 && heads <= 65535, "tw_attention_enc: grid dimension too large");
     TW_REQUIRE(out_ld % 8 == 0 && ((uintptr_t)qkv_bf16 & 15) == 0 && ((uintptr_t)out_bf16 & 15) == 0,

@@ -304,6 +304,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 2 : 1) skinny_gemm_
         __syncthreads();
         if (s_last) {
             __threadfence();
+            // (batching the rows of a warp, or 8 lanes per row, both measured slower than this simple form)
             for (int r = warp; r < p.B; r += WARPS)
                 warp_layernorm_row<true>(p.resid + (size_t)r * p.N, p.ln_g, p.ln_b, p.ln_out + (size_t)r * p.N, p.N, lane);
         }
@@ -381,58 +382,72 @@ __global__ void __launch_bounds__(256, 1) lmhead_kernel(const SkinnyParams p) {
             }
         }
         // acc[j][e]: vocab row n0+g (e<2) / n0+g+8 (e>=2), batch row j*8 + 2*tg + (e&1)
+        // Slab-level facts are warp-uniform: the 16 suppress bits of the slab come from one 32-bit word, and a slab
+        // is all-text (99 % of them), all-timestamp or the single mixed one, so the unused reduction is skipped.
+        const uint32_t sup16 = (p.suppress_bits[n0 >> 5] >> (n0 & 16)) & 0xffffu;
+        const uint32_t bsup16 = (p.begin_suppress_bits[n0 >> 5] >> (n0 & 16)) & 0xffffu;
+        const bool slab_has_text = n0 < p.gc.ts_begin;
+        const bool slab_has_ts = n0 + 16 > p.gc.ts_begin;
 #pragma unroll
         for (int c = 0; c < NB * 2; ++c) {
             const int j = c >> 1, e = c & 1;
             const int bb = j * 8 + 2 * tg + e;
+            const RowState& rs = st[c];
             float vt = -INFINITY, vs = -INFINITY;
             int jt = 0x7fffffff, js = 0x7fffffff;
+            bool ts_ok[2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const int n = n0 + g + 8 * h;
+                const int rr = g + 8 * h;
+                const int n = n0 + rr;
                 const float v = acc[j][e + 2 * h];
+                ts_ok[h] = false;
                 if (bb < p.B && n < p.N) {
                     if (p.logits_out) p.logits_out[(size_t)bb * p.N + n] = v;
-                    if (token_allowed(n, st[c], p.gc, p.suppress_bits, p.begin_suppress_bits)) {
-                        if (n >= p.gc.ts_begin && st[c].mode == 0) {
+                    bool ok;
+                    if (rs.mode == 1) ok = n >= p.gc.lang_first && n <= p.gc.lang_last;
+                    else ok = !((sup16 >> rr) & 1u) && !(rs.begin && ((bsup16 >> rr) & 1u)) && n != p.gc.no_timestamps &&
+                              (n >= p.gc.ts_begin ? (n >= rs.ts_lo && n <= rs.ts_hi) : n >= rs.text_lo);
+                    if (ok) {
+                        if (n >= p.gc.ts_begin && rs.mode == 0) {
+                            ts_ok[h] = true;
                             if (v > vs) { vs = v; js = n; }   // rows ascend with h: ties keep the lower id
                         } else if (v > vt) { vt = v; jt = n; }
                     }
                 }
             }
             // reduce over the 8 lanes that share tg (vocab rows g = 0..7): xor 4, 8, 16
-            float ms = vs;
-            int ks = js;
+            if (slab_has_text) {
 #pragma unroll
-            for (int d = 4; d < 32; d <<= 1) {
-                const float ot = __shfl_xor_sync(0xffffffffu, vt, d);
-                const int oi = __shfl_xor_sync(0xffffffffu, jt, d);
-                if (ot > vt || (ot == vt && oi < jt)) { vt = ot; jt = oi; }
-                const float os = __shfl_xor_sync(0xffffffffu, ms, d);
-                const int oj = __shfl_xor_sync(0xffffffffu, ks, d);
-                if (os > ms || (os == ms && oj < ks)) { ms = os; ks = oj; }
+                for (int d = 4; d < 32; d <<= 1) {
+                    const float ot = __shfl_xor_sync(0xffffffffu, vt, d);
+                    const int oi = __shfl_xor_sync(0xffffffffu, jt, d);
+                    if (ot > vt || (ot == vt && oi < jt)) { vt = ot; jt = oi; }
+                }
+                if (vt > bt[c] || (vt == bt[c] && jt < it[c])) { bt[c] = vt; it[c] = jt; }
             }
-            // sum of exp(ts logit - slab max) over this thread's (up to 2) timestamp entries, then over lanes
-            float ex = 0.f;
+            if (slab_has_ts) {
+                float ms = vs;
+                int ks = js;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int n = n0 + g + 8 * h;
-                const float v = acc[j][e + 2 * h];
-                if (bb < p.B && n < p.N && n >= p.gc.ts_begin && st[c].mode == 0 &&
-                    token_allowed(n, st[c], p.gc, p.suppress_bits, p.begin_suppress_bits))
-                    ex += __expf(v - ms);
-            }
+                for (int d = 4; d < 32; d <<= 1) {
+                    const float os = __shfl_xor_sync(0xffffffffu, ms, d);
+                    const int oj = __shfl_xor_sync(0xffffffffu, ks, d);
+                    if (os > ms || (os == ms && oj < ks)) { ms = os; ks = oj; }
+                }
+                // sum of exp(ts logit - slab max) over this thread's (up to 2) timestamp entries, then over lanes
+                float ex = (ts_ok[0] ? __expf(acc[j][e] - ms) : 0.f) + (ts_ok[1] ? __expf(acc[j][e + 2] - ms) : 0.f);
 #pragma unroll
-            for (int d = 4; d < 32; d <<= 1) ex += __shfl_xor_sync(0xffffffffu, ex, d);
-            if (vt > bt[c] || (vt == bt[c] && jt < it[c])) { bt[c] = vt; it[c] = jt; }
-            if (ms > -INFINITY) {
-                if (ms > bs[c]) {
-                    sm[c] = (bs[c] > -INFINITY ? sm[c] * __expf(bs[c] - ms) : 0.f) + ex;
-                    bs[c] = ms;
-                    is[c] = ks;
-                } else {
-                    sm[c] += ex * __expf(ms - bs[c]);
-                    if (ms == bs[c] && ks < is[c]) is[c] = ks;
+                for (int d = 4; d < 32; d <<= 1) ex += __shfl_xor_sync(0xffffffffu, ex, d);
+                if (ms > -INFINITY) {
+                    if (ms > bs[c]) {
+                        sm[c] = (bs[c] > -INFINITY ? sm[c] * __expf(bs[c] - ms) : 0.f) + ex;
+                        bs[c] = ms;
+                        is[c] = ks;
+                    } else {
+                        sm[c] += ex * __expf(ms - bs[c]);
+                        if (ms == bs[c] && ks < is[c]) is[c] = ks;
+                    }
                 }
             }
         }
@@ -747,7 +762,7 @@ __global__ void __launch_bounds__(ATT_THREADS) decode_attn_kernel(const AttnPara
 using namespace tw;
 using namespace tw::dec;
 
-static int g_use_pdl = 1;
+static int g_use_pdl = 0;  // off by default: inside CUDA graphs plain edges measured faster (212 vs 220 ms / 447 steps); eager stepping gains 10 % with it
 extern "C" int tw_set_pdl(int32_t enabled) { g_use_pdl = enabled ? 1 : 0; return 0; }
 
 // launch with the programmatic-stream-serialization attribute (the kernel's own griddepcontrol.wait orders it
@@ -794,6 +809,7 @@ extern "C" int tw_dec_embed(const int32_t* tokens, int32_t tokens_ld, const void
                             const float* pos_emb, float* x, int32_t batch, int32_t d_model, const float* ln_gamma,
                             const float* ln_beta, void* ln_out_bf16, void* stream) {
     TW_REQUIRE(tokens && row_state && tok_emb_bf16 && pos_emb && x, "tw_dec_embed: null argument");
+    if (tw::ensure_device(x)) return 1;
     TW_REQUIRE(d_model <= 2048, "tw_dec_embed: d_model %d > 2048", d_model);
     TW_REQUIRE(!ln_out_bf16 || (ln_gamma && ln_beta), "tw_dec_embed: LayerNorm output needs gamma and beta");
     if (batch <= 0) return 0;
@@ -806,6 +822,7 @@ extern "C" int tw_dec_embed(const int32_t* tokens, int32_t tokens_ld, const void
 
 static int check_skinny(const tw_skinny_args* a, const char* who) {
     TW_REQUIRE(a && a->w && a->x, "%s: null argument", who);
+    if (tw::ensure_device(a->w)) return 1;
     TW_REQUIRE(a->batch >= 1 && a->batch <= MAXB, "%s: batch %d not in [1,%d]", who, a->batch, MAXB);
     TW_REQUIRE(a->k % 256 == 0, "%s: K (%d) must be a multiple of 256", who, a->k);
     TW_REQUIRE(a->ldx % 8 == 0 && ((uintptr_t)a->x & 15) == 0 && ((uintptr_t)a->w & 15) == 0, "%s: alignment", who);
@@ -908,6 +925,7 @@ extern "C" int tw_dec_finalize(const float* part_val, const int32_t* part_idx, i
                                int32_t tokens_ld, const int32_t* forced, int32_t* choices, void* row_state,
                                const tw_grammar* g, int32_t batch, void* stream) {
     TW_REQUIRE(part_val && part_idx && tokens && forced && row_state && g, "tw_dec_finalize: null argument");
+    if (tw::ensure_device(tokens)) return 1;
     if (batch <= 0) return 0;
     FinalizeParams p;
     p.part_val = part_val; p.part_idx = part_idx; p.n_parts = n_parts; p.tokens = tokens; p.tokens_ld = tokens_ld;
@@ -921,6 +939,7 @@ extern "C" int tw_dec_self_attn(const void* q_bf16, void* out_bf16, const void* 
                                 int32_t pages_per_row, int32_t n_pages, const void* row_state, int32_t batch,
                                 int32_t heads, void* stream) {
     TW_REQUIRE(q_bf16 && out_bf16 && kv_pool_layer && block_table && row_state, "tw_dec_self_attn: null argument");
+    if (tw::ensure_device(q_bf16)) return 1;
     TW_REQUIRE(pages_per_row * PAGE <= ATT_MAXKEYS, "tw_dec_self_attn: more than %d positions", ATT_MAXKEYS);
     if (batch <= 0) return 0;
     AttnParams p{};
@@ -937,6 +956,7 @@ extern "C" int tw_dec_cross_attn(const void* q_bf16, void* out_bf16, const void*
                                  const int32_t* enc_row, int32_t src_len, int32_t batch, int32_t heads,
                                  int32_t splits, float* part, uint32_t* counters, void* stream) {
     TW_REQUIRE(q_bf16 && out_bf16 && k_bf16 && v_bf16, "tw_dec_cross_attn: null argument");
+    if (tw::ensure_device(q_bf16)) return 1;
     TW_REQUIRE(splits >= 1 && (src_len + splits - 1) / splits <= ATT_MAXKEYS,
                "tw_dec_cross_attn: %d keys / %d splits exceeds %d per CTA", src_len, splits, ATT_MAXKEYS);
     TW_REQUIRE(splits == 1 || (part && counters), "tw_dec_cross_attn: split needs scratch");

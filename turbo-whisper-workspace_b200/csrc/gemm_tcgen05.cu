@@ -256,6 +256,7 @@ using namespace tw::gemm;
 extern "C" int tw_gemm_bf16(const tw_gemm_args* a, void* stream) {
     TW_REQUIRE(a != nullptr, "tw_gemm_bf16: null args");
     TW_REQUIRE(a->a && a->w && a->out, "tw_gemm_bf16: null tensor pointer");
+    if (tw::ensure_device(a->a)) return 1;
     TW_REQUIRE(a->batches >= 0 && a->rows >= 0 && a->n > 0 && a->k > 0, "tw_gemm_bf16: bad shape");
     TW_REQUIRE(a->n % 8 == 0 && a->k % 8 == 0, "tw_gemm_bf16: N (%d) and K (%d) must be multiples of 8",
                a->n, a->k);

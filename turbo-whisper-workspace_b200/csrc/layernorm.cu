@@ -64,6 +64,7 @@ extern "C" int tw_layernorm(const float* x, const float* gamma, const float* bet
                             int64_t rows, int32_t cols, float eps, void* stream) {
     using namespace tw;
     TW_REQUIRE(x && gamma && beta && out_bf16, "tw_layernorm: null argument");
+    if (tw::ensure_device(x)) return 1;
     TW_REQUIRE(cols > 0 && cols % 4 == 0 && cols <= tw::ln::MAX_VEC * 128,
                "tw_layernorm: cols (%d) must be a multiple of 4 and <= %d", cols, tw::ln::MAX_VEC * 128);
     TW_REQUIRE(rows >= 0, "tw_layernorm: negative rows");

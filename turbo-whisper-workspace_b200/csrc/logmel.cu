@@ -321,6 +321,7 @@ extern "C" int tw_logmel(const void* tables_dev, const float* pcm, int64_t pcm_s
                          void* out_bf16_t, int64_t out_t_bstride, int32_t out_t_row_off,
                          void* stream) {
     TW_REQUIRE(tables_dev && pcm && scratch, "tw_logmel: null argument");
+    if (tw::ensure_device(pcm)) return 1;
     TW_REQUIRE(batch >= 0 && batch <= 65535, "tw_logmel: batch %d out of range", batch);
     TW_REQUIRE(pcm_stride >= N_SAMPLES, "tw_logmel: pcm_stride %lld < %d", (long long)pcm_stride,
                N_SAMPLES);

@@ -67,8 +67,27 @@ int encode_tensor_map(CUtensorMap* map, CUtensorMapDataType dtype, uint32_t rank
     return 0;
 }
 
+int ensure_device(const void* device_ptr) {
+    static thread_local int bound = -1;
+    if (bound >= 0 || device_ptr == nullptr) return 0;
+    cudaPointerAttributes attr;
+    cudaError_t e = cudaPointerGetAttributes(&attr, device_ptr);
+    if (e != cudaSuccess || attr.type != cudaMemoryTypeDevice) {
+        cudaGetLastError();
+        set_error("expected a device pointer (%s)", e != cudaSuccess ? cudaGetErrorString(e) : "host memory");
+        return 1;
+    }
+    e = cudaSetDevice(attr.device);
+    if (e != cudaSuccess) {
+        set_error("cudaSetDevice(%d) failed: %s", attr.device, cudaGetErrorString(e));
+        return 1;
+    }
+    bound = attr.device;
+    return 0;
+}
+
 int num_sms() {
-    static int n = 0;
+    static thread_local int n = 0;   // per thread: threads may serve different devices
     if (n == 0) {
         int dev = 0;
         if (cudaGetDevice(&dev) != cudaSuccess) return 0;

@@ -30,6 +30,7 @@ extern "C" int tw_shift_frames(const void* src_bf16, void* dst_bf16, const int32
                                void* stream) {
     using namespace tw;
     TW_REQUIRE(src_bf16 && dst_bf16 && seek, "tw_shift_frames: null argument");
+    if (tw::ensure_device(src_bf16)) return 1;
     TW_REQUIRE(cols % 8 == 0 && batch_stride % 8 == 0, "tw_shift_frames: cols and batch_stride must be multiples of 8");
     TW_REQUIRE(src_bf16 != dst_bf16, "tw_shift_frames: in-place shift is not supported");
     TW_REQUIRE(batch >= 0 && batch <= 65535, "tw_shift_frames: bad batch");

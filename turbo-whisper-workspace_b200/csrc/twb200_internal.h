@@ -12,4 +12,8 @@ int encode_tensor_map(CUtensorMap* map, CUtensorMapDataType dtype, uint32_t rank
                       const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
                       CUtensorMapSwizzle swizzle);
 int num_sms();
+// Binds the device that owns `device_ptr` to the calling host thread (first call per thread only).  The library links
+// its own static cudart: a host thread in which PyTorch has not yet made a context current would otherwise reach the
+// driver without a context (cuTensorMapEncodeTiled -> CUDA_ERROR_INVALID_CONTEXT) or launch on device 0.
+int ensure_device(const void* device_ptr);
 }  // namespace tw

@@ -405,6 +405,7 @@ class WhisperEngine:
             self.state[:B].copy_(st0.to(dev))
             self.stats["h2d_bytes"] += 2 * B * max_len * 4 + B * ROWSTATE_INTS * 4
             steps = (max_len - 1) if n_steps is None else min(n_steps, max_len - 1)
+            _lib.load().tw_set_pdl(0 if self.use_graphs else 1)   # PDL only pays off for eager stepping
             graph = self._graph_for(B) if self.use_graphs else None
             for s in range(steps):
                 if graph is not None:
