@@ -106,3 +106,16 @@ def test_pipeline_short_clip_and_errors(pipes):
         p(pcm, return_timestamps=True, generate_kwargs={"task": "summarize"})
     with pytest.raises(NotImplementedError):
         p(pcm, return_timestamps="word")
+    with pytest.raises(NotImplementedError):
+        p(pcm)
+    # explicit language / translate task use the forced-prompt path (no language detection step)
+    gen = p.generation
+    gen.lang_to_id = {"<|en|>": 50259, "<|fr|>": 50265}
+    eng = p.scheduler.flat_engines[0]
+    B = eng.load_pcm([pcm])
+    eng.features(B)
+    tr = {}
+    eng.generate(B, task="translate", language="fr", trace=tr)
+    assert tr["iterations"][0]["tokens"][0][:3] == [50258, 50265, 50359]
+    with pytest.raises(ValueError):
+        eng.generate(B, language="xx")

@@ -9,7 +9,7 @@
 // time-major activations, so im2col is never materialised
 // ($TF/models/whisper/modeling_whisper.py:619-620 conv1/conv2 + gelu).
 //
-// CTA = 192 threads: warp 0 TMA producer, warp 1 MMA issuer (+TMEM owner), warps 2-5 epilogue.
+// CTA = 320 threads: warp 0 TMA producer, warp 1 MMA issuer (+TMEM owner), warps 2-9 epilogue.
 // Tile 128 x 256 x 64, 4-stage smem ring (48 KB / stage), two 256-column fp32 accumulators in
 // TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.  Grid = #SMs, static tile striding.
 #include "common.cuh"
@@ -25,9 +25,10 @@ constexpr int UMMA_K = 16;
 constexpr int STAGES = 4;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two warps per TMEM lane quarter)
 constexpr int TMEM_COLS = 512;
-constexpr int EPI_STAGE_BYTES = 4 * 32 * 32 * 4;  // one 32x32 fp32 tile per epilogue warp
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_STAGE_BYTES = EPI_WARPS * 32 * 32 * 4;  // one 32x32 fp32 tile per epilogue warp
 constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align*/ + 256 /*barriers*/ + EPI_STAGE_BYTES;
 
 struct Params {
@@ -87,7 +88,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full_bar[s], 1);
-            mbar_init(&tmem_empty_bar[s], 128);
+            mbar_init(&tmem_empty_bar[s], EPI_WARPS * 32);
         }
         fence_barrier_init();
     }
@@ -154,9 +155,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         //      (16-byte chunks XOR-swizzled by row, conflict-free)
         //   B  8 lanes = one 128-byte row segment: bias, activation, fp32 residual (coalesced 128 B
         //      loads), store (128 B fp32 / 64 B bf16 per row per instruction)
-        const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+        const int quarter = warp & 3;       // TMEM lane quarter this warp may access
+        const int chalf = (warp - 2) >> 2;  // warps 2-5 take column chunks 0-3, warps 6-9 chunks 4-7 of the tile
         float* stage = reinterpret_cast<float*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256) +
-                       quarter * (32 * 32);
+                       (warp - 2) * (32 * 32);
         const int sub = lane & 7;    // phase B: 16-byte column chunk within the 32-column chunk
         const int rgrp = lane >> 3;  // phase B: row = rgrp + 4*i
         int acc = 0;
@@ -168,7 +170,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
             const int row_base = t.m0 + quarter * 32;  // first row of this warp within the batch
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = chalf * (BN / 64); c < (chalf + 1) * (BN / 64); ++c) {
                 const int n_base = t.n0 + c * 32;
                 if (n_base >= p.N) break;  // warp-uniform
                 uint32_t v[32];

@@ -187,6 +187,11 @@ class B200WhisperPipeline:
             raise NotImplementedError("beam search is not implemented by the B200 engine (greedy only)")
         if return_timestamps == "word":
             raise NotImplementedError('return_timestamps="word" is not implemented by the B200 engine')
+        if not return_timestamps:
+            # HF would decode with <|notimestamps|> and without the timestamp grammar; the reference always passes
+            # return_timestamps=True (ref:vocalis/core/audio_pipeline.py:357), which is the mode this engine implements
+            raise NotImplementedError("return_timestamps=False/None is not implemented by the B200 engine; "
+                                      "pass return_timestamps=True as the reference does")
         if return_timestamps == "char":
             raise ValueError("Whisper cannot return `char` timestamps, only word level or segment level timestamps. "
                              "Use `return_timestamps='word'` or `return_timestamps=True` respectively.")
