@@ -119,3 +119,21 @@ def test_pipeline_short_clip_and_errors(pipes):
     assert tr["iterations"][0]["tokens"][0][:3] == [50258, 50265, 50359]
     with pytest.raises(ValueError):
         eng.generate(B, language="xx")
+
+
+def test_multi_gpu_single_process_sharding(gold, long_wav):
+    """WindowScheduler over every visible GPU (one host thread + engine contexts per device): same tokens as one GPU."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    from oracle import whisper_ref as R
+    from turbo_whisper_workspace_b200.config import WhisperDims
+    from turbo_whisper_workspace_b200.scheduler import WindowScheduler
+    from turbo_whisper_workspace_b200.config import GenerationSettings
+    sd = helpers.variant_state_dict(R.WhisperDims(**helpers.TINY), "decisive")
+    dims = WhisperDims(**helpers.TINY)
+    clips = [helpers.synth_clip(50 + i, kind="mod" if i % 2 else "noise", seconds=30 if i % 3 else 12.5) for i in range(7)]
+    one = WindowScheduler(sd, dims, GenerationSettings(), devices=["cuda:0"], max_batch=2, contexts_per_device=1)
+    many = WindowScheduler(sd, dims, GenerationSettings(), devices=[f"cuda:{i}" for i in range(torch.cuda.device_count())],
+                           max_batch=2, contexts_per_device=2)
+    assert many.run(clips) == one.run(clips)
+    assert many.last_stats["workers"] == torch.cuda.device_count()

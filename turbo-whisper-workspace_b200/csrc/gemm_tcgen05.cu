@@ -325,11 +325,12 @@ extern "C" int tw_gemm_bf16(const tw_gemm_args* a, void* stream) {
         gemm_bf16_kernel<false, false, 0>, gemm_bf16_kernel<false, false, 1>, gemm_bf16_kernel<false, true, 0>,
         gemm_bf16_kernel<false, true, 1>,  gemm_bf16_kernel<true, false, 0>,  gemm_bf16_kernel<true, false, 1>,
         gemm_bf16_kernel<true, true, 0>,   gemm_bf16_kernel<true, true, 1>};
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};
+    const int dev = current_device();
+    if (!attr_set[dev]) {
         for (int i = 0; i < 8; ++i)
             TW_CUDA_CHECK(cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        attr_set = true;
+        attr_set[dev] = true;
     }
     const kern_t k = kernels[(p.out_f32 ? 4 : 0) + (p.resid ? 2 : 0) + (p.act ? 1 : 0)];
     k<<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmB, p);

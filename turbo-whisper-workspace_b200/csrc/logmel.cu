@@ -329,12 +329,13 @@ extern "C" int tw_logmel(const void* tables_dev, const float* pcm, int64_t pcm_s
     cudaStream_t st = (cudaStream_t)stream;
     float* scr = (float*)scratch;
     int* clip_max = (int*)(scr + (size_t)batch * N_MEL * N_FRAMES);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};
+    const int dev = current_device();
+    if (!attr_set[dev]) {
         TW_CUDA_CHECK(cudaFuncSetAttribute(logmel_power_kernel,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)sizeof(Smem)));
-        attr_set = true;
+        attr_set[dev] = true;
     }
     // 0x80000000 is the ordered-int image of the most negative float
     TW_CUDA_CHECK(cudaMemsetAsync(clip_max, 0x80, (size_t)batch * sizeof(int), st));

@@ -86,6 +86,12 @@ int ensure_device(const void* device_ptr) {
     return 0;
 }
 
+int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    return dev & 63;
+}
+
 int num_sms() {
     static thread_local int n = 0;   // per thread: threads may serve different devices
     if (n == 0) {

@@ -16,4 +16,6 @@ int num_sms();
 // its own static cudart: a host thread in which PyTorch has not yet made a context current would otherwise reach the
 // driver without a context (cuTensorMapEncodeTiled -> CUDA_ERROR_INVALID_CONTEXT) or launch on device 0.
 int ensure_device(const void* device_ptr);
+// device currently bound to this host thread (0..63); kernel attributes (max dynamic smem) are per device
+int current_device();
 }  // namespace tw

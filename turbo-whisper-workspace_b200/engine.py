@@ -167,6 +167,7 @@ class WhisperEngine:
         with torch.cuda.device(dev):
             self.w = shared_weights if shared_weights is not None else pack_weights(state_dict, dims, dev)
             self.stream = torch.cuda.Stream(device=dev) if own_stream else None
+            self._capture_stream = torch.cuda.Stream(device=dev)
             bf, f32, i32 = torch.bfloat16, torch.float32, torch.int32
             z = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, device=dev)
             self.logmel = ops.LogMel(dev, Bm)
@@ -370,7 +371,9 @@ class WhisperEngine:
             self.tokens.copy_(tokens_backup)
             g = torch.cuda.CUDAGraph()
             with _CAPTURE_LOCK:
-                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                # explicit per-device capture stream: torch's default capture stream is a process-wide singleton
+                # that lives on whichever device captured first
+                with torch.cuda.graph(g, stream=self._capture_stream, capture_error_mode="thread_local"):
                     self._decode_step(B)
             self.state.copy_(state_backup)
             self.tokens.copy_(tokens_backup)
