@@ -178,7 +178,7 @@ def run_reference(args, rank, world):
                              "sample": sample},
             "e2e": {"value": rtfx, "unit": "x realtime", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "host": {"cpu_count": cores, "torch_threads": torch.get_num_threads(), "torch": torch.__version__}}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -399,13 +399,33 @@ def run_own(args, rank, world, local_rank):
                            f"generate(max_new_tokens=4, 20) measured in {s['measured_s']:.1f} s, extrapolated to the "
                            f"3 encoder + 891 decoder forwards of the full reference call (t_enc={s['t_enc']:.2f}s, "
                            f"t_dec_step={s['t_dec_step'] * 1e3:.1f}ms)")}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version
+    banner on fd 1 under torchrun), so fd 1 is pointed at stderr for the whole run and the result line goes
+    to a private duplicate of the original stdout."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_RESULT_FD if _RESULT_FD is not None else 1, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
