@@ -14,6 +14,8 @@ ops.attention_enc(qkv, B, 1500, 20, out=out); torch.cuda.synchronize()
 t = buf.cpu().tolist()
 t0 = min(x for x in t if x > 0)
 mma = [x - t0 for x in t[:64] if x > 0]; sm = [x - t0 for x in t[64:128] if x > 0]
-print("MMA thread stamps (start, after q/k0, then [p_full_A, p_full_B] per j):"); print(mma[:30])
-print("softmax A row0 stamps per j: [enter, S ready, S loaded, P stored]:")
-for j in range(0, min(len(sm), 48), 4): print(j // 4, sm[j:j + 4], "softmax", sm[j + 3] - sm[j + 1] if j + 3 < len(sm) else None, "wait", sm[j + 1] - sm[j] if j + 1 < len(sm) else None)
+print("MMA thread stamps (start, after q/k0, then [p_full_A, p_full_B] per j):"); print(mma[:60])
+print("softmax A row0 (keys 0-63) stamps per kv tile: [S ready, S loaded, max agreed + PV(j-1) done, P stored]")
+for j in range(0, len(sm) - 3, 4):
+    a = sm[j:j + 4]
+    print(j // 4, a, "ld", a[1] - a[0], "max+o_wait", a[2] - a[1], "exp+st", a[3] - a[2], "period", (a[0] - sm[j - 4]) if j else None)

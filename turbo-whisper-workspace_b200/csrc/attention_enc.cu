@@ -6,17 +6,22 @@
 // which is exact for a power of two).
 //
 // Input is the fused QKV projection output [B*T, 3*D] bf16 (q | k | v, head h at columns 64h..).
-// One CTA = one (batch, head) and TWO 128-query tiles (A, B) that ping-pong on the tensor pipe.  320 threads:
-// warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 / 6-9 softmax + accumulation of tile A / B (one query row
-// per thread, no shuffles).  While the threads of A run the softmax of kv-tile j, the tensor core computes
-// S_B(j), P_B V(j-1) ... : MMA order S_A(0) S_B(0) | PV_A(j) S_A(j+1) PV_B(j) S_B(j+1) | ...
-//   S  = Q K_j^T      tcgen05.mma 128x128x64  -> TMEM cols [0,128)
-//   P  = exp2(S - m)  softmax threads, written to smem as the bf16 K-major SW128 A-operand
-//   O_j = P V_j       tcgen05.mma 128x64x128 (V consumed MN-major straight from its TMA tile)
-//                     -> TMEM cols [128,192); threads fold it into fp32 registers with the usual
-//                     online-softmax rescale.
-// K/V tiles are shared by both query tiles (half the smem / L2 traffic per query); 160 KB smem and 384 of the 512
-// TMEM columns per CTA (S_A, S_B, O_A, O_B).
+// One CTA = one (batch, head) and TWO 128-query tiles (A, B).  320 threads: warp 0 TMA producer, warp 1 MMA
+// issuer, warps 2-5 / 6-9 softmax of tile A / B (one query row per thread, no shuffles).
+//   S  = Q K_j^T      tcgen05.mma 128x128x64 (SS)  -> TMEM S_g (128 fp32 columns)
+//   P  = exp2(S - m)  softmax threads: S_g -> registers -> bf16 pairs -> TMEM P_g (64 columns)
+//   O += P V_j        tcgen05.mma 128x64x128 (TS: A = P_g from tensor memory, B = V_j MN-major straight from its
+//                     TMA tile) accumulating in TMEM O_g across all kv tiles
+// The exponentials (MUFU) are the co-limiter of this head size, so the schedule is built to keep the softmax
+// warps busy at all times: S_g is released (s_free) as soon as a thread has copied its row to registers, so
+// S_g(j+1) is computed WHILE softmax(j) runs; P has its own TMEM columns, so PV_g(j) runs while softmax(j+1)
+// runs.  In steady state a softmax thread never waits: S(j+1) is ready and PV(j-1) is done long before it asks.
+// Row sums are kept in registers; the softmax reference point only moves when the running maximum grows by
+// more than 2^8 (lazy rescale of O in TMEM).  K/V tiles are shared by both query tiles; ~100 KB smem and all
+// 512 TMEM columns (S_A S_B | P_A P_B | O_A O_B) per CTA.
+#ifndef ATTN_EXPERIMENT
+#define ATTN_EXPERIMENT 0
+#endif
 #include "common.cuh"
 #include "twb200_internal.h"
 
@@ -26,17 +31,16 @@ namespace attn {
 constexpr int BQ = 128;   // query rows per tile; a CTA owns two tiles (A, B) that ping-pong
 constexpr int BKV = 128;  // keys per iteration
 constexpr int DH = 64;
-constexpr int NUM_THREADS = 320;           // warp 0 TMA, warp 1 MMA, warps 2-5 softmax A, warps 6-9 softmax B
+constexpr int NUM_THREADS = 576;           // warp 0 TMA, warp 1 MMA, warps 2-9 softmax A, warps 10-17 softmax B
+constexpr int GROUP_THREADS = 256;         // softmax threads per query tile: two per row (64 keys each)
 constexpr int TILE_BYTES = 128 * DH * 2;   // 16 KB: Q, K, V tiles and each half of P
 constexpr int TMEM_COLS = 512;
-constexpr int S_COL = 0;                   // S_A [0,128)   S_B [128,256)
-constexpr int O_N = 80;                    // 64 output columns + 16 row-sum columns (V is extended by a block of ones)
-constexpr int O_COL = 256;                 // O_A [256,336) O_B [336,416); row sums at O_COL + 64
-constexpr int ONES_BYTES = 2048;           // 16 key rows x 128 B of bf16 1.0: second MN atom of the PV B operand
-// smem tiles: Q_A Q_B | K0 K1 | V0 V1 | ones.  P never touches shared memory: the softmax threads store it (bf16,
-// two keys per 32-bit column) into the first 64 TMEM columns of their own S tile and tcgen05.mma reads the A
-// operand from tensor memory.
-constexpr int SMEM_BYTES = 6 * TILE_BYTES + ONES_BYTES + 1024 + 256;
+constexpr int S_COL = 0;                   // S_A [0,128)   S_B [128,256)   fp32 scores
+constexpr int P_COL = 256;                 // P_A [256,320) P_B [320,384)   bf16 probabilities, two keys per column
+constexpr int O_COL = 384;                 // O_A [384,448) O_B [448,512)   fp32 output accumulators
+// smem tiles: Q_A Q_B | K0 K1 | V0 V1.  P never touches shared memory: tcgen05.mma reads it from tensor memory.
+constexpr int XCH_BYTES = 2 * 2 * 2 * 128 * 4;   // row-max / row-sum exchange between the two threads of a row: [parity][tile][half][row]
+constexpr int SMEM_BYTES = 6 * TILE_BYTES + XCH_BYTES + 1024 + 256;
 constexpr float LOG2E = 1.4426950408889634f;
 
 // single-instruction exp2 (MUFU.EX2, flush-to-zero): arguments here are <= 0, so the slow path of exp2f()
@@ -55,6 +59,29 @@ TW_DEVINL float ex2_approx(float x) {
     return y;
 }
 
+// packed fp32x2 arithmetic (one issue slot for two lanes of work): the softmax inner loop is issue-bound next to
+// the MUFU, so the scale/shift FMA and the row-sum ADD are done on register pairs
+TW_DEVINL uint64_t pack_f32x2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+TW_DEVINL void unpack_f32x2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+TW_DEVINL uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+TW_DEVINL uint64_t add_f32x2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// named barriers 1 / 2: the MUFU turn of tile A / B (see the softmax loop)
+TW_DEVINL void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+TW_DEVINL void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
 struct Params {
     int T, H, D;        // sequence length, heads, model width (H*64)
     long long out_ld;   // elements
@@ -69,8 +96,8 @@ attention_enc_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
     uint8_t* sQ = smem;                       // 2 tiles
     uint8_t* sK = smem + 2 * TILE_BYTES;      // 2 stages
     uint8_t* sV = smem + 4 * TILE_BYTES;      // 2 stages
-    uint8_t* sOnes = smem + 6 * TILE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * TILE_BYTES + ONES_BYTES);
+    float* xch = reinterpret_cast<float*>(smem + 6 * TILE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * TILE_BYTES + XCH_BYTES);
     uint64_t* q_full = bars + 0;
     uint64_t* k_full = bars + 1;   // [2]
     uint64_t* k_empty = bars + 3;  // [2]
@@ -79,14 +106,19 @@ attention_enc_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
     uint64_t* s_full = bars + 9;   // [2] per group
     uint64_t* p_full = bars + 11;  // [2] per group
     uint64_t* o_full = bars + 13;  // [2] per group
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 15);
+    uint64_t* s_free = bars + 15;  // [2] per group: every thread of the group holds its S row in registers
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 17);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * (2 * BQ), h = blockIdx.y, b = blockIdx.z;
     const int nkv = (p.T + BKV - 1) / BKV;
     const bool trace = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
     int ti = 0;
+#ifdef ATTN_TRACE
 #define TRACE(base) do { if (trace && ti < 60) p.dbg[(base) + ti++] = clock64(); } while (0)
+#else
+#define TRACE(base) do { } while (0)
+#endif
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQKV);
@@ -94,7 +126,8 @@ attention_enc_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
         for (int i = 0; i < 2; ++i) {
             mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
             mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
-            mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&o_full[i], 1);
+            mbar_init(&s_full[i], 1); mbar_init(&p_full[i], GROUP_THREADS); mbar_init(&o_full[i], 1);
+            mbar_init(&s_free[i], GROUP_THREADS);
         }
         fence_barrier_init();
     }
@@ -102,8 +135,6 @@ attention_enc_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
         tmem_alloc(tmem_ptr_smem, TMEM_COLS);
         tmem_relinquish();
     }
-    for (int i = threadIdx.x; i < ONES_BYTES / 4; i += NUM_THREADS) reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3F803F80u;  // bf16 1.0 pairs
-    fence_proxy_async_smem();
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
@@ -126,110 +157,131 @@ attention_enc_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc_s = umma_idesc_bf16(BQ, BKV, 0, 0);
-            constexpr uint32_t idesc_o = umma_idesc_bf16(BQ, O_N, 0, 1);  // B = [V | ones] is MN-major, N = 80
-            // Every descriptor is loop-invariant: build them once.  The single issuing thread must spend ~2
-            // instructions per tcgen05.mma, not ~30, because these MMAs only last 32-64 cycles each.
-            uint64_t dq[2][DH / 16], dk[2][DH / 16], dv[2][BKV / 16];
-#pragma unroll
-            for (int k = 0; k < DH / 16; ++k) {
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    dq[g][k] = umma_desc_sw128(smem_u32(sQ) + g * TILE_BYTES + k * 32, 16, 1024);
-                    dk[g][k] = umma_desc_sw128(smem_u32(sK) + g * TILE_BYTES + k * 32, 16, 1024);
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < BKV / 16; ++k) {
-#pragma unroll
-                for (int st = 0; st < 2; ++st) {
-                    const uint32_t va = smem_u32(sV) + st * TILE_BYTES + k * 2048;
-                    // MN atom 0 = the 64 head-dim columns of V (16 key rows x 128 B); atom 1 (LBO away) = ones
-                    dv[st][k] = umma_desc_sw128(va, smem_u32(sOnes) - va, 1024);
-                }
-            }
-            auto issue_s = [&](int g, int j) {   // S_g = Q_g K_j^T
-                const int st = j & 1;
+        // The whole warp runs this loop converged and one elected lane issues: every operand of tcgen05.mma is
+        // then warp-uniform (uniform registers), so an issue costs ~3 instructions.  (With a single divergent
+        // thread and descriptor arrays in local memory each issue cost ~110 cycles - more than the 32-64
+        // cycles the MMAs themselves last - and the issuing thread, not the tensor pipe or the MUFU, set the pace.)
+        constexpr uint32_t idesc_s = umma_idesc_bf16(BQ, BKV, 0, 0);
+        constexpr uint32_t idesc_o = umma_idesc_bf16(BQ, DH, 0, 1);  // B = V is MN-major
+        const uint64_t dq0 = umma_desc_sw128(smem_u32(sQ), 16, 1024);
+        const uint64_t dk0 = umma_desc_sw128(smem_u32(sK), 16, 1024);
+        // V: one 64-wide MN atom (the head dim), 16 key rows x 128 B per K step, 8-row groups 1024 B apart
+        const uint64_t dv0 = umma_desc_sw128(smem_u32(sV), 1024, 1024);
+        constexpr uint64_t TILE_D = TILE_BYTES >> 4;   // descriptor address field is in 16-byte units
+        auto issue_s = [&](int g, int j) {   // S_g = Q_g K_j^T
+            const uint64_t a = dq0 + (uint64_t)g * TILE_D, bd = dk0 + (uint64_t)(j & 1) * TILE_D;
+            if (elect_one_sync()) {
 #pragma unroll
                 for (int k = 0; k < DH / 16; ++k)
-                    tcgen05_mma_f16(tmem_base + S_COL + g * BKV, dq[g][k], dk[st][k], idesc_s, k != 0);
+                    tcgen05_mma_f16(tmem_base + S_COL + g * BKV, a + k * 2, bd + k * 2, idesc_s, k != 0);
                 tcgen05_commit(&s_full[g]);
-            };
-            auto issue_pv = [&](int g, int j) {  // [O_g | rowsum_g] += P_g [V_j | 1]   (A = P from TMEM)
-                const int st = j & 1;
-                const uint32_t p_tmem = tmem_base + S_COL + g * BKV;   // P aliases the first 64 columns of S_g
-                const uint32_t acc0 = j != 0;
+            }
+            __syncwarp();
+        };
+        auto issue_pv = [&](int g, int j) {  // O_g += P_g V_j   (A = P from TMEM)
+            const uint64_t bd = dv0 + (uint64_t)(j & 1) * TILE_D;
+            const uint32_t p_tmem = tmem_base + P_COL + g * (BKV / 2);
+            const uint32_t acc0 = j != 0;
+            if (elect_one_sync()) {
 #pragma unroll
                 for (int k = 0; k < BKV / 16; ++k)
-                    tcgen05_mma_f16_ts(tmem_base + O_COL + g * O_N, p_tmem + k * 8, dv[st][k], idesc_o, k != 0 ? 1u : acc0);
+                    tcgen05_mma_f16_ts(tmem_base + O_COL + g * DH, p_tmem + k * 8, bd + k * 128, idesc_o, k != 0 ? 1u : acc0);
                 tcgen05_commit(&o_full[g]);
-            };
-            TRACE(0);
-            mbar_wait(q_full, 0);
-            mbar_wait(&k_full[0], 0);
-            TRACE(0);
-            tcgen05_fence_after();
-            issue_s(0, 0);
-            issue_s(1, 0);
-            tcgen05_commit(&k_empty[0]);
-            // The two query tiles are served in whatever order their P tiles become ready (non-blocking polls), so a
-            // slow softmax of one tile never delays the MMAs of the other.  K/V stages are released once both tiles
-            // have issued the MMAs that read them; a tile can therefore run at most one kv tile ahead of the other.
-            int jg[2] = {0, 0};          // next PV index per tile
-            while (jg[0] < nkv || jg[1] < nkv) {
+            }
+            __syncwarp();
+        };
+        auto release = [&](uint64_t* bar) {   // hand a K/V stage back to the producer once the MMAs issued so far finish
+            if (elect_one_sync()) tcgen05_commit(bar);
+            __syncwarp();
+        };
+        if (lane == 0) TRACE(0);
+        mbar_wait(q_full, 0);
+        mbar_wait(&k_full[0], 0);
+        if (lane == 0) TRACE(0);
+        tcgen05_fence_after();
+        issue_s(0, 0);
+        issue_s(1, 0);
+        release(&k_empty[0]);
+        // Event loop over the four things that can become issuable, polled without blocking so that neither
+        // tile ever delays the other:  S_g(j) once the group has copied S_g(j-1) to registers (s_free) and K_j
+        // has landed;  PV_g(j) once P_g(j) is stored (p_full) and V_j has landed.  A K/V stage is handed back
+        // to the producer by whichever tile issues the second MMA that reads it.
+        int js0 = 1, js1 = 1;   // next S index per tile
+        int jp0 = 0, jp1 = 0;   // next PV index per tile
+        while (jp0 < nkv || jp1 < nkv) {
 #pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    const int j = jg[g];
-                    if (j >= nkv) continue;
-                    if (!mbar_try_wait(&p_full[g], j & 1)) continue;
-                    mbar_wait(&v_full[j & 1], (j >> 1) & 1);
+            for (int g = 0; g < 2; ++g) {
+                int& js = g ? js1 : js0;
+                int& jp = g ? jp1 : jp0;
+                const int js_other = g ? js0 : js1, jp_other = g ? jp0 : jp1;
+                // (K_j / V_j are part of the non-blocking condition: a tile that runs two kv tiles ahead of the other
+                // needs a stage the slower tile has not released yet, and only this warp can make it release it)
+                if (js < nkv && __any_sync(0xffffffffu, mbar_test_wait(&s_free[g], (js - 1) & 1) &&
+                                                            mbar_test_wait(&k_full[js & 1], (js >> 1) & 1))) {
+                    const int j = js;
                     tcgen05_fence_after();
+                    if (g == 0 && lane == 0) TRACE(0);
+                    issue_s(g, j);
+                    if (g == 0 && lane == 0) TRACE(0);
+                    if (js_other > j) release(&k_empty[j & 1]);   // second reader of K_j
+                    js = j + 1;
+                }
+                if (jp < nkv && __any_sync(0xffffffffu, mbar_test_wait(&p_full[g], jp & 1) &&
+                                                            mbar_test_wait(&v_full[jp & 1], (jp >> 1) & 1))) {
+                    const int j = jp;
+                    tcgen05_fence_after();
+                    if (g == 0 && lane == 0) TRACE(0);
                     issue_pv(g, j);
-                    if (jg[g ^ 1] > j) tcgen05_commit(&v_empty[j & 1]);          // second reader of V_j
-                    if (j + 1 < nkv) {
-                        mbar_wait(&k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
-                        tcgen05_fence_after();
-                        issue_s(g, j + 1);
-                        if (jg[g ^ 1] > j) tcgen05_commit(&k_empty[(j + 1) & 1]);  // second reader of K_{j+1}
-                    }
-                    jg[g] = j + 1;
+                    if (g == 0 && lane == 0) TRACE(0);
+                    if (jp_other > j) release(&v_empty[j & 1]);   // second reader of V_j
+                    jp = j + 1;
                 }
             }
         }
     } else {
-        const int grp = (warp - 2) >> 2;    // 0: tile A, 1: tile B
+        // Two threads per query row (64 keys each): four softmax warps per SM sub-partition.  A warp issues in order
+        // and every MUFU.EX2 holds the XU port for 8 cycles, so one warp per tile per sub-partition leaves the MUFU
+        // idle during its TMEM load / row-max / store phases and the FMA pipe idle during its exp phase; with four
+        // warps in different phases both stay busy.  Warps w and w+4 of a tile share a TMEM lane quarter (w % 4) and
+        // split the columns; they agree on the row maximum through shared memory (named barrier per warp pair).
+        const int grp = (warp - 2) >> 3;    // 0: tile A, 1: tile B
         const int quarter = warp & 3;       // TMEM lane quarter this warp may access
+        const int hf = ((warp - 2) >> 2) & 1;   // which 64 keys of the tile (and which 32 output columns) this thread owns
         const int r = quarter * 32 + lane;  // query row within the tile == TMEM lane
+        const int pair_bar = 1 + grp * 4 + quarter;   // named barrier of the two warps that share these rows
         const uint32_t t_lane = (uint32_t)(quarter * 32) << 16;
-        const uint32_t s_col = S_COL + grp * BKV, o_col = O_COL + grp * O_N, l_col = o_col + DH;
-        // O and the row sums accumulate in TMEM across kv tiles (tcgen05.mma accumulate); S is read from TMEM
-        // exactly once per tile (TMEM read bandwidth is the scarce resource).  The softmax reference point
-        // m_used only moves when the running maximum grows by more than RESCALE_LOG2 (lazy rescaling: P <= 2^8,
-        // mathematically identical after the final O / rowsum division); a move rescales O and rowsum in TMEM.
+        const uint32_t s_col = S_COL + grp * BKV + hf * (BKV / 2), p_col = P_COL + grp * (BKV / 2) + hf * (BKV / 4);
+        const uint32_t o_col = O_COL + grp * DH + hf * (DH / 2);
+        constexpr int HK = BKV / 2;         // keys per thread per kv tile
+        // O accumulates in TMEM across kv tiles (tcgen05.mma accumulate); S is read from TMEM exactly once per
+        // tile.  The softmax reference point m_used only moves when the running maximum grows by more than
+        // RESCALE_LOG2 (lazy rescaling: P <= 2^8, mathematically identical after the final O / rowsum
+        // division); a move rescales O in TMEM and the row sum in its register.
         constexpr float RESCALE_LOG2 = 8.0f;
         float m_used = -INFINITY;   // in log2 units (score * log2e)
+        float l_sum = 0.0f;         // running sum of exp2(s - m_used) over this thread's keys
+        const bool tr = trace && grp == 0 && hf == 0 && r == 0;
 
         for (int j = 0; j < nkv; ++j) {
             const uint32_t ph = j & 1;
-            const int kvalid = p.T - j * BKV;  // keys >= kvalid are padding (TMA zero-fill)
-            const bool full = kvalid >= BKV;
-            if (grp == 0 && r == 0) TRACE(64);
+            const int kvalid = p.T - j * BKV - hf * HK;  // keys >= kvalid (of this thread's 64) are padding (TMA zero-fill)
+            const bool full = kvalid >= HK;
             mbar_wait(&s_full[grp], ph);
-            if (j > 0) mbar_wait(&o_full[grp], (j - 1) & 1);
-            if (grp == 0 && r == 0) TRACE(64);  // PV(j-1) done (implied by S(j) done; keeps phases in step)
+            if (tr) TRACE(64);
             tcgen05_fence_after();
-            uint32_t v[BKV];
+            uint32_t v[HK];
 #pragma unroll
-            for (int c = 0; c < BKV / 32; ++c)
-                tmem_ld_32x32b_x32(tmem_base + t_lane + s_col + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
+            for (int c = 0; c < HK / 16; ++c)
+                tmem_ld_32x32b_x16(tmem_base + t_lane + s_col + c * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[c * 16]));
             tmem_ld_wait();
-            if (grp == 0 && r == 0) TRACE(64);
+            tcgen05_fence_before();
+            mbar_arrive(&s_free[grp]);          // the tensor core may now overwrite S_g with S_g(j+1)
+            if (tr) TRACE(64);
             float mx = -INFINITY;
             if (full) {
                 float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // independent chains
 #pragma unroll
-                for (int i = 0; i < BKV; i += 4) {
+                for (int i = 0; i < HK; i += 4) {
                     m4[0] = fmaxf(m4[0], __uint_as_float(v[i]));
                     m4[1] = fmaxf(m4[1], __uint_as_float(v[i + 1]));
                     m4[2] = fmaxf(m4[2], __uint_as_float(v[i + 2]));
@@ -238,71 +290,94 @@ attention_enc_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
                 mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
             } else {
 #pragma unroll
-                for (int i = 0; i < BKV; ++i)
+                for (int i = 0; i < HK; ++i)
                     if (i < kvalid) mx = fmaxf(mx, __uint_as_float(v[i]));
             }
+            // agree on the row maximum with the thread that owns the other 64 keys of this row
+            float* xm = xch + ((ph * 2 + grp) * 2) * 128;
+            xm[hf * 128 + r] = mx;
+            named_bar_sync(pair_bar, 64);
+            mx = fmaxf(mx, xm[(hf ^ 1) * 128 + r]);
             const float mx2 = mx * LOG2E;
             const bool move = mx2 > m_used + RESCALE_LOG2;   // always true on the first tile (m_used = -inf)
-            const float alpha = move ? ex2_approx(m_used - mx2) : 1.0f;   // first tile: exp2(-inf) = 0, O is overwritten
+            const float alpha = move ? ex2_approx(m_used - mx2) : 1.0f;   // first tile: exp2(-inf) = 0
             if (move) m_used = mx2;
             const float mb = m_used;
+            // PV_g(j-1) must be complete before P_g is overwritten and before O_g may be rescaled; it was issued
+            // a whole softmax phase ago, so this does not block in steady state
+            if (j > 0) {
+                mbar_wait(&o_full[grp], (j - 1) & 1);
+                tcgen05_fence_after();
+                if (__any_sync(0xffffffffu, move)) {   // warp-collective ld/st; this thread's 32 output columns
+#pragma unroll 1
+                    for (int c = 0; c < DH / 2; c += 8) {   // rare path: small pieces keep the register peak low
+                        uint32_t o[8];
+                        tmem_ld_32x32b_x8(tmem_base + t_lane + o_col + c, o);
+                        tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < BKV / 32; ++c) {
-                uint32_t pk[16];
-                if (full || c * 32 + 32 <= kvalid) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        pk[i] = ex2_bf16x2(pack_bf16x2(fmaf(__uint_as_float(v[c * 32 + 2 * i]), LOG2E, -mb),
-                                                       fmaf(__uint_as_float(v[c * 32 + 2 * i + 1]), LOG2E, -mb)));
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float a0 = (c * 32 + 2 * i < kvalid) ? fmaf(__uint_as_float(v[c * 32 + 2 * i]), LOG2E, -mb) : -INFINITY;
-                        const float a1 = (c * 32 + 2 * i + 1 < kvalid) ? fmaf(__uint_as_float(v[c * 32 + 2 * i + 1]), LOG2E, -mb) : -INFINITY;
-                        pk[i] = ex2_bf16x2(pack_bf16x2(a0, a1));
+                        for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st_32x32b_x8(tmem_base + t_lane + o_col + c, o);
                     }
                 }
-                // keys [32c, 32c+32) of this row -> TMEM columns [16c, 16c+16) of the P tile (aliases S_g, already in registers)
-                asm volatile(
-                    "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-                    "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-                    :
-                    : "r"(tmem_base + t_lane + s_col + c * 16), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]),
-                      "r"(pk[5]), "r"(pk[6]), "r"(pk[7]), "r"(pk[8]), "r"(pk[9]), "r"(pk[10]), "r"(pk[11]), "r"(pk[12]),
-                      "r"(pk[13]), "r"(pk[14]), "r"(pk[15])
-                    : "memory");
             }
-            // rescale the TMEM accumulators of this row when its reference point moved (warp-collective ld/st)
-            if (j > 0 && __any_sync(0xffffffffu, move)) {
+            if (tr) TRACE(64);
+            const uint64_t sc2 = pack_f32x2(LOG2E, LOG2E), mb2 = pack_f32x2(-mb, -mb);
+            uint64_t sum2[2] = {0ull, 0ull};
+            auto store_p = [&](int c, const uint32_t (&pk)[16]) {
+                // this thread's keys [32c, 32c+32) -> TMEM columns [16c, 16c+16) of its half of P_g
+                tmem_st_32x32b_x16(tmem_base + t_lane + p_col + c * 16, pk);
+            };
+            if (full) {   // two separate instruction streams: the masked one must not tax the full tiles
 #pragma unroll
-                for (int c = 0; c < DH / 32; ++c) {
-                    uint32_t o[32];
-                    tmem_ld_32x32b_x32(tmem_base + t_lane + o_col + c * 32, o);
-                    tmem_ld_wait();
+                for (int c = 0; c < HK / 32; ++c) {
+                    uint32_t pk[16];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                    tmem_st_32x32b_x32(tmem_base + t_lane + o_col + c * 32, o);
+                    for (int i = 0; i < 16; ++i) {
+                        const int k0 = c * 32 + 2 * i;
+                        float a0, a1;
+                        unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(v[k0]), __uint_as_float(v[k0 + 1])), sc2, mb2), a0, a1);
+                        const float p0 = ex2_approx(a0), p1 = ex2_approx(a1);
+                        sum2[i & 1] = add_f32x2(sum2[i & 1], pack_f32x2(p0, p1));
+                        pk[i] = pack_bf16x2(p0, p1);
+                    }
+                    store_p(c, pk);
                 }
-                const uint32_t ls = tmem_ld_32x32b_x1(tmem_base + t_lane + l_col);
-                tmem_ld_wait();
-                tmem_st_32x32b_x1(tmem_base + t_lane + l_col, __float_as_uint(__uint_as_float(ls) * alpha));
+            } else {      // last kv tile: keys >= kvalid are TMA zero-fill and must not contribute
+#pragma unroll
+                for (int c = 0; c < HK / 32; ++c) {
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int k0 = c * 32 + 2 * i;
+                        const float p0 = (k0 < kvalid) ? ex2_approx(fmaf(__uint_as_float(v[k0]), LOG2E, -mb)) : 0.0f;
+                        const float p1 = (k0 + 1 < kvalid) ? ex2_approx(fmaf(__uint_as_float(v[k0 + 1]), LOG2E, -mb)) : 0.0f;
+                        sum2[i & 1] = add_f32x2(sum2[i & 1], pack_f32x2(p0, p1));
+                        pk[i] = pack_bf16x2(p0, p1);
+                    }
+                    store_p(c, pk);
+                }
             }
+            float s0, s1, s2, s3;
+            unpack_f32x2(sum2[0], s0, s1);
+            unpack_f32x2(sum2[1], s2, s3);
+            l_sum = l_sum * alpha + ((s0 + s1) + (s2 + s3));
             tmem_st_wait();
-            if (grp == 0 && r == 0) TRACE(64);
+            if (tr) TRACE(64);
             tcgen05_fence_before();
             mbar_arrive(&p_full[grp]);
         }
+        // total row sum = this thread's half + the partner's
+        float* xl = xch + ((((nkv & 1) * 2) + grp) * 2) * 128;   // the parity slot the last max exchange did not use
+        xl[hf * 128 + r] = l_sum;
+        named_bar_sync(pair_bar, 64);
+        const float inv = 1.0f / (l_sum + xl[(hf ^ 1) * 128 + r]);
         mbar_wait(&o_full[grp], (nkv - 1) & 1);
         tcgen05_fence_after();
         const int q = q0 + grp * BQ + r;
-        const uint32_t ls = tmem_ld_32x32b_x1(tmem_base + t_lane + l_col);
-        tmem_ld_wait();
-        const float inv = 1.0f / __uint_as_float(ls);
-        __nv_bfloat16* o = p.out + ((size_t)b * p.T + q) * p.out_ld + h * DH;
-#pragma unroll
-        for (int c = 0; c < DH / 32; ++c) {
+        __nv_bfloat16* o = p.out + ((size_t)b * p.T + q) * p.out_ld + h * DH + hf * (DH / 2);
+        {
             uint32_t acc[32];
-            tmem_ld_32x32b_x32(tmem_base + t_lane + o_col + c * 32, acc);
+            tmem_ld_32x32b_x32(tmem_base + t_lane + o_col, acc);
             tmem_ld_wait();
             if (q < p.T) {
 #pragma unroll
@@ -312,7 +387,7 @@ attention_enc_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
                     pk.y = pack_bf16x2(__uint_as_float(acc[g * 8 + 2]) * inv, __uint_as_float(acc[g * 8 + 3]) * inv);
                     pk.z = pack_bf16x2(__uint_as_float(acc[g * 8 + 4]) * inv, __uint_as_float(acc[g * 8 + 5]) * inv);
                     pk.w = pack_bf16x2(__uint_as_float(acc[g * 8 + 6]) * inv, __uint_as_float(acc[g * 8 + 7]) * inv);
-                    reinterpret_cast<uint4*>(o)[c * 4 + g] = pk;
+                    reinterpret_cast<uint4*>(o)[g] = pk;
                 }
             }
         }

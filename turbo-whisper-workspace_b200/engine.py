@@ -147,10 +147,13 @@ class WhisperEngine:
 
     def __init__(self, dims: WhisperDims, state_dict: Optional[Dict[str, torch.Tensor]], device="cuda:0",
                  gen: Optional[GenerationSettings] = None, max_batch: int = 24, cross_splits: int = 4,
-                 shared_weights: Optional[Dict[str, torch.Tensor]] = None, own_stream: bool = False):
+                 shared_weights: Optional[Dict[str, torch.Tensor]] = None, own_stream: bool = False,
+                 max_enc_batch: Optional[int] = None):
         """``shared_weights``: the packed weights (``.w``) of another engine on the same device — several engine
         contexts (each with its own workspaces, KV pool and stream) then serve one GPU from one copy of the model,
-        so that one context's latency-bound decode overlaps another's tensor-bound encoder."""
+        so that one context's latency-bound decode overlaps another's tensor-bound encoder.
+        ``max_enc_batch``: capacity of the front-end/encoder workspaces when it should exceed the decode batch
+        (BASELINE.json configs[4], the log-mel + encoder-only sweep up to 256 windows); default = max_batch."""
         dims.validate()
         _lib.load()
         if not torch.cuda.is_available():
@@ -162,6 +165,7 @@ class WhisperEngine:
         self.max_batch = max_batch
         self.cross_splits = cross_splits
         D, F, L, Bm = dims.d_model, dims.ffn, dims.dec_layers, max_batch
+        self.max_enc_batch = Be = max(max_batch, int(max_enc_batch or 0))
         S, T = dims.max_source_positions, N_FRAMES
         dev = self.device
         with torch.cuda.device(dev):
@@ -170,19 +174,19 @@ class WhisperEngine:
             self._capture_stream = torch.cuda.Stream(device=dev)
             bf, f32, i32 = torch.bfloat16, torch.float32, torch.int32
             z = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, device=dev)
-            self.logmel = ops.LogMel(dev, Bm)
+            self.logmel = ops.LogMel(dev, Be)
             # ---- encoder workspaces
-            self.pcm = z(Bm, N_SAMPLES, dtype=f32)
-            self.n_valid = z(Bm, dtype=i32)
-            self.mel_t = z(Bm, T + 2, dims.n_mels, dtype=bf)    # row 1+t = frame t; rows 0, T+1 = conv padding
-            self.mel_s = z(Bm, T + 2, dims.n_mels, dtype=bf)    # seek-shifted windows
-            self.h1 = z(Bm, T + 2, D, dtype=bf)                 # conv1 output, same padding convention
-            self.x = z(Bm * S, D, dtype=f32)                    # residual stream
-            self.xn = z(Bm * S, D, dtype=bf)                    # LayerNorm output / encoder output
-            self.qkv = z(Bm * S, 3 * D, dtype=bf)
-            self.att = z(Bm * S, D, dtype=bf)
-            self.hid = z(Bm * S, F, dtype=bf)
-            self.ckv = z(Bm * S, L * 2 * D, dtype=bf)           # cross-attention K/V of every decoder layer
+            self.pcm = z(Be, N_SAMPLES, dtype=f32)
+            self.n_valid = z(Be, dtype=i32)
+            self.mel_t = z(Be, T + 2, dims.n_mels, dtype=bf)    # row 1+t = frame t; rows 0, T+1 = conv padding
+            self.mel_s = z(Be, T + 2, dims.n_mels, dtype=bf)    # seek-shifted windows
+            self.h1 = z(Be, T + 2, D, dtype=bf)                 # conv1 output, same padding convention
+            self.x = z(Be * S, D, dtype=f32)                    # residual stream
+            self.xn = z(Be * S, D, dtype=bf)                    # LayerNorm output / encoder output
+            self.qkv = z(Be * S, 3 * D, dtype=bf)
+            self.att = z(Be * S, D, dtype=bf)
+            self.hid = z(Be * S, F, dtype=bf)
+            self.ckv = z(Be * S, L * 2 * D, dtype=bf)           # cross-attention K/V of every decoder layer
             # ---- decoder workspaces
             self.max_len = min(self.gen.max_length, dims.max_target_positions)
             self.pages_per_row = (self.max_len + PAGE - 1) // PAGE
@@ -219,8 +223,8 @@ class WhisperEngine:
         self.use_graphs = True
         self.finish_check_every = 16
         self.stats = {"enc_windows": 0, "dec_steps": 0, "launches": 0, "h2d_bytes": 0, "d2h_bytes": 0}
-        self._pcm_host = torch.zeros(Bm, N_SAMPLES, dtype=torch.float32).pin_memory()
-        self._nv_host = torch.zeros(Bm, dtype=torch.int32).pin_memory()
+        self._pcm_host = torch.zeros(Be, N_SAMPLES, dtype=torch.float32).pin_memory()
+        self._nv_host = torch.zeros(Be, dtype=torch.int32).pin_memory()
 
     # ------------------------------------------------------------------------------------ helpers
     def _stream(self):
@@ -238,8 +242,8 @@ class WhisperEngine:
         """H2D of up to max_batch clips (each <= 30 s of fp32 PCM at 16 kHz; longer clips are truncated
         like WhisperFeatureExtractor(truncation=True)).  Returns the batch size."""
         B = len(clips)
-        if B > self.max_batch:
-            raise ValueError(f"{B} windows > max_batch {self.max_batch}")
+        if B > self.max_enc_batch:
+            raise ValueError(f"{B} windows > max_enc_batch {self.max_enc_batch}")
         torch.cuda.current_stream(self.device).synchronize()   # the pinned staging buffer may still be in flight
         host, nv = self._pcm_host, self._nv_host
         for i, c in enumerate(clips):
