@@ -161,3 +161,44 @@ def quantize_pcm16(pcm: np.ndarray) -> np.ndarray:
     """What a PCM16 WAV round trip does to the samples (so array inputs and file inputs agree)."""
     return (np.clip(np.asarray(pcm, dtype=np.float64) * 32768.0, -32768, 32767).astype("<i2").astype(np.float32)
             / 32768.0)
+
+
+def compare_generate_traces(ref_trace, eng_trace, margin_tol: float):
+    """Margin-aware comparison of two free-running seek loops (oracle trace vs engine trace).
+
+    North-star rule: greedy ids must be identical wherever the oracle's top-1 margin (and the timestamp-rule
+    gap) exceeds the stated tolerance.  Rows are walked iteration by iteration; a row stops being compared at
+    its first differing token, which must be a NON-decisive oracle step (afterwards the two loops legitimately
+    see different contexts / seeks).  Returns (tokens_compared_equal, rows_fully_identical, first_diffs)."""
+    assert eng_trace["langs"] == ref_trace["langs"], "language detection differs"
+    alive = None
+    agreed, first_diffs = 0, {}
+    for k, it in enumerate(ref_trace["iterations"]):
+        rows = list(it["rows"])
+        if alive is None:
+            alive = set(rows)
+        if not any(b in alive for b in rows):
+            break
+        assert k < len(eng_trace["iterations"]), f"engine ran {len(eng_trace['iterations'])} seek iterations, oracle more"
+        e = eng_trace["iterations"][k]
+        for i, b in enumerate(rows):
+            if b not in alive:
+                continue
+            assert b in e["rows"], f"row {b} retired early in the engine (iteration {k})"
+            ei = e["rows"].index(b)
+            assert e["seek"][ei] == it["seek"][i], f"row {b}: seek differs at iteration {k}"
+            want_row = [int(t) for t in it["tokens"][i].tolist()]
+            got_row = [int(t) for t in e["tokens"][ei][3:3 + len(want_row)]]
+            for g, t in enumerate(want_row):
+                if g >= len(it["record"]):
+                    break
+                if got_row[g] != t:
+                    rec = it["record"][g]
+                    decisive = float(rec["margin"][i]) > margin_tol and float(rec["rule_gap"][i]) > margin_tol
+                    assert not decisive, (f"row {b} diverges at DECISIVE step {g} of iteration {k}: margin "
+                                          f"{float(rec['margin'][i]):.3f}, rule gap {float(rec['rule_gap'][i]):.3f}")
+                    first_diffs[b] = (k, g, float(rec["margin"][i]))
+                    alive.discard(b)
+                    break
+                agreed += 1
+    return agreed, sorted(alive or []), first_diffs
