@@ -432,7 +432,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--contexts", type=int, default=2, help="engine contexts (streams) per GPU sharing one weight copy")
+    ap.add_argument("--contexts", type=int, default=4, help="engine contexts (streams) per GPU sharing one weight copy")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

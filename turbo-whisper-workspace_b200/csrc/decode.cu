@@ -328,12 +328,13 @@ __global__ void __launch_bounds__(256, 1) lmhead_kernel(const SkinnyParams p) {
     const int rounds = p.K / (32 * UN);  // K % 128 == 0
 
     pdl_launch_dependents();
-    uint4 alo[2][UN], ahi[2][UN];
-    if (gwarp < n_slabs) {  // first round of this warp's first slab: independent of the previous kernel
+    // two named fragment buffers (no dynamically indexed arrays: those would live in local memory)
+    uint4 a0lo[UN], a0hi[UN], a1lo[UN], a1hi[UN];
+    if (gwarp < n_slabs) {  // round 0 of this warp's first slab: independent of the previous kernel
         const __nv_bfloat16* wa0 = p.W + (size_t)min(gwarp * 16 + g, p.N - 1) * p.K + tg * 8;
         const __nv_bfloat16* wb0 = p.W + (size_t)min(gwarp * 16 + g + 8, p.N - 1) * p.K + tg * 8;
 #pragma unroll
-        for (int u = 0; u < UN; ++u) { alo[0][u] = ldg_stream(wa0 + u * 32); ahi[0][u] = ldg_stream(wb0 + u * 32); }
+        for (int u = 0; u < UN; ++u) { a0lo[u] = ldg_stream(wa0 + u * 32); a0hi[u] = ldg_stream(wb0 + u * 32); }
     }
     pdl_wait();
     // per-thread running partials for its 2*NB batch columns (j*8 + 2*tg + e)
@@ -350,37 +351,58 @@ __global__ void __launch_bounds__(256, 1) lmhead_kernel(const SkinnyParams p) {
 #pragma unroll
     for (int j = 0; j < NB; ++j) xr[j] = p.X + (size_t)min(j * 8 + g, p.B - 1) * p.ldx + tg * 8;
 
+    // Buffer 0 always holds the round about to be computed.  When a slab's last round sits in buffer 1 (even number
+    // of rounds) buffer 0 receives round 0 of the warp's NEXT slab meanwhile, so the weight stream does not stop
+    // while the logits of this slab are masked and reduced.
+    bool have_first = true;   // buffer 0 already holds round 0 of the current slab
     for (int slab = gwarp; slab < n_slabs; slab += nwarps) {
         const int n0 = slab * 16;
         const __nv_bfloat16* wa = p.W + (size_t)min(n0 + g, p.N - 1) * p.K + tg * 8;
         const __nv_bfloat16* wb = p.W + (size_t)min(n0 + g + 8, p.N - 1) * p.K + tg * 8;
+        const int nslab = slab + nwarps;
         float acc[NB][4];
 #pragma unroll
         for (int j = 0; j < NB; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-        if (slab != gwarp) {
+        if (!have_first) {
 #pragma unroll
-            for (int u = 0; u < UN; ++u) { alo[0][u] = ldg_stream(wa + u * 32); ahi[0][u] = ldg_stream(wb + u * 32); }
+            for (int u = 0; u < UN; ++u) { a0lo[u] = ldg_stream(wa + u * 32); a0hi[u] = ldg_stream(wb + u * 32); }
         }
-#pragma unroll 2
-        for (int r = 0; r < rounds; ++r) {
-            const int cur = r & 1;
-            if (r + 1 < rounds) {
-#pragma unroll
-                for (int u = 0; u < UN; ++u) {
-                    alo[cur ^ 1][u] = ldg_stream(wa + ((r + 1) * UN + u) * 32);
-                    ahi[cur ^ 1][u] = ldg_stream(wb + ((r + 1) * UN + u) * 32);
-                }
-            }
+        have_first = false;
+        auto compute = [&](const uint4 (&lo)[UN], const uint4 (&hi)[UN], int r) {
 #pragma unroll
             for (int u = 0; u < UN; ++u) {
 #pragma unroll
                 for (int j = 0; j < NB; ++j) {
                     const uint4 xb = __ldg(reinterpret_cast<const uint4*>(xr[j] + (r * UN + u) * 32));
-                    mma_bf16_16816(acc[j], alo[cur][u].x, ahi[cur][u].x, alo[cur][u].y, ahi[cur][u].y, xb.x, xb.y);
-                    mma_bf16_16816(acc[j], alo[cur][u].z, ahi[cur][u].z, alo[cur][u].w, ahi[cur][u].w, xb.z, xb.w);
+                    mma_bf16_16816(acc[j], lo[u].x, hi[u].x, lo[u].y, hi[u].y, xb.x, xb.y);
+                    mma_bf16_16816(acc[j], lo[u].z, hi[u].z, lo[u].w, hi[u].w, xb.z, xb.w);
                 }
             }
+        };
+        int r = 0;
+        for (; r + 1 < rounds; r += 2) {
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                a1lo[u] = ldg_stream(wa + ((r + 1) * UN + u) * 32);
+                a1hi[u] = ldg_stream(wb + ((r + 1) * UN + u) * 32);
+            }
+            compute(a0lo, a0hi, r);
+            if (r + 2 < rounds) {
+#pragma unroll
+                for (int u = 0; u < UN; ++u) {
+                    a0lo[u] = ldg_stream(wa + ((r + 2) * UN + u) * 32);
+                    a0hi[u] = ldg_stream(wb + ((r + 2) * UN + u) * 32);
+                }
+            } else if (nslab < n_slabs) {
+                const __nv_bfloat16* na = p.W + (size_t)min(nslab * 16 + g, p.N - 1) * p.K + tg * 8;
+                const __nv_bfloat16* nb = p.W + (size_t)min(nslab * 16 + g + 8, p.N - 1) * p.K + tg * 8;
+#pragma unroll
+                for (int u = 0; u < UN; ++u) { a0lo[u] = ldg_stream(na + u * 32); a0hi[u] = ldg_stream(nb + u * 32); }
+                have_first = true;
+            }
+            compute(a1lo, a1hi, r + 1);
         }
+        if (r < rounds) compute(a0lo, a0hi, r);   // odd number of rounds: the last one is in buffer 0
         // acc[j][e]: vocab row n0+g (e<2) / n0+g+8 (e>=2), batch row j*8 + 2*tg + (e&1)
         // Slab-level facts are warp-uniform: the 16 suppress bits of the slab come from one 32-bit word, and a slab
         // is all-text (99 % of them), all-timestamp or the single mixed one, so the unused reduction is skipped.

@@ -149,7 +149,7 @@ class B200WhisperPipeline:
 
     def __init__(self, state_dict, dims: WhisperDims, tokenizer, generation: Optional[GenerationSettings] = None,
                  devices: Sequence[Union[str, int]] = ("cuda:0",), max_batch: int = 24, time_precision: float = 0.02,
-                 scheduler=None, contexts_per_device: int = 2):
+                 scheduler=None, contexts_per_device: int = 4):
         """``scheduler``: any object with ``run(clips, task=, language=) -> token rows`` and ``last_stats``;
         defaults to a :class:`WindowScheduler` with one GPU engine per entry of ``devices``."""
         self.dims = dims
@@ -166,7 +166,7 @@ class B200WhisperPipeline:
 
     @classmethod
     def from_hf_model(cls, model, tokenizer, devices=("cuda:0",), max_batch: int = 24,
-                      contexts_per_device: int = 2) -> "B200WhisperPipeline":
+                      contexts_per_device: int = 4) -> "B200WhisperPipeline":
         """Build from a ``transformers.WhisperForConditionalGeneration`` (weights, config, generation_config)."""
         dims = WhisperDims.from_hf_config(model.config)
         gen = GenerationSettings.from_hf(model.generation_config)
