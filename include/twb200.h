@@ -194,6 +194,36 @@ int tw_dec_finalize(const float* part_val, const int32_t* part_idx, int32_t n_pa
                     int32_t tokens_ld, const int32_t* forced, int32_t* choices, void* row_state,
                     const tw_grammar* g, int32_t batch, void* stream);
 
+/* ---- host: per-window token streams -> timestamped chunks ------------------------------------------------
+ * Replaces tokenizer._decode_asr / _find_longest_common_sequence for return_timestamps in {False, True}
+ * ($TF/models/whisper/tokenization_whisper.py:901-1150, 1153-1270; called from the pipeline's postprocess,
+ * $TF/pipelines/automatic_speech_recognition.py:562-656).  Token ids in, token ids + times out; no device work. */
+typedef struct tw_asr_window {
+    const int32_t* tokens;      /* generated ids of one window (prompt, specials, timestamps and text) */
+    int32_t n_tokens;
+    int32_t has_stride;         /* 0: the window carries no stride triple */
+    double chunk_len, stride_left, stride_right;   /* seconds, as the pipeline's postprocess passes them */
+} tw_asr_window;
+
+typedef struct tw_asr_config {
+    int32_t timestamp_begin;          /* id of <|0.00|> */
+    int32_t prompt_token_id;          /* <|startofprev|> */
+    int32_t decoder_start_token_id;   /* <|startoftranscript|> */
+    int32_t return_timestamps;        /* 0 / 1 (word timestamps are not handled here) */
+    int32_t segment_size;             /* encoder positions per window (1500) */
+    int32_t n_special;
+    const int32_t* special_ids;       /* sorted ascending: tokenizer.all_special_ids */
+    const int32_t* special_lang;      /* per special id: language index >= 0, or -1 for any other special token */
+    double time_precision;            /* seconds per timestamp step (0.02) */
+} tw_asr_config;
+
+/* Chunk c owns out_tokens[chunk_offsets[c] .. chunk_offsets[c+1]); chunk_t0 / chunk_t1 are NaN where Python has
+ * None; chunk_lang is a language index or -1.  flags bit 0: the last chunk has no closing timestamp.
+ * Capacities: out_tokens_cap >= total input tokens, max_chunks (+1 offsets) >= total input tokens + 1. */
+int tw_decode_asr(const tw_asr_window* windows, int32_t n_windows, const tw_asr_config* cfg, int32_t* out_tokens,
+                  int64_t out_tokens_cap, int64_t* chunk_offsets, double* chunk_t0, double* chunk_t1,
+                  int32_t* chunk_lang, int32_t max_chunks, int32_t* n_chunks_out, int32_t* flags_out);
+
 #ifdef __cplusplus
 }
 #endif

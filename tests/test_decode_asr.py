@@ -1,0 +1,158 @@
+"""CPU parity of the native token -> chunk stitching (tw_decode_asr + byte-level text decode) against the
+implementation the reference delegates to: transformers' tokenizer._decode_asr (5.5.0, installed here).
+Thousands of randomised multi-window token streams (timestamps in and out of order, strides, seek segments,
+language switches, duplicated timestamps, invalid UTF-8 across token boundaries) must give the identical
+(text, chunks) — times bit-identical — for return_timestamps True and False, with and without return_language."""
+import ctypes as C
+import random
+
+import numpy as np
+import pytest
+
+import helpers
+
+TB = 50365           # <|0.00|>
+EOS, SOT, TRANSLATE, TRANSCRIBE, PREV, NOSPEECH, NOTS = 50257, 50258, 50359, 50360, 50362, 50363, 50364
+PREC = 0.02
+
+
+@pytest.fixture(scope="module")
+def tok():
+    return helpers.build_tokenizer()
+
+
+@pytest.fixture(scope="module")
+def dec(tok):
+    from turbo_whisper_workspace_b200.decode_asr import AsrDecoder
+    return AsrDecoder(tok)
+
+
+def _text_run(rng, pool, lo=0, hi=12):
+    return [rng.choice(pool) for _ in range(rng.randint(lo, hi))]
+
+
+def _window_tokens(rng, pool, chunk_s, two_segments, with_ts):
+    """A plausible (and sometimes implausible) generate() output for one window."""
+    ids = [SOT, 50259 + rng.choice([0, 0, 0, 2, 6]), TRANSCRIBE]
+    if not with_ts:
+        ids.append(NOTS)
+        return ids + _text_run(rng, pool, 0, 30) + ([EOS] if rng.random() < 0.5 else [])
+    steps = int(chunk_s / PREC)
+    t = rng.randint(0, 20)
+    n_seg = rng.randint(0, 7)
+    for s in range(n_seg):
+        if t >= steps:
+            break
+        e = min(steps, t + rng.randint(1, 400))
+        ids.append(TB + t)
+        ids += _text_run(rng, pool)
+        r = rng.random()
+        if r < 0.85:
+            ids.append(TB + e)
+            if rng.random() < 0.1:
+                ids.append(TB + e)          # duplicated timestamp
+        elif r < 0.93:
+            pass                            # missing end timestamp (cut mid-word)
+        else:
+            ids.append(TB + t)              # end == start (the "bug" case the reference tolerates)
+        t = e + (0 if rng.random() < 0.7 else rng.randint(0, 30))
+    if two_segments:                        # a second seek segment: timestamps restart from a small value
+        t = rng.randint(0, 50)
+        single_end = rng.random() < 0.5
+        if single_end and ids[-1] >= TB:
+            ids += _text_run(rng, pool, 1, 4)
+        for s in range(rng.randint(1, 3)):
+            e = min(steps, t + rng.randint(1, 300))
+            ids += [TB + t] + _text_run(rng, pool) + [TB + e]
+            t = e
+    if rng.random() < 0.3:
+        ids += _text_run(rng, pool, 1, 5)   # trailing text without a timestamp
+    if rng.random() < 0.5:
+        ids.append(EOS)
+    return ids
+
+
+def _make_case(rng, pool, with_ts):
+    n_win = rng.randint(1, 5)
+    mode = rng.choice(["stride", "stride", "nostride", "zero"])
+    outs = []
+    for w in range(n_win):
+        chunk_s = rng.choice([30.0, 30.0, 12.34, 7.5])
+        ids = _window_tokens(rng, pool, chunk_s, two_segments=rng.random() < 0.25, with_ts=with_ts)
+        if rng.random() < 0.1:
+            ids = [PREV] + _text_run(rng, pool, 1, 4) + ids           # prompt to strip
+        rec = {"tokens": np.asarray([ids], dtype=np.int64)}
+        if mode != "nostride":
+            sl = 0.0 if (w == 0 or mode == "zero") else rng.choice([5.0, 2.5, 1.0])
+            sr = 0.0 if (w == n_win - 1 or mode == "zero") else rng.choice([5.0, 2.5, 1.0])
+            rec["stride"] = (chunk_s, sl, sr)
+        outs.append(rec)
+    # make consecutive windows overlap in text now and then so that the merge has something to find
+    for w in range(1, n_win):
+        if rng.random() < 0.5:
+            prev = [t for t in outs[w - 1]["tokens"][0].tolist() if t < EOS]
+            if len(prev) >= 3:
+                k = rng.randint(2, min(6, len(prev)))
+                cur = outs[w]["tokens"][0].tolist()
+                pos = next((i for i, t in enumerate(cur) if t >= TB), len(cur)) + 1
+                cur[pos:pos] = prev[-k:]
+                outs[w]["tokens"] = np.asarray([cur], dtype=np.int64)
+    return outs
+
+
+@pytest.mark.parametrize("with_ts", [True, False])
+def test_random_streams_match_transformers(tok, dec, with_ts):
+    rng = random.Random(1234 + int(with_ts))
+    # text pool: printable ASCII bytes, bytes that form multi-byte UTF-8 only in combination (invalid sequences
+    # appear and must be replaced the same way), and multi-character "words"
+    pool = list(range(33, 127)) + [195, 169, 226, 130, 172, 240, 159, 152, 128, 255, 192] + list(range(300, 340))
+    n_cases = 1500
+    for case in range(n_cases):
+        outs = _make_case(rng, pool, with_ts)
+        rl = rng.random() < 0.3
+        want = tok._decode_asr(outs, return_timestamps=with_ts, return_language=rl, time_precision=PREC)
+        got = dec(outs, return_timestamps=with_ts, return_language=rl, time_precision=PREC)
+        assert got[0] == want[0], (case, outs)
+        wc, gc = want[1].get("chunks"), got[1].get("chunks")
+        assert (wc is None) == (gc is None), case
+        if wc is not None:
+            assert len(wc) == len(gc), (case, wc, gc)
+            for a, b in zip(wc, gc):
+                assert dict(a) == dict(b), (case, a, b)
+
+
+def test_golden_pipeline_outputs_reproduced(tok, dec):
+    """The stored transformers pipeline goldens (tests/golden) were produced from token lists by HF's _decode_asr;
+    replaying HF on a long real-shaped case and comparing against the native path closes the loop on real strides."""
+    rng = random.Random(7)
+    pool = list(range(300, 2000))
+    outs = []
+    for w in range(8):
+        ids = [SOT, 50259, TRANSCRIBE]
+        t = 0
+        while t < 1400:
+            e = min(1500, t + rng.randint(20, 300))
+            ids += [TB + t] + [rng.choice(pool) for _ in range(rng.randint(3, 40))] + [TB + e]
+            t = e
+        outs.append({"tokens": np.asarray([ids]), "stride": (30.0, 0.0 if w == 0 else 5.0, 0.0 if w == 7 else 5.0)})
+    want = tok._decode_asr(outs, return_timestamps=True, return_language=None, time_precision=PREC)
+    got = dec(outs, return_timestamps=True, return_language=None, time_precision=PREC)
+    assert got[0] == want[0]
+    assert [dict(c) for c in got[1]["chunks"]] == [dict(c) for c in want[1]["chunks"]]
+    assert len(got[1]["chunks"]) > 20
+
+
+def test_language_table_matches_transformers():
+    from transformers.models.whisper.tokenization_whisper import LANGUAGES
+    from turbo_whisper_workspace_b200.decode_asr import LANGUAGE_NAMES
+    assert list(LANGUAGE_NAMES.items()) == list(LANGUAGES.items())
+
+
+def test_error_reporting(dec):
+    from turbo_whisper_workspace_b200 import _lib
+    lib = _lib.load()
+    n = C.c_int32(0)
+    assert lib.tw_decode_asr(None, 1, None, None, 0, None, None, None, None, 0, C.byref(n), None) != 0
+    assert b"tw_decode_asr" in lib.tw_last_error()
+    with pytest.raises(NotImplementedError):
+        dec([], return_timestamps="word", time_precision=PREC)

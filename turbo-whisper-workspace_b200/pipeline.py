@@ -11,8 +11,10 @@ logic of ``AutomaticSpeechRecognitionPipeline`` (transformers 5.5.0, ``$TF/``):
   * _forward (stride plumbing)  $TF/pipelines/automatic_speech_recognition.py:479-560
   * postprocess                 $TF/pipelines/automatic_speech_recognition.py:562-656
   * batching of windows         $TF/pipelines/base.py:1298-1318, $TF/pipelines/pt_utils.py:156-298
-Token -> text/chunk stitching is the tokenizer's own ``_decode_asr`` (the tokenizer object is an input
-of the pipeline, exactly as in HF).  Everything between PCM and token ids runs on the GPU engine(s).
+Token -> text/chunk stitching ($TF/models/whisper/tokenization_whisper.py:901-1270) is native as well:
+:class:`decode_asr.AsrDecoder` (C library ``tw_decode_asr`` + a byte table built once from the tokenizer's
+vocabulary); the tokenizer object is only an input of the pipeline, exactly as in HF.  Everything between PCM and
+token ids runs on the GPU engine(s).
 """
 from __future__ import annotations
 
@@ -162,6 +164,8 @@ class B200WhisperPipeline:
             scheduler = WindowScheduler(state_dict, dims, self.generation, devices, max_batch,
                                         contexts_per_device=contexts_per_device)
         self.scheduler = scheduler
+        from .decode_asr import AsrDecoder
+        self.asr_decoder = AsrDecoder(tokenizer, segment_size=dims.max_source_positions)
         self.last_stats: Dict[str, Any] = {}
 
     @classmethod
@@ -239,8 +243,12 @@ class B200WhisperPipeline:
                     ln, sl, srr = windows[g0 + i][2]
                     item["stride"] = (ln / sr, sl / sr, srr / sr)
                 model_outputs.append(item)
-        text, optional = self.tokenizer._decode_asr(model_outputs, return_timestamps=return_timestamps,
-                                                    return_language=return_language, time_precision=self.time_precision)
+        text, optional = self.asr_decoder(model_outputs, return_timestamps=return_timestamps,
+                                          return_language=return_language, time_precision=self.time_precision)
+        if return_timestamps and self.asr_decoder.last_flags & 1:
+            import logging
+            logging.getLogger(__name__).warning(
+                "Whisper did not predict an ending timestamp, which can happen if audio is cut off in the middle of a word.")
         return {"text": text, **optional, **{k: [v] for k, v in extra.items()}}
 
     def close(self):
