@@ -194,6 +194,17 @@ int tw_dec_finalize(const float* part_val, const int32_t* part_idx, int32_t n_pa
                     int32_t tokens_ld, const int32_t* forced, int32_t* choices, void* row_state,
                     const tw_grammar* g, int32_t batch, void* stream);
 
+/* ---- audio ingest: format conversion + channel down-mix + polyphase windowed-sinc resampling ---------------
+ * Replaces torchaudio.functional.resample (sinc_interp_hann, lowpass_filter_width 6, rolloff 0.99) in the pipeline's
+ * preprocess ($TF/pipelines/automatic_speech_recognition.py:394-407) and the sample conversion / `-ac 1` down-mix
+ * of the file reader ($TF/pipelines/audio_utils.py:9-45).  `in`: device, [n_in, channels] interleaved float32 or
+ * int16 (scaled by 1/32768); rates already divided by their gcd; filt: device fp32 [new_rate, 2*width + orig_rate]
+ * (the torchaudio filter bank), span: device int32 [new_rate, 2] = first non-zero tap and tap count per phase;
+ * out: device fp32 [n_out], n_out <= ceil(new_rate * n_in / orig_rate). */
+int tw_resample(const void* in, int32_t in_is_int16, int32_t channels, int64_t n_in, float* out, int64_t n_out,
+                const float* filt, const int32_t* span, int32_t orig_rate, int32_t new_rate, int32_t width,
+                void* stream);
+
 /* ---- host: per-window token streams -> timestamped chunks ------------------------------------------------
  * Replaces tokenizer._decode_asr / _find_longest_common_sequence for return_timestamps in {False, True}
  * ($TF/models/whisper/tokenization_whisper.py:901-1150, 1153-1270; called from the pipeline's postprocess,

@@ -193,3 +193,31 @@ def test_shift_frames(ops, cuda_device):
     assert torch.equal(dst[0, 1:3001 - 1234], src[2, 1235:3001])
     assert float(dst[0, 3001 - 1234:].abs().max()) == 0.0
     assert torch.equal(dst[1], src[0])
+
+
+# ------------------------------------------------------------------ K0 audio ingest (convert + down-mix + resample)
+@pytest.mark.parametrize("orig,ch,dtype", [(48000, 1, "f32"), (44100, 2, "i16"), (8000, 1, "i16"), (22050, 3, "f32")])
+def test_resample_matches_torchaudio(ops, cuda_device, orig, ch, dtype):
+    """tw_resample vs torchaudio.functional.resample on the channel mean (the reference's preprocess branch,
+    $TF/pipelines/automatic_speech_recognition.py:394-407).  fp32 dot products of ~35 taps in a different summation order than conv1d: 1e-5 absolute on
+    |x| <= 0.8 (a third of a 16-bit LSB)."""
+    import torchaudio.functional as AF
+    g = torch.Generator().manual_seed(orig + ch)
+    n = orig * 3 + 1234
+    x = torch.rand(n, ch, generator=g) * 1.6 - 0.8
+    if dtype == "i16":
+        xi = (x * 32767).round().to(torch.int16)
+        host = xi.float() / 32768.0
+        dev_in = xi.to(cuda_device)
+    else:
+        host = x
+        dev_in = x.to(cuda_device)
+    want = AF.resample(host.mean(dim=1), orig, 16000)
+    rs = ops.Resampler(orig, 16000, cuda_device)
+    got = rs(dev_in if ch > 1 else dev_in[:, 0].contiguous()).cpu()
+    assert got.shape == want.shape
+    assert float((got - want).abs().max()) < 1e-5
+    # empty and tiny inputs
+    assert rs(torch.zeros(0, dtype=torch.float32, device=cuda_device)).numel() == 0
+    tiny = torch.ones(5, dtype=torch.float32, device=cuda_device)
+    assert torch.allclose(rs(tiny).cpu(), AF.resample(torch.ones(5), orig, 16000), atol=1e-5)

@@ -137,3 +137,27 @@ def test_multi_gpu_single_process_sharding(gold, long_wav):
                            max_batch=2, contexts_per_device=2)
     assert many.run(clips) == one.run(clips)
     assert many.last_stats["workers"] == torch.cuda.device_count()
+
+
+def test_pipeline_ingests_other_sample_rates(pipes, tmp_path):
+    """A 44.1 kHz stereo PCM16 WAV and a {"raw", "sampling_rate": 8000} dict go through the GPU ingest kernel and
+    give the PCM torchaudio's resample (the reference's branch) produces; the transcription call runs on it."""
+    import wave
+    import torchaudio.functional as AF
+    from turbo_whisper_workspace_b200 import pipeline as P
+    pipe = pipes["decisive"]
+    rng = np.random.default_rng(3)
+    x = (rng.standard_normal((44100 * 4, 2)) * 0.1).clip(-1, 1)
+    xi = (x * 32767).round().astype("<i2")
+    path = tmp_path / "stereo44k.wav"
+    with wave.open(str(path), "wb") as wf:
+        wf.setnchannels(2); wf.setsampwidth(2); wf.setframerate(44100); wf.writeframes(xi.tobytes())
+    audio, _ = P.load_audio(str(path), 16000, pipe.ingest_device)
+    want = AF.resample(torch.from_numpy(xi.astype(np.float32) / 32768.0).mean(dim=1), 44100, 16000).numpy()
+    assert audio.shape == want.shape and float(np.abs(audio - want).max()) < 1e-5
+    y = (rng.standard_normal(8000 * 3) * 0.1).astype(np.float32)
+    audio2, _ = P.load_audio({"raw": y, "sampling_rate": 8000}, 16000, pipe.ingest_device)
+    want2 = AF.resample(torch.from_numpy(y), 8000, 16000).numpy()
+    assert audio2.shape == want2.shape and float(np.abs(audio2 - want2).max()) < 1e-5
+    r = pipe(str(path), chunk_length_s=30, batch_size=4, return_timestamps=True)
+    assert set(r) == {"text", "chunks"} and len(r["chunks"]) >= 1

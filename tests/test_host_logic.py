@@ -128,3 +128,21 @@ def test_mel_filters_match_oracle():
     from oracle import logmel_ref as L
     from turbo_whisper_workspace_b200.ops import slaney_mel_filters
     np.testing.assert_array_equal(slaney_mel_filters(), L.mel_filter_bank().astype(np.float32))
+
+
+# ------------------------------------------------------------------ audio ingest (filter bank of the GPU resampler)
+@pytest.mark.parametrize("orig,new", [(48000, 16000), (44100, 16000), (8000, 16000), (22050, 16000), (11025, 16000)])
+def test_resample_filter_bank_is_torchaudios(orig, new):
+    """The GPU ingest kernel consumes the torchaudio filter bank: bit-identical construction (including torchaudio's
+    fp32 phase offsets), and the per-phase non-zero span the kernel walks loses nothing."""
+    import math
+    import torch
+    from torchaudio.functional import functional as AF
+    from turbo_whisper_workspace_b200.ops import sinc_resample_filters
+    want, w = AF._get_sinc_resample_kernel(orig, new, math.gcd(orig, new))
+    got, w2, o, n = sinc_resample_filters(orig, new)
+    assert (w2, got.shape) == (w, tuple(want[:, 0, :].shape)) and (o, n) == (orig // math.gcd(orig, new), new // math.gcd(orig, new))
+    assert np.array_equal(got, want[:, 0, :].numpy())
+    nz = np.abs(got) > 1e-30
+    assert float(np.abs(got[~nz]).sum()) < 1e-25          # what the span skips is numerically nothing
+    assert int(nz.sum(axis=1).max()) <= 2 * w + 2          # ~2*width useful taps per phase, not 2*width + orig

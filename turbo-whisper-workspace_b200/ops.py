@@ -153,3 +153,66 @@ def shift_frames(src, dst, seek, src_row=None, frames: int = N_FRAMES, row_off: 
         check(lib.tw_shift_frames(_ptr(src), _ptr(dst), _ptr(src_row), _ptr(seek), B, frames, src.shape[2],
                                   src.stride(0), row_off, _stream()), "tw_shift_frames")
     return dst
+
+
+# ------------------------------------------------------------------------------------------------
+# K0: audio ingest (format conversion + down-mix + windowed-sinc resampling)
+# ------------------------------------------------------------------------------------------------
+def sinc_resample_filters(orig_freq: int, new_freq: int, lowpass_filter_width: int = 6, rolloff: float = 0.99):
+    """Filter bank of torchaudio.functional.resample (sinc_interp_hann): fp32 [new, 2*width + orig] for the
+    gcd-reduced rates, plus width.  Same arithmetic, including torchaudio's fp32 phase offset -i/new that is
+    promoted to fp64 before the rest of the computation; the result is cast to fp32 at the end."""
+    import math
+    g = math.gcd(int(orig_freq), int(new_freq))
+    orig, new = int(orig_freq) // g, int(new_freq) // g
+    base = min(orig, new) * rolloff
+    width = math.ceil(lowpass_filter_width * orig / base)
+    idx = np.arange(-width, width + orig, dtype=np.float64)[None, :] / orig
+    phase = (np.arange(0, -new, -1, dtype=np.int64).astype(np.float32) / np.float32(new)).astype(np.float64)[:, None]
+    t = (phase + idx) * base
+    t = np.clip(t, -lowpass_filter_width, lowpass_filter_width)
+    window = np.cos(t * math.pi / lowpass_filter_width / 2) ** 2
+    t = t * math.pi
+    with np.errstate(invalid="ignore", divide="ignore"):
+        k = np.where(t == 0, 1.0, np.sin(t) / t)
+    k = k * window * (base / orig)
+    return k.astype(np.float32), width, orig, new
+
+
+class Resampler:
+    """GPU replacement of ``torchaudio.functional.resample(x, orig_freq, new_freq)`` for mono or interleaved
+    multi-channel PCM (float32 or int16): one fused pass that converts, averages the channels and resamples."""
+
+    def __init__(self, orig_freq: int, new_freq: int, device):
+        self.device = torch.device(device)
+        filt, self.width, self.orig, self.new = sinc_resample_filters(orig_freq, new_freq)
+        # non-zero span of every phase (the clamped tails of the window are exactly or numerically zero)
+        nz = np.abs(filt) > 1e-30
+        first = nz.argmax(axis=1)
+        last = filt.shape[1] - 1 - nz[:, ::-1].argmax(axis=1)
+        span = np.stack([first, last - first + 1], axis=1).astype(np.int32)
+        self.filt = torch.from_numpy(np.ascontiguousarray(filt)).to(self.device)
+        self.span = torch.from_numpy(span).to(self.device)
+        self.taps = int(span[:, 1].max())
+
+    def out_len(self, n_in: int) -> int:
+        return -((-self.new * int(n_in)) // self.orig)   # ceil(new * n / orig), as torchaudio
+
+    def __call__(self, x: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+        """x: device tensor [n] or [n, channels], float32 or int16 -> fp32 [ceil(new*n/orig)] (channel mean)."""
+        _need_cuda(x)
+        if x.dtype not in (torch.float32, torch.int16):
+            raise _lib.TwError(f"Resampler: unsupported sample dtype {x.dtype}")
+        x = x.contiguous()
+        n_in = int(x.shape[0])
+        ch = 1 if x.dim() == 1 else int(x.shape[1])
+        n_out = self.out_len(n_in)
+        if out is None:
+            out = torch.empty(n_out, dtype=torch.float32, device=x.device)
+        if n_out == 0:
+            return out
+        with torch.cuda.device(x.device):
+            check(_lib.load().tw_resample(_ptr(x), 1 if x.dtype == torch.int16 else 0, ch, n_in, _ptr(out), n_out,
+                                          _ptr(self.filt), _ptr(self.span), self.orig, self.new, self.width, _stream()),
+                  "tw_resample")
+        return out

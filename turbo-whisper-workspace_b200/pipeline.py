@@ -31,8 +31,8 @@ from .config import N_SAMPLES, SAMPLING_RATE, GenerationSettings, WhisperDims
 # ------------------------------------------------------------------------------------------------
 # audio ingest (host)
 # ------------------------------------------------------------------------------------------------
-def _read_wav_bytes(payload: bytes, sampling_rate: int) -> Optional[np.ndarray]:
-    """RIFF/WAVE PCM16 / PCM32 / 8-bit reader for 16 kHz files; returns None when not applicable."""
+def _read_wav(payload: bytes) -> Optional[Tuple[np.ndarray, int]]:
+    """RIFF/WAVE PCM reader (8 / 16 / 32-bit): (samples [n, channels] int16 or float32, sample rate), or None."""
     if len(payload) < 12 or payload[:4] != b"RIFF" or payload[8:12] != b"WAVE":
         return None
     try:
@@ -41,28 +41,45 @@ def _read_wav_bytes(payload: bytes, sampling_rate: int) -> Optional[np.ndarray]:
             raw = wf.readframes(n)
     except wave.Error:
         return None
-    if sr != sampling_rate:
-        return None
     if sw == 2:
-        x = np.frombuffer(raw, dtype="<i2").astype(np.float32) / 32768.0
+        x = np.frombuffer(raw, dtype="<i2")
     elif sw == 4:
         x = np.frombuffer(raw, dtype="<i4").astype(np.float32) / 2147483648.0
     elif sw == 1:
         x = (np.frombuffer(raw, dtype=np.uint8).astype(np.float32) - 128.0) / 128.0
     else:
         return None
-    if ch > 1:
-        x = x.reshape(-1, ch).mean(axis=1)
-    return np.ascontiguousarray(x, dtype=np.float32)
+    return x.reshape(-1, ch), sr
 
 
-def ffmpeg_read(payload: bytes, sampling_rate: int) -> np.ndarray:
-    """bytes -> mono fp32 at ``sampling_rate`` ($TF/pipelines/audio_utils.py:9-45).  16 kHz WAV files are
-    decoded in-process; anything else goes through the same ``ffmpeg -i pipe:0 -ac 1 -ar SR -f f32le``
-    subprocess HF uses."""
-    x = _read_wav_bytes(payload, sampling_rate)
-    if x is not None:
-        return x
+_RESAMPLERS: Dict[Tuple[int, int, str], Any] = {}
+
+
+def gpu_resample(x: np.ndarray, in_sr: int, out_sr: int, device) -> np.ndarray:
+    """[n] or [n, channels] int16 / float32 host samples -> mono fp32 at ``out_sr`` through the fused GPU ingest
+    kernel (conversion + channel mean + torchaudio-compatible windowed-sinc resampling; ops.Resampler)."""
+    import torch
+    from . import ops
+    key = (int(in_sr), int(out_sr), str(device))
+    rs = _RESAMPLERS.get(key)
+    if rs is None:
+        rs = _RESAMPLERS[key] = ops.Resampler(in_sr, out_sr, device)
+    t = torch.from_numpy(np.ascontiguousarray(x if x.dtype == np.int16 else x.astype(np.float32))).to(rs.device)
+    return rs(t).cpu().numpy()
+
+
+def ffmpeg_read(payload: bytes, sampling_rate: int, device=None) -> np.ndarray:
+    """bytes -> mono fp32 at ``sampling_rate`` ($TF/pipelines/audio_utils.py:9-45).  WAV files are decoded
+    in-process — at the target rate on the host, at any other rate through the GPU ingest kernel when a device is
+    given; anything else goes through the same ``ffmpeg -i pipe:0 -ac 1 -ar SR -f f32le`` subprocess HF uses."""
+    wav = _read_wav(payload)
+    if wav is not None:
+        x, sr = wav
+        if sr == sampling_rate:
+            x = x.astype(np.float32) / 32768.0 if x.dtype == np.int16 else x
+            return np.ascontiguousarray(x[:, 0] if x.shape[1] == 1 else x.mean(axis=1), dtype=np.float32)
+        if device is not None:
+            return gpu_resample(x, sr, sampling_rate, device)
     cmd = ["ffmpeg", "-i", "pipe:0", "-ac", "1", "-ar", str(sampling_rate), "-f", "f32le", "-hide_banner",
            "-loglevel", "quiet", "pipe:1"]
     try:
@@ -77,9 +94,11 @@ def ffmpeg_read(payload: bytes, sampling_rate: int) -> np.ndarray:
     return audio
 
 
-def load_audio(inputs: Any, sampling_rate: int = SAMPLING_RATE) -> Tuple[np.ndarray, Dict[str, Any]]:
+def load_audio(inputs: Any, sampling_rate: int = SAMPLING_RATE, device=None) -> Tuple[np.ndarray, Dict[str, Any]]:
     """The input handling of ``preprocess`` ($TF/pipelines/automatic_speech_recognition.py:341-426):
-    str path | bytes | np.ndarray | torch.Tensor | {"raw"|"array", "sampling_rate"} -> fp32 mono PCM."""
+    str path | bytes | np.ndarray | torch.Tensor | {"raw"|"array", "sampling_rate"} -> fp32 mono PCM.
+    ``device``: CUDA device for the ingest kernel (resampling of arrays / WAV files that are not at 16 kHz);
+    without one the torchaudio call HF makes is used for arrays and ffmpeg for files."""
     extra: Dict[str, Any] = {}
     if isinstance(inputs, str):
         if inputs.startswith("http://") or inputs.startswith("https://"):
@@ -87,7 +106,7 @@ def load_audio(inputs: Any, sampling_rate: int = SAMPLING_RATE) -> Tuple[np.ndar
         with open(inputs, "rb") as f:
             inputs = f.read()
     if isinstance(inputs, bytes):
-        inputs = ffmpeg_read(inputs, sampling_rate)
+        inputs = ffmpeg_read(inputs, sampling_rate, device)
     if hasattr(inputs, "detach") and hasattr(inputs, "cpu"):  # torch.Tensor
         inputs = inputs.detach().cpu().numpy()
     if isinstance(inputs, dict):
@@ -107,7 +126,10 @@ def load_audio(inputs: Any, sampling_rate: int = SAMPLING_RATE) -> Tuple[np.ndar
         extra = inputs
         if hasattr(arr, "detach"):
             arr = arr.detach().cpu().numpy()
-        if in_sr != sampling_rate:
+        if in_sr != sampling_rate and device is not None:
+            a = np.asarray(arr)
+            arr = gpu_resample(a if a.ndim == 1 else a.mean(axis=0), in_sr, sampling_rate, device)
+        elif in_sr != sampling_rate:
             try:
                 import torch
                 from torchaudio import functional as AF
@@ -164,6 +186,8 @@ class B200WhisperPipeline:
             scheduler = WindowScheduler(state_dict, dims, self.generation, devices, max_batch,
                                         contexts_per_device=contexts_per_device)
         self.scheduler = scheduler
+        # device of the audio-ingest kernel (resampling of inputs that are not at 16 kHz); none with an injected scheduler
+        self.ingest_device = None if not hasattr(scheduler, "devices") else scheduler.devices[0]
         from .decode_asr import AsrDecoder
         self.asr_decoder = AsrDecoder(tokenizer, segment_size=dims.max_source_positions)
         self.last_stats: Dict[str, Any] = {}
@@ -200,7 +224,7 @@ class B200WhisperPipeline:
             raise ValueError("Whisper cannot return `char` timestamps, only word level or segment level timestamps. "
                              "Use `return_timestamps='word'` or `return_timestamps=True` respectively.")
 
-        audio, extra = load_audio(inputs, self.sampling_rate)
+        audio, extra = load_audio(inputs, self.sampling_rate, self.ingest_device)
         sr = self.sampling_rate
         if chunk_length_s:
             if stride_length_s is None:
