@@ -173,9 +173,11 @@ class WhisperRef:
     # -------------------------------------------------------------------------------- processors
     @staticmethod
     def process_logits(scores: torch.Tensor, generated: Sequence[Sequence[int]], gc: GenConfig,
-                       apply_rule: bool = True) -> torch.Tensor:
+                       apply_rule: bool = True, timestamps: bool = True) -> torch.Tensor:
         """SuppressTokens -> SuppressTokensAtBegin -> WhisperTimeStamp, on fp32 scores [B, V].
-        ``generated[k]`` = tokens of row k after the decoder prompt (begin_index)."""
+        ``generated[k]`` = tokens of row k after the decoder prompt (begin_index).  ``timestamps=False``: the
+        processor list of generate(return_timestamps=False) — no WhisperTimeStampLogitsProcessor
+        ($TF/models/whisper/generation_whisper.py, _retrieve_logit_processors)."""
         s = scores.clone().float()
         NEG = float("-inf")
         TB = gc.no_timestamps_token_id + 1
@@ -183,6 +185,8 @@ class WhisperRef:
         g = len(generated[0])
         if g == 0:
             s[:, gc.begin_suppress_tokens] = NEG
+        if not timestamps:
+            return s
         s[:, gc.no_timestamps_token_id] = NEG
         for k, seq in enumerate(generated):
             last_ts = len(seq) >= 1 and seq[-1] >= TB
@@ -221,7 +225,8 @@ class WhisperRef:
         logits = logits.masked_fill(mask[None], float("-inf"))
         return logits.argmax(-1).tolist()
 
-    def greedy(self, enc_out: torch.Tensor, prompt: torch.Tensor, gc: GenConfig, record: Optional[list] = None):
+    def greedy(self, enc_out: torch.Tensor, prompt: torch.Tensor, gc: GenConfig, record: Optional[list] = None,
+               timestamps: bool = True):
         """GenerationMixin._sample, greedy: returns generated tokens per row, [B, <=max_length-len(prompt)];
         finished rows keep emitting pad (= eos).  ``record`` collects (raw fp32 logits, processed scores)."""
         B, P = prompt.shape
@@ -231,8 +236,12 @@ class WhisperRef:
         logits = self.decode(prompt, enc_out, cache, 0)[:, -1]
         while True:
             gen = [tokens[k, P:].tolist() for k in range(B)]
-            scores = self.process_logits(logits, gen, gc)
-            if record is not None:
+            scores = self.process_logits(logits, gen, gc, timestamps=timestamps)
+            if record is not None and not timestamps:
+                top2 = scores.topk(2, dim=-1).values
+                record.append({"margin": (top2[:, 0] - top2[:, 1]), "rule_gap": torch.full((B,), float("inf")),
+                               "logits": None})
+            elif record is not None:
                 # decisiveness of this step: top-1 margin of the processed scores and the gap of the
                 # timestamp-probability rule; raw logits are kept only for the sampled steps
                 TB = gc.no_timestamps_token_id + 1
@@ -274,7 +283,7 @@ class WhisperRef:
         return [list(seq)], seek_num_frames
 
     def generate(self, feats: torch.Tensor, task: str = "transcribe", gc: Optional[GenConfig] = None,
-                 trace: Optional[dict] = None) -> List[List[int]]:
+                 trace: Optional[dict] = None, return_timestamps: bool = True) -> List[List[int]]:
         """WhisperGenerationMixin.generate for a batch of <=30 s windows (short-form), greedy, timestamps on.
         feats [B, n_mels, 3000] fp32.  Returns the generated ids per row (segments concatenated, no padding)."""
         gc = gc or GenConfig()
@@ -283,7 +292,8 @@ class WhisperRef:
         feats = feats.to(torch.float32)
         enc0 = self.encode(feats)
         langs = self.detect_language(enc0, gc)
-        init = torch.tensor([[gc.decoder_start_token_id, langs[b], gc.task_to_id[task]] for b in range(B)],
+        tail = [] if return_timestamps else [gc.no_timestamps_token_id]   # <|notimestamps|> joins the prompt
+        init = torch.tensor([[gc.decoder_start_token_id, langs[b], gc.task_to_id[task]] + tail for b in range(B)],
                             dtype=torch.long)
         seek = [0] * B
         max_frames = [feats.shape[-1]] * B
@@ -302,7 +312,7 @@ class WhisperRef:
                 seg[i, :, :nfr[b]] = feats[b, :, seek[b]:seek[b] + nfr[b]]
             enc = enc0 if (guard == 1) else self.encode(seg)
             rec = [] if trace is not None else None
-            toks = self.greedy(enc, init[rows], gc, record=rec)
+            toks = self.greedy(enc, init[rows], gc, record=rec, timestamps=return_timestamps)
             if trace is not None:
                 trace["iterations"].append({"rows": rows, "seek": [seek[b] for b in rows], "tokens": toks.clone(),
                                             "record": rec, "enc": enc})

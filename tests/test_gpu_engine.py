@@ -141,6 +141,30 @@ def test_generate_matches_oracle_decisive(setup):
     assert agreed >= 0.9 * sum(len(r) for r in want), f"only {agreed} tokens compared equal; diffs {first_diffs}"
 
 
+@pytest.mark.parametrize("variant", ["decisive", "varied"])
+def test_generate_without_timestamps_matches_oracle(setup, variant):
+    """return_timestamps=False: <|notimestamps|> joins the prompt (begin index 4), only the suppress lists apply and
+    every id competes in one arg-max; same margin rule as the timestamp mode."""
+    clips, feats, out = setup
+    ref, eng = out[variant]
+    fb = feats.to(torch.bfloat16).float()
+    trace, etrace = {}, {}
+    want = ref.generate(fb, trace=trace, return_timestamps=False)
+    B = eng.load_pcm(clips)
+    eng.features(B)
+    got = eng.generate(B, trace=etrace, return_timestamps=False)
+    assert all(row[3] == 50364 for it in etrace["iterations"] for row in it["tokens"]), "<|notimestamps|> must be forced"
+    # the oracle trace holds the generated part only; the engine rows carry the 4-token prompt
+    for it in etrace["iterations"]:
+        it["tokens"] = [row[1:] for row in it["tokens"]]     # compare_generate_traces skips 3 prompt tokens
+    agreed, identical_rows, first_diffs = helpers.compare_generate_traces(trace, etrace, MARGIN_TOL)
+    assert agreed >= 3 * B, f"free-running agreement is implausibly short: {first_diffs}"
+    for b in identical_rows:
+        assert got[b] == want[b], f"row {b}: identical raw tokens but different segment output"
+    # switching back to the timestamp grammar on the same engine (other begin index, other graph) still works
+    assert eng.generate(B)[0][0] >= 50365
+
+
 def test_generate_matches_oracle_varied_prefix(setup):
     """Free-running on the low-margin model: identical up to the first non-decisive oracle step."""
     clips, feats, out = setup

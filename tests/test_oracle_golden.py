@@ -98,6 +98,23 @@ def test_generate_oracle_vs_hf_golden(model_gold, variant):
         assert row == want, f"row {b}"
 
 
+@pytest.mark.parametrize("variant", ["decisive", "varied"])
+def test_generate_without_timestamps_oracle_vs_hf_golden(variant):
+    """generate(return_timestamps=False): <|notimestamps|> in the prompt, suppress lists only — token-exact with
+    transformers, including the extra seek iterations the (unmasked) timestamp ids of these random models cause."""
+    import json
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "notimestamps_tiny.json")))
+    _, fb = _clips_feats()
+    dims = R.WhisperDims(**helpers.TINY)
+    ref = R.WhisperRef(dims, helpers.variant_state_dict(dims, variant))
+    got = ref.generate(fb, return_timestamps=False)
+    for b, row in enumerate(got):
+        want = list(gold[f"{variant}_generate"][b])
+        while want and want[-1] == 50257:
+            want.pop()
+        assert row == want, f"row {b}"
+
+
 def test_retrieve_segment_cases():
     TB = R.TIMESTAMP_BEGIN
     f = R.WhisperRef.retrieve_segment

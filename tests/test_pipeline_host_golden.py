@@ -25,9 +25,9 @@ class OracleScheduler:
         self.ref = R.WhisperRef(rd, helpers.variant_state_dict(rd, variant))
         self.last_stats = {}
 
-    def run(self, clips, task="transcribe", language=None):
+    def run(self, clips, task="transcribe", language=None, return_timestamps=True):
         feats = torch.stack([torch.from_numpy(L.log_mel(c)) for c in clips])
-        return self.ref.generate(feats, task=task)
+        return self.ref.generate(feats, task=task, return_timestamps=return_timestamps)
 
 
 @pytest.fixture(scope="module")
@@ -56,3 +56,15 @@ def test_host_pipeline_matches_hf_golden(wav, variant, cl, st, bs):
     if (variant, cl, st) == ("varied", 60, 5):
         ref = gold["reference_process_audio_varied"]   # produced through vocalis...process_audio
         assert r["text"] == ref["text"] and _norm(r)["chunks"] == ref["segments"]
+
+
+@pytest.mark.parametrize("variant,cl,st,bs", [("varied", 30, 5, 24), ("decisive", 30, 0, 24)])
+def test_host_pipeline_without_timestamps_matches_hf_golden(wav, variant, cl, st, bs):
+    """return_timestamps omitted (the HF default): <|notimestamps|> generation + text-only merge of the windows;
+    the oracle's no-timestamp generate is pinned token-exact on the same golden file (test_oracle_golden.py)."""
+    gold = json.load(open(os.path.join(GOLD, "notimestamps_tiny.json")))
+    pipe = B200WhisperPipeline(None, WhisperDims(**helpers.TINY), helpers.build_tokenizer(),
+                               scheduler=OracleScheduler(variant))
+    r = pipe(wav, chunk_length_s=cl, stride_length_s=st, batch_size=bs, generate_kwargs={"task": "transcribe"})
+    g = gold[f"{variant}_{cl}_{st}_{bs}"]
+    assert sorted(r.keys()) == g["keys"] and r["text"] == g["text"]

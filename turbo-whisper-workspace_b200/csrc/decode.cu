@@ -39,7 +39,8 @@ struct RowState {
     int ts_lo;      // timestamp ids < ts_lo forbidden
     int ts_hi;      // timestamp ids > ts_hi forbidden (ts_hi < ts_lo: none allowed)
     int begin;      // 1 if the next token is the first generated one (begin-suppress applies)
-    int mode;       // 0 normal, 1 language detection (only language ids allowed)
+    int mode;       // bit 0: language detection at this step (only language ids allowed, cleared afterwards);
+                    // bit 1: row generates without timestamps (suppress lists only, plain arg-max)
 };
 
 struct GrammarConst {
@@ -159,7 +160,8 @@ TW_DEVINL void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t 
 
 TW_DEVINL bool token_allowed(int v, const RowState& s, const GrammarConst& gc, const uint32_t* sup,
                              const uint32_t* bsup) {
-    if (s.mode == 1) return v >= gc.lang_first && v <= gc.lang_last;
+    if (s.mode & 1) return v >= gc.lang_first && v <= gc.lang_last;
+    if (s.mode & 2) return !((sup[v >> 5] >> (v & 31)) & 1u) && !(s.begin && ((bsup[v >> 5] >> (v & 31)) & 1u));
     if ((sup[v >> 5] >> (v & 31)) & 1u) return false;
     if (s.begin && ((bsup[v >> 5] >> (v & 31)) & 1u)) return false;
     if (v == gc.no_timestamps) return false;
@@ -347,6 +349,11 @@ __global__ void __launch_bounds__(256, 1) lmhead_kernel(const SkinnyParams p) {
         const int bb = (c >> 1) * 8 + 2 * tg + (c & 1);
         st[c] = p.st[min(bb, p.B - 1)];
     }
+    // rows in language-detection or no-timestamp mode rank EVERY id in the "text" class, timestamp slabs included
+    bool flat = false;
+#pragma unroll
+    for (int c = 0; c < NB * 2; ++c) flat = flat || (st[c].mode != 0);
+    const bool any_flat = __any_sync(0xffffffffu, flat);
     const __nv_bfloat16* xr[NB];
 #pragma unroll
     for (int j = 0; j < NB; ++j) xr[j] = p.X + (size_t)min(j * 8 + g, p.B - 1) * p.ldx + tg * 8;
@@ -408,7 +415,7 @@ __global__ void __launch_bounds__(256, 1) lmhead_kernel(const SkinnyParams p) {
         // is all-text (99 % of them), all-timestamp or the single mixed one, so the unused reduction is skipped.
         const uint32_t sup16 = (p.suppress_bits[n0 >> 5] >> (n0 & 16)) & 0xffffu;
         const uint32_t bsup16 = (p.begin_suppress_bits[n0 >> 5] >> (n0 & 16)) & 0xffffu;
-        const bool slab_has_text = n0 < p.gc.ts_begin;
+        const bool slab_has_text = n0 < p.gc.ts_begin || any_flat;
         const bool slab_has_ts = n0 + 16 > p.gc.ts_begin;
 #pragma unroll
         for (int c = 0; c < NB * 2; ++c) {
@@ -427,7 +434,8 @@ __global__ void __launch_bounds__(256, 1) lmhead_kernel(const SkinnyParams p) {
                 if (bb < p.B && n < p.N) {
                     if (p.logits_out) p.logits_out[(size_t)bb * p.N + n] = v;
                     bool ok;
-                    if (rs.mode == 1) ok = n >= p.gc.lang_first && n <= p.gc.lang_last;
+                    if (rs.mode & 1) ok = n >= p.gc.lang_first && n <= p.gc.lang_last;
+                    else if (rs.mode & 2) ok = !((sup16 >> rr) & 1u) && !(rs.begin && ((bsup16 >> rr) & 1u));
                     else ok = !((sup16 >> rr) & 1u) && !(rs.begin && ((bsup16 >> rr) & 1u)) && n != p.gc.no_timestamps &&
                               (n >= p.gc.ts_begin ? (n >= rs.ts_lo && n <= rs.ts_hi) : n >= rs.text_lo);
                     if (ok) {
@@ -562,8 +570,8 @@ __global__ void __launch_bounds__(128) decode_finalize_kernel(const FinalizePara
         RowState s = p.st[b];
         const GrammarConst& gc = p.gc;
         int tok;
-        if (s.mode == 1) {
-            tok = it;  // language id arg-max
+        if (s.mode != 0) {
+            tok = it;  // language id arg-max / plain arg-max of the no-timestamp mode (every id is in the text class)
         } else {
             // sum of timestamp probability above every text token -> sample a timestamp
             // (log-softmax normaliser cancels on both sides of the comparison)
@@ -582,7 +590,7 @@ __global__ void __launch_bounds__(128) decode_finalize_kernel(const FinalizePara
         const int gen_before = wi - gc.begin_index;  // generated tokens before this one (may be < 0)
         if (gen_before >= 0 && tok == gc.eos) s.finished = 1;
         s.pos = wi;
-        s.mode = 0;
+        s.mode &= 2;   // language detection is over; the no-timestamp flag stays
         const int gen_now = gen_before + 1;  // generated tokens after appending tok
         if (gen_now <= 0) {
             // still inside the prompt: the next token is either forced or the first generated one

@@ -363,7 +363,8 @@ class WhisperEngine:
         return 1 + 8 * self.dims.dec_layers + 2
 
     def _graph_for(self, B: int) -> torch.cuda.CUDAGraph:
-        key = (B, self._ckv_batch)   # the K/V block stride depends on the encoder batch
+        # the K/V block stride depends on the encoder batch; begin_index (3 / 4 with <|notimestamps|>) is a kernel argument
+        key = (B, self._ckv_batch, int(self.grammar.begin_index))
         g = self._graphs.get(key)
         if g is None:
             # a warm-up step outside capture (sets kernel attributes); state is re-initialised afterwards
@@ -385,12 +386,14 @@ class WhisperEngine:
         return g
 
     def decode(self, B: int, prompts: Optional[torch.Tensor], n_steps: Optional[int] = None,
-               forced: Optional[torch.Tensor] = None, on_step=None) -> torch.Tensor:
+               forced: Optional[torch.Tensor] = None, on_step=None, timestamps: bool = True) -> torch.Tensor:
         """Greedy decode of B rows against the encoder state left by encode().
 
         prompts: int32 [B, 3] = [<|startoftranscript|>, language, task]; a language of -1 asks for
                  language detection at position 0 (detect_language, $TF/...generation_whisper.py:1610-1673).
         forced:  optional int32 [B, max_len] teacher-forcing table (-1 = free running).
+        timestamps: False = generate(return_timestamps=False): <|notimestamps|> is appended to the prompt and only
+                 the two suppress lists are applied (no WhisperTimeStampLogitsProcessor).
         Returns the int32 token matrix [B, max_len] on the device (prompt included)."""
         dev = self.device
         max_len = self.max_len
@@ -407,6 +410,10 @@ class WhisperEngine:
                 else:
                     frc[b, 1] = int(pr[b, 1])
                 frc[b, 2] = int(pr[b, 2])
+                if not timestamps:
+                    st0[b, 7] |= 2
+                    frc[b, 3] = self.gen.no_timestamps_token_id
+            self.grammar.begin_index = 3 if timestamps else 4
             self.tokens[:B].copy_(tok0.to(dev, non_blocking=False))
             self.forced[:B].copy_(frc.to(dev))
             self.state[:B].copy_(st0.to(dev))
@@ -432,17 +439,17 @@ class WhisperEngine:
 
     # ------------------------------------------------------------------------------------ generate
     def generate_from_pcm(self, clips: Sequence[np.ndarray], task: str = "transcribe",
-                          language: Optional[str] = None) -> List[List[int]]:
+                          language: Optional[str] = None, return_timestamps: bool = True) -> List[List[int]]:
         """PCM windows (<= 30 s each) -> generated token ids per window (segments concatenated), the
         output contract of ``WhisperGenerationMixin.generate(..., return_timestamps=True)`` minus padding."""
         if self.stream is not None:
             with torch.cuda.stream(self.stream):
                 B = self.load_pcm(clips)
                 self.features(B)
-                return self.generate(B, task=task, language=language)
+                return self.generate(B, task=task, language=language, return_timestamps=return_timestamps)
         B = self.load_pcm(clips)
         self.features(B)
-        return self.generate(B, task=task, language=language)
+        return self.generate(B, task=task, language=language, return_timestamps=return_timestamps)
 
     def _strip(self, row: List[int]) -> List[int]:
         """generate_with_fallback's pad / eos stripping ($TF/...generation_whisper.py:1063-1086)."""
@@ -459,8 +466,9 @@ class WhisperEngine:
         return s
 
     def generate(self, B: int, task: str = "transcribe", language: Optional[str] = None,
-                 trace: Optional[dict] = None) -> List[List[int]]:
-        """Short-form seek loop over the features in self.mel_t[:B] (greedy, timestamps on)."""
+                 trace: Optional[dict] = None, return_timestamps: bool = True) -> List[List[int]]:
+        """Short-form seek loop over the features in self.mel_t[:B] (greedy; timestamp grammar on unless
+        ``return_timestamps`` is False, in which case <|notimestamps|> joins the prompt)."""
         gen = self.gen
         if task not in gen.task_to_id:
             raise ValueError(f"The `{task}` task is not supported. The task should be one of {list(gen.task_to_id)}")
@@ -471,7 +479,7 @@ class WhisperEngine:
                 raise ValueError(f"Unsupported language: {language}")
             lang_id = gen.lang_to_id[key]
         ts_begin = gen.timestamp_begin
-        P = 3
+        P = 3 if return_timestamps else 4
         seek = [0] * B
         max_frames = [N_FRAMES] * B
         langs = [lang_id] * B
@@ -496,7 +504,7 @@ class WhisperEngine:
                 self.encode(n, mel)
                 prompts = torch.tensor([[gen.decoder_start_token_id, langs[b], gen.task_to_id[task]] for b in rows],
                                        dtype=torch.int32)
-                toks = self.decode(n, prompts).cpu().tolist()
+                toks = self.decode(n, prompts, timestamps=bool(return_timestamps)).cpu().tolist()
                 self.stats["d2h_bytes"] += n * self.max_len * 4
                 if trace is not None:
                     trace.setdefault("iterations", []).append({"rows": list(rows), "seek": [seek[b] for b in rows],

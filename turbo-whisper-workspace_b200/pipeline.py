@@ -64,7 +64,7 @@ def gpu_resample(x: np.ndarray, in_sr: int, out_sr: int, device) -> np.ndarray:
     rs = _RESAMPLERS.get(key)
     if rs is None:
         rs = _RESAMPLERS[key] = ops.Resampler(in_sr, out_sr, device)
-    t = torch.from_numpy(np.ascontiguousarray(x if x.dtype == np.int16 else x.astype(np.float32))).to(rs.device)
+    t = torch.from_numpy(np.array(x if x.dtype == np.int16 else x.astype(np.float32), order="C", copy=True)).to(rs.device)
     return rs(t).cpu().numpy()
 
 
@@ -215,11 +215,6 @@ class B200WhisperPipeline:
             raise NotImplementedError("beam search is not implemented by the B200 engine (greedy only)")
         if return_timestamps == "word":
             raise NotImplementedError('return_timestamps="word" is not implemented by the B200 engine')
-        if not return_timestamps:
-            # HF would decode with <|notimestamps|> and without the timestamp grammar; the reference always passes
-            # return_timestamps=True (ref:vocalis/core/audio_pipeline.py:357), which is the mode this engine implements
-            raise NotImplementedError("return_timestamps=False/None is not implemented by the B200 engine; "
-                                      "pass return_timestamps=True as the reference does")
         if return_timestamps == "char":
             raise ValueError("Whisper cannot return `char` timestamps, only word level or segment level timestamps. "
                              "Use `return_timestamps='word'` or `return_timestamps=True` respectively.")
@@ -248,7 +243,12 @@ class B200WhisperPipeline:
 
         # the feature extractor truncates every window to its first 30 s (truncation=True, max_length=480000)
         clips = [audio[s:e][:N_SAMPLES] for (s, e, _, _) in windows]
-        token_rows = self.scheduler.run(clips, task=task, language=language)
+        # return_timestamps falsy (the HF default): generate runs with <|notimestamps|> in the prompt and without the
+        # timestamp grammar, and the windows are merged on their overlapping text only
+        if return_timestamps:
+            token_rows = self.scheduler.run(clips, task=task, language=language)
+        else:
+            token_rows = self.scheduler.run(clips, task=task, language=language, return_timestamps=False)
         self.last_stats = dict(self.scheduler.last_stats, windows=len(windows), audio_seconds=audio.shape[0] / sr)
 
         # HF batches `batch_size` consecutive windows per generate call and right-pads each batch to its

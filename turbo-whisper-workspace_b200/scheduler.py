@@ -34,11 +34,13 @@ def partition(n_items: int, n_workers: int) -> List[Tuple[int, int]]:
     return out
 
 
-def run_in_microbatches(engine, clips: Sequence[np.ndarray], task: str, language: Optional[str]) -> List[List[int]]:
+def run_in_microbatches(engine, clips: Sequence[np.ndarray], task: str, language: Optional[str],
+                        return_timestamps: bool = True) -> List[List[int]]:
     rows: List[List[int]] = []
     mb = engine.max_batch
     for i in range(0, len(clips), mb):
-        rows.extend(engine.generate_from_pcm(clips[i:i + mb], task=task, language=language))
+        rows.extend(engine.generate_from_pcm(clips[i:i + mb], task=task, language=language,
+                                             return_timestamps=return_timestamps))
     return rows
 
 
@@ -71,8 +73,8 @@ class WindowScheduler:
     def flat_engines(self) -> List[Any]:
         return [e for ctxs in self.engines for e in ctxs]
 
-    def run(self, clips: Sequence[np.ndarray], task: str = "transcribe", language: Optional[str] = None
-            ) -> List[List[int]]:
+    def run(self, clips: Sequence[np.ndarray], task: str = "transcribe", language: Optional[str] = None,
+            return_timestamps: bool = True) -> List[List[int]]:
         t0 = time.perf_counter()
         n = len(clips)
         ranges = partition(n, len(self.devices))
@@ -92,7 +94,8 @@ class WindowScheduler:
                             if not queue or errors:
                                 return
                             a, b = queue.pop(0)
-                        rows = engine.generate_from_pcm(clips[a:b], task=task, language=language)
+                        rows = engine.generate_from_pcm(clips[a:b], task=task, language=language,
+                                                        return_timestamps=return_timestamps)
                         results[a:b] = rows
                 except BaseException as ex:  # surfaced on the calling thread
                     with lock:
@@ -128,10 +131,10 @@ class DistributedWindowScheduler:
     def local_range(self, n: int) -> Tuple[int, int]:
         return partition(n, self.world_size)[self.rank]
 
-    def run_local(self, clips: Sequence[np.ndarray], task: str = "transcribe", language: Optional[str] = None
-                  ) -> List[List[int]]:
+    def run_local(self, clips: Sequence[np.ndarray], task: str = "transcribe", language: Optional[str] = None,
+                  return_timestamps: bool = True) -> List[List[int]]:
         s, e = self.local_range(len(clips))
-        return run_in_microbatches(self.engine, clips[s:e], task, language) if e > s else []
+        return run_in_microbatches(self.engine, clips[s:e], task, language, return_timestamps) if e > s else []
 
     def gather(self, local_rows: List[List[int]]) -> List[List[int]]:
         if self.world_size == 1:
@@ -144,6 +147,6 @@ class DistributedWindowScheduler:
             rows.extend(b)
         return rows
 
-    def run(self, clips: Sequence[np.ndarray], task: str = "transcribe", language: Optional[str] = None
-            ) -> List[List[int]]:
-        return self.gather(self.run_local(clips, task, language))
+    def run(self, clips: Sequence[np.ndarray], task: str = "transcribe", language: Optional[str] = None,
+            return_timestamps: bool = True) -> List[List[int]]:
+        return self.gather(self.run_local(clips, task, language, return_timestamps))
