@@ -6,9 +6,11 @@
 // which is exact for a power of two).
 //
 // Input is the fused QKV projection output [B*T, 3*D] bf16 (q | k | v, head h at columns 64h..).
-// One CTA = one (batch, head) and TWO 128-query tiles (A, B).  576 threads: warp 0 TMA producer, warp 1 MMA
-// issuer (whole warp converged, one elected lane issues from uniform registers), warps 2-9 / 10-17 softmax of
-// tile A / B with TWO threads per query row (64 keys each).
+// One CTA = one (batch, head) and NT 128-query tiles (template parameter; default NT = 1: 320 threads, 256 TMEM
+// columns, TWO independent CTAs per SM that overlap each other's prologue / epilogue; NT = 2: 576 threads, all 512
+// columns, K/V tiles shared by both query tiles, one CTA per SM).  Warp 0 TMA producer, warp 1 MMA issuer (whole
+// warp converged, one elected lane issues from uniform registers), 8 softmax warps per tile with TWO threads per
+// query row (64 keys each).
 //   S  = Q K_j^T      tcgen05.mma 128x128x64 (SS)  -> TMEM S_g (128 fp32 columns)
 //   P  = exp2(S - m)  softmax threads: S_g -> registers -> bf16 pairs -> TMEM P_g (64 columns)
 //   O += P V_j        tcgen05.mma 128x64x128 (TS: A = P_g from tensor memory, B = V_j MN-major straight from its
@@ -23,9 +25,10 @@
 //   * optionally (ATTN_POLY_EVERY) a share of the exponentials runs as a degree-3 polynomial on the FMA pipe;
 //   * scale/shift FMA and row-sum ADD are packed f32x2; row sums stay in registers; the softmax reference
 //     point only moves when the running maximum grows by more than 2^8 (lazy rescale of O in TMEM).
-// K/V tiles are shared by both query tiles; ~100 KB smem and all 512 TMEM columns (S_A S_B | P_A P_B | O_A O_B).
+// TMEM per tile: S (128 fp32 columns) | P (64) | O (64); 80 KB smem per CTA at NT = 1.
 // Measured history (B=24, T=1500, H=20, per layer): 0.61 ms with P aliased on S and one thread per row,
-// 0.50-0.52 ms now, 0.47 ms with the polynomial share (torch SDPA 0.35 ms); tools/probes/ holds the MUFU / instruction-mix probes behind the numbers.
+// 0.50-0.52 ms with two threads per row (NT = 2), 0.46-0.49 ms with NT = 1 / two CTAs per SM (torch SDPA 0.35 ms); tools/probes/ holds the MUFU / instruction-mix probes behind the numbers.
+#include <cstdlib>
 #include "common.cuh"
 #include "twb200_internal.h"
 
@@ -35,16 +38,16 @@ namespace attn {
 constexpr int BQ = 128;   // query rows per tile; a CTA owns two tiles (A, B) that ping-pong
 constexpr int BKV = 128;  // keys per iteration
 constexpr int DH = 64;
-constexpr int NUM_THREADS = 576;           // warp 0 TMA, warp 1 MMA, warps 2-9 softmax A, warps 10-17 softmax B
 constexpr int GROUP_THREADS = 256;         // softmax threads per query tile: two per row (64 keys each)
 constexpr int TILE_BYTES = 128 * DH * 2;   // 16 KB: Q, K, V tiles and each half of P
-constexpr int TMEM_COLS = 512;
-constexpr int S_COL = 0;                   // S_A [0,128)   S_B [128,256)   fp32 scores
-constexpr int P_COL = 256;                 // P_A [256,320) P_B [320,384)   bf16 probabilities, two keys per column
-constexpr int O_COL = 384;                 // O_A [384,448) O_B [448,512)   fp32 output accumulators
-// smem tiles: Q_A Q_B | K0 K1 | V0 V1.  P never touches shared memory: tcgen05.mma reads it from tensor memory.
+// A CTA owns NT query tiles (template parameter): NT = 2 -> 576 threads, all 512 TMEM columns, K/V tiles shared by both
+// query tiles, one CTA per SM; NT = 1 -> 320 threads, 256 TMEM columns, two independent CTAs per SM (each overlaps the
+// other's prologue / epilogue).  TMEM map: S_g at g*128 (fp32 scores) | P_g at NT*128 + g*64 (bf16 probabilities, two
+// keys per column) | O_g at NT*192 + g*64 (fp32 output accumulators).  smem tiles: Q_0..Q_{NT-1} | K0 K1 | V0 V1.
+// P never touches shared memory: tcgen05.mma reads it from tensor memory.
 constexpr int XCH_BYTES = 2 * 2 * 2 * 128 * 4;   // row-max / row-sum exchange between the two threads of a row: [parity][tile][half][row]
-constexpr int SMEM_BYTES = 6 * TILE_BYTES + XCH_BYTES + 1024 + 256;
+constexpr int smem_bytes(int nt) { return (nt + 4) * TILE_BYTES + XCH_BYTES + 1024 + 256; }
+constexpr int num_threads(int nt) { return 64 + nt * GROUP_THREADS; }   // warp 0 TMA, warp 1 MMA, 8 softmax warps per tile
 constexpr float LOG2E = 1.4426950408889634f;
 // One pair of exponentials in POLY_EVERY takes the FMA-pipe polynomial path (1000 = none).  Measured on one box:
 // none 0.526 ms, every 4th 0.476 ms, every 3rd 0.470 ms, every 2nd 0.484 ms per layer.  It is OFF by default: the
@@ -123,15 +126,18 @@ struct Params {
     long long* dbg;   // optional clock64 trace of CTA (0,0,0): [0..63] MMA thread, [64..] softmax A row 0
 };
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int NT>
+__global__ void __launch_bounds__(num_threads(NT), NT == 1 ? 2 : 1)
 attention_enc_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;                       // 2 tiles
-    uint8_t* sK = smem + 2 * TILE_BYTES;      // 2 stages
-    uint8_t* sV = smem + 4 * TILE_BYTES;      // 2 stages
-    float* xch = reinterpret_cast<float*>(smem + 6 * TILE_BYTES);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * TILE_BYTES + XCH_BYTES);
+    constexpr int TMEM_COLS = NT * 256;
+    constexpr int S_COL = 0, P_COL = NT * 128, O_COL = NT * 192;
+    uint8_t* sQ = smem;                              // NT tiles
+    uint8_t* sK = smem + NT * TILE_BYTES;            // 2 stages
+    uint8_t* sV = smem + (NT + 2) * TILE_BYTES;      // 2 stages
+    float* xch = reinterpret_cast<float*>(smem + (NT + 4) * TILE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (NT + 4) * TILE_BYTES + XCH_BYTES);
     uint64_t* q_full = bars + 0;
     uint64_t* k_full = bars + 1;   // [2]
     uint64_t* k_empty = bars + 3;  // [2]
@@ -144,7 +150,7 @@ attention_enc_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 17);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q0 = blockIdx.x * (2 * BQ), h = blockIdx.y, b = blockIdx.z;
+    const int q0 = blockIdx.x * (NT * BQ), h = blockIdx.y, b = blockIdx.z;
     const int nkv = (p.T + BKV - 1) / BKV;
     const bool trace = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
     int ti = 0;
@@ -176,9 +182,9 @@ attention_enc_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
 
     if (warp == 0) {
         if (lane == 0) {
-            mbar_arrive_expect_tx(q_full, 2 * TILE_BYTES);
-            tma_load_3d(&tmQKV, q_full, sQ, h * DH, q0, b);
-            tma_load_3d(&tmQKV, q_full, sQ + TILE_BYTES, h * DH, q0 + BQ, b);
+            mbar_arrive_expect_tx(q_full, NT * TILE_BYTES);
+#pragma unroll
+            for (int g = 0; g < NT; ++g) tma_load_3d(&tmQKV, q_full, sQ + g * TILE_BYTES, h * DH, q0 + g * BQ, b);
             for (int j = 0; j < nkv; ++j) {
                 const int s = j & 1;
                 const uint32_t ph = (j >> 1) & 1;
@@ -233,42 +239,46 @@ attention_enc_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
         mbar_wait(&k_full[0], 0);
         if (lane == 0) TRACE(0);
         tcgen05_fence_after();
-        issue_s(0, 0);
-        issue_s(1, 0);
-        release(&k_empty[0]);
-        // Event loop over the four things that can become issuable, polled without blocking so that neither
-        // tile ever delays the other:  S_g(j) once the group has copied S_g(j-1) to registers (s_free) and K_j
-        // has landed;  PV_g(j) once P_g(j) is stored (p_full) and V_j has landed.  A K/V stage is handed back
-        // to the producer by whichever tile issues the second MMA that reads it.
-        int js0 = 1, js1 = 1;   // next S index per tile
-        int jp0 = 0, jp1 = 0;   // next PV index per tile
-        while (jp0 < nkv || jp1 < nkv) {
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {
-                int& js = g ? js1 : js0;
-                int& jp = g ? jp1 : jp0;
-                const int js_other = g ? js0 : js1, jp_other = g ? jp0 : jp1;
+        for (int g = 0; g < NT; ++g) issue_s(g, 0);
+        release(&k_empty[0]);
+        // Event loop over the things that can become issuable, polled without blocking so that no tile ever delays
+        // another:  S_g(j) once the group has copied S_g(j-1) to registers (s_free) and K_j has landed;  PV_g(j)
+        // once P_g(j) is stored (p_full) and V_j has landed.  A K/V stage is handed back to the producer by
+        // whichever tile issues the last MMA that reads it.
+        int js[NT], jp[NT];   // next S / PV index per tile (constant indices after unrolling: registers)
+#pragma unroll
+        for (int g = 0; g < NT; ++g) { js[g] = 1; jp[g] = 0; }
+        auto pending = [&]() { bool any = false;
+#pragma unroll
+            for (int g = 0; g < NT; ++g) any = any || jp[g] < nkv;
+            return any; };
+        while (pending()) {
+#pragma unroll
+            for (int g = 0; g < NT; ++g) {
                 // (K_j / V_j are part of the non-blocking condition: a tile that runs two kv tiles ahead of the other
                 // needs a stage the slower tile has not released yet, and only this warp can make it release it)
-                if (js < nkv && __any_sync(0xffffffffu, mbar_test_wait(&s_free[g], (js - 1) & 1) &&
-                                                            mbar_test_wait(&k_full[js & 1], (js >> 1) & 1))) {
-                    const int j = js;
+                if (js[g] < nkv && __any_sync(0xffffffffu, mbar_test_wait(&s_free[g], (js[g] - 1) & 1) &&
+                                                               mbar_test_wait(&k_full[js[g] & 1], (js[g] >> 1) & 1))) {
+                    const int j = js[g];
                     tcgen05_fence_after();
-                    if (g == 0 && lane == 0) TRACE(0);
                     issue_s(g, j);
-                    if (g == 0 && lane == 0) TRACE(0);
-                    if (js_other > j) release(&k_empty[j & 1]);   // second reader of K_j
-                    js = j + 1;
+                    bool last_reader = true;
+#pragma unroll
+                    for (int o = 0; o < NT; ++o) if (o != g) last_reader = last_reader && js[o] > j;
+                    if (last_reader) release(&k_empty[j & 1]);
+                    js[g] = j + 1;
                 }
-                if (jp < nkv && __any_sync(0xffffffffu, mbar_test_wait(&p_full[g], jp & 1) &&
-                                                            mbar_test_wait(&v_full[jp & 1], (jp >> 1) & 1))) {
-                    const int j = jp;
+                if (jp[g] < nkv && __any_sync(0xffffffffu, mbar_test_wait(&p_full[g], jp[g] & 1) &&
+                                                               mbar_test_wait(&v_full[jp[g] & 1], (jp[g] >> 1) & 1))) {
+                    const int j = jp[g];
                     tcgen05_fence_after();
-                    if (g == 0 && lane == 0) TRACE(0);
                     issue_pv(g, j);
-                    if (g == 0 && lane == 0) TRACE(0);
-                    if (jp_other > j) release(&v_empty[j & 1]);   // second reader of V_j
-                    jp = j + 1;
+                    bool last_reader = true;
+#pragma unroll
+                    for (int o = 0; o < NT; ++o) if (o != g) last_reader = last_reader && jp[o] > j;
+                    if (last_reader) release(&v_empty[j & 1]);
+                    jp[g] = j + 1;
                 }
             }
             // (backing off with nanosleep when nothing fired was measured slower at every setting: the latency of
@@ -444,6 +454,9 @@ attention_enc_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
 }  // namespace tw
 
 static long long* g_attn_dbg = nullptr;
+// query tiles per CTA: 1 (two independent CTAs per SM: default, 16 % faster on the same box) or 2 (one CTA per SM, K/V shared);
+// TWB200_ATTN_TILES=2 selects the latter for comparison
+static int g_attn_tiles = [] { const char* e = getenv("TWB200_ATTN_TILES"); return (e && e[0] == '2') ? 2 : 1; }();
 extern "C" int tw_attention_enc_set_trace(void* dev_buf_int64_x192) { g_attn_dbg = (long long*)dev_buf_int64_x192; return 0; }
 
 extern "C" int tw_attention_enc(const void* qkv_bf16, void* out_bf16, int32_t batch, int32_t seq,
@@ -470,11 +483,17 @@ extern "C" int tw_attention_enc(const void* qkv_bf16, void* out_bf16, int32_t ba
     static bool attr_set[64] = {};
     const int dev = current_device();
     if (!attr_set[dev]) {
-        TW_CUDA_CHECK(cudaFuncSetAttribute(attention_enc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        TW_CUDA_CHECK(cudaFuncSetAttribute(attention_enc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(1)));
+        TW_CUDA_CHECK(cudaFuncSetAttribute(attention_enc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(2)));
         attr_set[dev] = true;
     }
-    dim3 grid((seq + 2 * BQ - 1) / (2 * BQ), heads, batch);
-    attention_enc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tm, p);
+    if (g_attn_tiles == 1) {
+        dim3 grid((seq + BQ - 1) / BQ, heads, batch);
+        attention_enc_kernel<1><<<grid, num_threads(1), smem_bytes(1), (cudaStream_t)stream>>>(tm, p);
+    } else {
+        dim3 grid((seq + 2 * BQ - 1) / (2 * BQ), heads, batch);
+        attention_enc_kernel<2><<<grid, num_threads(2), smem_bytes(2), (cudaStream_t)stream>>>(tm, p);
+    }
     TW_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
