@@ -90,6 +90,51 @@ TW_DEVINL float gelu_erf_fast(float x) {
     const float erf_v = copysignf(erf_abs, x);
     return 0.5f * x * (1.0f + erf_v);
 }
+// The same function on two values with packed fp32x2 arithmetic (fma/mul/add.f32x2: one issue slot per pair).  Every
+// operation is the IEEE operation of the scalar version in the same order, so the results are bit-identical; the
+// four MUFU ops per pair (2 rcp, 2 ex2) stay scalar.  The GELU GEMM epilogue is issue-bound next to the MMA.
+TW_DEVINL uint64_t f32x2_pack(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+TW_DEVINL void f32x2_unpack(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+TW_DEVINL uint64_t f32x2_fma(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+TW_DEVINL uint64_t f32x2_mul(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+TW_DEVINL uint64_t f32x2_add(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+#define TW_F2(c) f32x2_pack((c), (c))
+TW_DEVINL void gelu_erf_fast_x2(float& x0, float& x1) {
+    const uint64_t X = f32x2_pack(x0, x1);
+    const uint64_t Z = f32x2_mul(f32x2_pack(fabsf(x0), fabsf(x1)), TW_F2(0.70710678118654752f));
+    float d0, d1;
+    f32x2_unpack(f32x2_fma(TW_F2(0.3275911f), Z, TW_F2(1.0f)), d0, d1);
+    const uint64_t T = f32x2_pack(__fdividef(1.0f, d0), __fdividef(1.0f, d1));
+    uint64_t P = f32x2_fma(TW_F2(1.061405429f), T, TW_F2(-1.453152027f));
+    P = f32x2_fma(P, T, TW_F2(1.421413741f));
+    P = f32x2_fma(P, T, TW_F2(-0.284496736f));
+    P = f32x2_fma(P, T, TW_F2(0.254829592f));
+    P = f32x2_mul(P, T);
+    float zz0, zz1;
+    f32x2_unpack(f32x2_mul(Z, Z), zz0, zz1);
+    const uint64_t E = f32x2_pack(__expf(-zz0), __expf(-zz1));
+    // p * e - 1 = -(1 - p * e): the sign is replaced by x's below, so the negation costs nothing
+    float m0, m1;
+    f32x2_unpack(f32x2_fma(P, E, TW_F2(-1.0f)), m0, m1);
+    const uint64_t ERF = f32x2_pack(copysignf(m0, x0), copysignf(m1, x1));
+    f32x2_unpack(f32x2_mul(f32x2_mul(TW_F2(0.5f), X), f32x2_add(TW_F2(1.0f), ERF)), x0, x1);
+}
 // reference-accuracy variant (decoder path, where cost is irrelevant)
 TW_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 

@@ -217,8 +217,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         float4 f = val[i];
                         f.x += bias4.x; f.y += bias4.y; f.z += bias4.z; f.w += bias4.w;
                         if (ACT == 1) {
-                            f.x = gelu_erf_fast(f.x); f.y = gelu_erf_fast(f.y);
-                            f.z = gelu_erf_fast(f.z); f.w = gelu_erf_fast(f.w);
+                            gelu_erf_fast_x2(f.x, f.y);
+                            gelu_erf_fast_x2(f.z, f.w);
                         }
                         if (HAS_RESID) { f.x += res[i].x; f.y += res[i].y; f.z += res[i].z; f.w += res[i].w; }
                         if (4 * i < nrows) {
