@@ -133,7 +133,9 @@ int tw_shift_frames(const void* src_bf16, void* dst_bf16, const int32_t* src_row
  * fp32-logits -> processors -> argmax -> pad-if-finished step ($TF/generation/utils.py:2762-2797).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct tw_skinny_args {
-    const void* w;      /* bf16 [n, k] */
+    const void* w;      /* bf16, n rounded up to 16 rows x k, FRAGMENT-MAJOR: [n/16][k/32][2][8][4][8] with element
+                         * W[16*slab + 8*half + g][32*kstep + 8*tg + e] (zero rows beyond n) — each warp load of the
+                         * mma.m16n8k16 A fragments is then 512 contiguous bytes; engine.pack_skinny_weight builds it */
     const void* x;      /* bf16 [batch, ldx] */
     int32_t ldx;
     const float* bias;  /* fp32 [n] or NULL */

@@ -93,7 +93,16 @@ def load() -> C.CDLL:
     return _lib
 
 
+_SYNC_CHECK = bool(os.environ.get("TWB200_SYNC_CHECK"))   # debug: synchronise after every call so a device fault names its kernel
+
+
 def check(status: int, what: str = "") -> None:
     if status != 0:
         msg = load().tw_last_error().decode("utf-8", "replace")
         raise TwError(f"{what or 'libtwb200'} failed (status {status}): {msg}")
+    if _SYNC_CHECK:
+        import torch
+        try:
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            raise TwError(f"device fault detected after {what or 'a libtwb200 call'}: {e}") from e

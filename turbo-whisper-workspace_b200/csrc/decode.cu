@@ -143,9 +143,23 @@ struct SkinnyParams {
     int* part_idx;           // [B][n_ctas][2]
 };
 
+// Decoder weights are stored FRAGMENT-MAJOR (packed once at load time, engine.pack_skinny_weight): for every slab of
+// 16 output rows and every k-step of 32, the 32 lanes' A-fragments of mma.m16n8k16 are contiguous —
+//   [slab][k-step][half: rows g | rows g+8][lane = g*4 + tg][8 bf16 = W[16*slab + g + 8*half][32*kstep + 8*tg ..]]
+// so a warp's 16-byte-per-lane load covers 512 contiguous bytes (four full 128-byte lines) instead of sixteen 64-byte
+// pieces 2*K bytes apart.  Rows beyond N are zero padding.
+constexpr int FRAG_STEP = 512;   // elements per (slab, k-step) block
+constexpr int FRAG_HALF = 256;   // offset of the rows g+8 half
+TW_DEVINL const __nv_bfloat16* frag_ptr(const __nv_bfloat16* W, int K, int slab, int kstep, int lane) {
+    return W + ((size_t)slab * (K >> 5) + kstep) * FRAG_STEP + lane * 8;
+}
+// `volatile`: a plain asm is a pure function to the compiler, which may then execute it speculatively ABOVE the
+// condition that guards it (next-slab / next-round prefetches) — an out-of-range address that way is a real fault
+// (seen as a layout-dependent illegal access when the weight buffer started a fresh memory segment).  The mma asm
+// stays non-volatile, so only the loads keep their program order, which is the order they are written in anyway.
 TW_DEVINL uint4 ldg_stream(const void* p) {
     uint4 r;
-    asm("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                  : "l"(p));
     return r;
@@ -221,8 +235,9 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 2 : 1) skinny_gemm_
 
     const int n0 = blockIdx.x * 16;
     const int ra = min(n0 + g, p.N - 1), rb = min(n0 + g + 8, p.N - 1);
-    const __nv_bfloat16* wa = p.W + (size_t)ra * p.K + k_begin + tg * 8;
-    const __nv_bfloat16* wb = p.W + (size_t)rb * p.K + k_begin + tg * 8;
+    // fragment-major weights (see frag_ptr): one 16-byte fragment per lane, 512 contiguous bytes per warp load
+    const __nv_bfloat16* wa = frag_ptr(p.W, p.K, blockIdx.x, k_begin >> 5, lane);
+    const __nv_bfloat16* wb = wa + FRAG_HALF;
     const __nv_bfloat16* xr[NB];
 #pragma unroll
     for (int j = 0; j < NB; ++j) xr[j] = p.X + (size_t)min(j * 8 + g, p.B - 1) * p.ldx + k_begin + tg * 8;
@@ -236,14 +251,14 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 2 : 1) skinny_gemm_
     uint4 alo[UN], ahi[UN];
 #pragma unroll
     for (int u = 0; u < UN; ++u)
-        if (u < steps) { alo[u] = ldg_stream(wa + u * 32); ahi[u] = ldg_stream(wb + u * 32); }
+        if (u < steps) { alo[u] = ldg_stream(wa + u * FRAG_STEP); ahi[u] = ldg_stream(wb + u * FRAG_STEP); }
     pdl_wait();
     for (int s0 = 0; s0 < steps; s0 += UN) {
         uint4 xb[UN][NB];
 #pragma unroll
         for (int u = 0; u < UN; ++u) {
             if (s0 + u < steps) {
-                if (s0 > 0) { alo[u] = ldg_stream(wa + (s0 + u) * 32); ahi[u] = ldg_stream(wb + (s0 + u) * 32); }
+                if (s0 > 0) { alo[u] = ldg_stream(wa + (s0 + u) * FRAG_STEP); ahi[u] = ldg_stream(wb + (s0 + u) * FRAG_STEP); }
 #pragma unroll
                 for (int j = 0; j < NB; ++j) xb[u][j] = __ldg(reinterpret_cast<const uint4*>(xr[j] + (s0 + u) * 32));
             }
@@ -320,12 +335,19 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 2 : 1) skinny_gemm_
 // 16-byte loads is in flight while the current round's mma run).  The mma accumulator layout already has
 // every (vocab row, batch row) logit in a known lane, so masks and reductions are warp shuffles.
 // ------------------------------------------------------------------------------------------------
+#ifndef LMH_WARPS_DEF
+#define LMH_WARPS_DEF 8
+#endif
+constexpr int LMH_WARPS = LMH_WARPS_DEF;   // warps per CTA of the persistent LM-head grid (one CTA per SM)
+
 template <int NB>
-__global__ void __launch_bounds__(256, 1) lmhead_kernel(const SkinnyParams p) {
+__global__ void __launch_bounds__(LMH_WARPS * 32, 1) lmhead_kernel(const SkinnyParams p) {
+    // grammar state of the batch rows: shared memory, not 6 register copies per thread (the registers go to fragments)
+    __shared__ RowState s_st[MAXB];
     constexpr int UN = 4;  // k-steps (of 32) per round
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, tg = lane & 3;
-    const int gwarp = blockIdx.x * 8 + warp, nwarps = gridDim.x * 8;
+    const int gwarp = blockIdx.x * LMH_WARPS + warp, nwarps = gridDim.x * LMH_WARPS;
     const int n_slabs = (p.N + 15) >> 4;
     const int rounds = p.K / (32 * UN);  // K % 128 == 0
 
@@ -333,26 +355,24 @@ __global__ void __launch_bounds__(256, 1) lmhead_kernel(const SkinnyParams p) {
     // two named fragment buffers (no dynamically indexed arrays: those would live in local memory)
     uint4 a0lo[UN], a0hi[UN], a1lo[UN], a1hi[UN];
     if (gwarp < n_slabs) {  // round 0 of this warp's first slab: independent of the previous kernel
-        const __nv_bfloat16* wa0 = p.W + (size_t)min(gwarp * 16 + g, p.N - 1) * p.K + tg * 8;
-        const __nv_bfloat16* wb0 = p.W + (size_t)min(gwarp * 16 + g + 8, p.N - 1) * p.K + tg * 8;
+        const __nv_bfloat16* wa0 = frag_ptr(p.W, p.K, gwarp, 0, lane);
+        const __nv_bfloat16* wb0 = wa0 + FRAG_HALF;
 #pragma unroll
-        for (int u = 0; u < UN; ++u) { a0lo[u] = ldg_stream(wa0 + u * 32); a0hi[u] = ldg_stream(wb0 + u * 32); }
+        for (int u = 0; u < UN; ++u) { a0lo[u] = ldg_stream(wa0 + u * FRAG_STEP); a0hi[u] = ldg_stream(wb0 + u * FRAG_STEP); }
     }
     pdl_wait();
+    for (int i = threadIdx.x; i < p.B; i += LMH_WARPS * 32) s_st[i] = p.st[i];
+    __syncthreads();
     // per-thread running partials for its 2*NB batch columns (j*8 + 2*tg + e)
     float bt[NB * 2], bs[NB * 2], sm[NB * 2];
     int it[NB * 2], is[NB * 2];
-    RowState st[NB * 2];
 #pragma unroll
     for (int c = 0; c < NB * 2; ++c) {
         bt[c] = -INFINITY; bs[c] = -INFINITY; sm[c] = 0.f; it[c] = 0x7fffffff; is[c] = 0x7fffffff;
-        const int bb = (c >> 1) * 8 + 2 * tg + (c & 1);
-        st[c] = p.st[min(bb, p.B - 1)];
     }
     // rows in language-detection or no-timestamp mode rank EVERY id in the "text" class, timestamp slabs included
     bool flat = false;
-#pragma unroll
-    for (int c = 0; c < NB * 2; ++c) flat = flat || (st[c].mode != 0);
+    for (int i = lane; i < p.B; i += 32) flat = flat || (s_st[i].mode != 0);
     const bool any_flat = __any_sync(0xffffffffu, flat);
     const __nv_bfloat16* xr[NB];
 #pragma unroll
@@ -364,15 +384,15 @@ __global__ void __launch_bounds__(256, 1) lmhead_kernel(const SkinnyParams p) {
     bool have_first = true;   // buffer 0 already holds round 0 of the current slab
     for (int slab = gwarp; slab < n_slabs; slab += nwarps) {
         const int n0 = slab * 16;
-        const __nv_bfloat16* wa = p.W + (size_t)min(n0 + g, p.N - 1) * p.K + tg * 8;
-        const __nv_bfloat16* wb = p.W + (size_t)min(n0 + g + 8, p.N - 1) * p.K + tg * 8;
+        const __nv_bfloat16* wa = frag_ptr(p.W, p.K, slab, 0, lane);
+        const __nv_bfloat16* wb = wa + FRAG_HALF;
         const int nslab = slab + nwarps;
         float acc[NB][4];
 #pragma unroll
         for (int j = 0; j < NB; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
         if (!have_first) {
 #pragma unroll
-            for (int u = 0; u < UN; ++u) { a0lo[u] = ldg_stream(wa + u * 32); a0hi[u] = ldg_stream(wb + u * 32); }
+            for (int u = 0; u < UN; ++u) { a0lo[u] = ldg_stream(wa + u * FRAG_STEP); a0hi[u] = ldg_stream(wb + u * FRAG_STEP); }
         }
         have_first = false;
         auto compute = [&](const uint4 (&lo)[UN], const uint4 (&hi)[UN], int r) {
@@ -390,21 +410,21 @@ __global__ void __launch_bounds__(256, 1) lmhead_kernel(const SkinnyParams p) {
         for (; r + 1 < rounds; r += 2) {
 #pragma unroll
             for (int u = 0; u < UN; ++u) {
-                a1lo[u] = ldg_stream(wa + ((r + 1) * UN + u) * 32);
-                a1hi[u] = ldg_stream(wb + ((r + 1) * UN + u) * 32);
+                a1lo[u] = ldg_stream(wa + ((r + 1) * UN + u) * FRAG_STEP);
+                a1hi[u] = ldg_stream(wb + ((r + 1) * UN + u) * FRAG_STEP);
             }
             compute(a0lo, a0hi, r);
             if (r + 2 < rounds) {
 #pragma unroll
                 for (int u = 0; u < UN; ++u) {
-                    a0lo[u] = ldg_stream(wa + ((r + 2) * UN + u) * 32);
-                    a0hi[u] = ldg_stream(wb + ((r + 2) * UN + u) * 32);
+                    a0lo[u] = ldg_stream(wa + ((r + 2) * UN + u) * FRAG_STEP);
+                    a0hi[u] = ldg_stream(wb + ((r + 2) * UN + u) * FRAG_STEP);
                 }
             } else if (nslab < n_slabs) {
-                const __nv_bfloat16* na = p.W + (size_t)min(nslab * 16 + g, p.N - 1) * p.K + tg * 8;
-                const __nv_bfloat16* nb = p.W + (size_t)min(nslab * 16 + g + 8, p.N - 1) * p.K + tg * 8;
+                const __nv_bfloat16* na = frag_ptr(p.W, p.K, nslab, 0, lane);
+                const __nv_bfloat16* nb = na + FRAG_HALF;
 #pragma unroll
-                for (int u = 0; u < UN; ++u) { a0lo[u] = ldg_stream(na + u * 32); a0hi[u] = ldg_stream(nb + u * 32); }
+                for (int u = 0; u < UN; ++u) { a0lo[u] = ldg_stream(na + u * FRAG_STEP); a0hi[u] = ldg_stream(nb + u * FRAG_STEP); }
                 have_first = true;
             }
             compute(a1lo, a1hi, r + 1);
@@ -421,7 +441,7 @@ __global__ void __launch_bounds__(256, 1) lmhead_kernel(const SkinnyParams p) {
         for (int c = 0; c < NB * 2; ++c) {
             const int j = c >> 1, e = c & 1;
             const int bb = j * 8 + 2 * tg + e;
-            const RowState& rs = st[c];
+            const RowState& rs = s_st[min(bb, p.B - 1)];
             float vt = -INFINITY, vs = -INFINITY;
             int jt = 0x7fffffff, js = 0x7fffffff;
             bool ts_ok[2];
@@ -920,7 +940,7 @@ static GrammarConst to_gc(const tw_grammar* g) {
 static int lmhead_grid() { int n = num_sms(); return n > 0 ? n : 148; }
 extern "C" int32_t tw_dec_lmhead_parts(int32_t vocab) {
     (void)vocab;
-    return lmhead_grid() * 8;
+    return lmhead_grid() * LMH_WARPS;
 }
 
 extern "C" int tw_dec_lmhead(const tw_skinny_args* a, const tw_grammar* g, const void* row_state,
@@ -941,10 +961,10 @@ extern "C" int tw_dec_lmhead(const tw_skinny_args* a, const tw_grammar* g, const
     const int grid = lmhead_grid();
     cudaStream_t st = (cudaStream_t)stream;
     switch ((p.B + 7) / 8) {
-        case 1: TW_CUDA_CHECK(launch_pdl(lmhead_kernel<1>, dim3(grid), dim3(256), 0, st, p)); break;
-        case 2: TW_CUDA_CHECK(launch_pdl(lmhead_kernel<2>, dim3(grid), dim3(256), 0, st, p)); break;
-        case 3: TW_CUDA_CHECK(launch_pdl(lmhead_kernel<3>, dim3(grid), dim3(256), 0, st, p)); break;
-        case 4: TW_CUDA_CHECK(launch_pdl(lmhead_kernel<4>, dim3(grid), dim3(256), 0, st, p)); break;
+        case 1: TW_CUDA_CHECK(launch_pdl(lmhead_kernel<1>, dim3(grid), dim3(LMH_WARPS * 32), 0, st, p)); break;
+        case 2: TW_CUDA_CHECK(launch_pdl(lmhead_kernel<2>, dim3(grid), dim3(LMH_WARPS * 32), 0, st, p)); break;
+        case 3: TW_CUDA_CHECK(launch_pdl(lmhead_kernel<3>, dim3(grid), dim3(LMH_WARPS * 32), 0, st, p)); break;
+        case 4: TW_CUDA_CHECK(launch_pdl(lmhead_kernel<4>, dim3(grid), dim3(LMH_WARPS * 32), 0, st, p)); break;
         default: set_error("tw_dec_lmhead: batch %d > %d", p.B, MAXB); return 2;
     }
     TW_CUDA_CHECK(cudaGetLastError());

@@ -11,6 +11,8 @@ on the data path (tensor allocation, H2D / D2H copies and int bookkeeping only).
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 import threading
 from typing import Dict, List, Optional, Sequence
@@ -36,6 +38,20 @@ def _f32(t: torch.Tensor) -> torch.Tensor:
     return t.detach().to(torch.float32).contiguous()
 
 
+def pack_skinny_weight(w: torch.Tensor) -> torch.Tensor:
+    """[N, K] bf16 (nn.Linear layout) -> FRAGMENT-MAJOR layout of the decode GEMMs (csrc/decode.cu, frag_ptr):
+    ``[slab = N/16][k-step = K/32][half: rows g | rows g+8][g = 0..7][tg = 0..3][8]`` with
+    element = W[16*slab + 8*half + g][32*kstep + 8*tg + e]; N is zero-padded to a multiple of 16.  The result keeps
+    the 2-D shape [N_padded, K] (same bytes, different order) so that ``shape[0]`` / ``shape[1]`` still describe it."""
+    n, k = w.shape
+    if k % 32:
+        raise ValueError("decode GEMM weights need K % 32 == 0")
+    n_pad = (n + 15) // 16 * 16
+    if n_pad != n:
+        w = torch.cat([w, torch.zeros(n_pad - n, k, dtype=w.dtype, device=w.device)], 0)
+    return (w.view(n_pad // 16, 2, 8, k // 32, 4, 8).permute(0, 3, 1, 2, 4, 5).contiguous().view(n_pad, k))
+
+
 def pack_weights(sd: Dict[str, torch.Tensor], dims: WhisperDims, device) -> Dict[str, torch.Tensor]:
     """HF ``WhisperForConditionalGeneration.state_dict()`` -> packed device tensors.
 
@@ -47,6 +63,9 @@ def pack_weights(sd: Dict[str, torch.Tensor], dims: WhisperDims, device) -> Dict
     * all decoder layers' cross-attention k/v projections are stacked into one [L*2*D, D] matrix so
       the per-window cross K/V is one GEMM.
     * biases, LayerNorm parameters and positional embeddings stay fp32.
+    * the DECODER's linear weights (qkv, out, cross q / out, fc1, fc2) and a second copy of the tied embedding for
+      the LM head (``tok_emb_frag``) are stored fragment-major (:func:`pack_skinny_weight`): the decode GEMMs stream
+      every weight exactly once per step, and this makes each warp load 512 contiguous bytes.
     """
     D = dims.d_model
     scale = (D // dims.heads) ** -0.5
@@ -110,6 +129,10 @@ def pack_weights(sd: Dict[str, torch.Tensor], dims: WhisperDims, device) -> Dict
     put("ckv_w", _bf16(torch.cat(ckv_w, 0)))
     put("ckv_b", torch.cat(ckv_b, 0))
     ln(dd + "layer_norm", "dec_ln")
+    for i in range(dims.dec_layers):
+        for nm in ("qkv_w", "out_w", "cq_w", "cout_w", "fc1_w", "fc2_w"):
+            w[f"dec{i}.{nm}"] = pack_skinny_weight(w[f"dec{i}.{nm}"])
+    w["tok_emb_frag"] = pack_skinny_weight(w["tok_emb"])
     return w
 
 
@@ -220,9 +243,12 @@ class WhisperEngine:
         self.grammar = g
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
         self._ckv_batch = max_batch
-        self.use_graphs = True
+        self.use_graphs = not os.environ.get("TWB200_NO_GRAPHS")   # debug knob: eager stepping localises device faults
         self.finish_check_every = 16
         self.stats = {"enc_windows": 0, "dec_steps": 0, "launches": 0, "h2d_bytes": 0, "d2h_bytes": 0}
+        # weights were repacked and workspaces zeroed by kernels on the default stream; the engine's own (non-blocking)
+        # stream does not order against it
+        torch.cuda.synchronize(dev)
         self._pcm_host = torch.zeros(Be, N_SAMPLES, dtype=torch.float32).pin_memory()
         self._nv_host = torch.zeros(Be, dtype=torch.int32).pin_memory()
 
@@ -313,7 +339,8 @@ class WhisperEngine:
         wt = self.w[wname]
         a.w, a.x, a.ldx = wt.data_ptr(), x.data_ptr(), x.stride(0)
         a.bias = None if bias is None else self.w[bias].data_ptr()
-        a.batch, a.n, a.k = B, wt.shape[0], k
+        # fragment-major weights are padded to 16 rows: the true N is the bias length (the LM head has N = vocab)
+        a.batch, a.n, a.k = B, (self.dims.vocab if bias is None else self.w[bias].shape[0]), k
         if ln is not None:
             a.ln_gamma, a.ln_beta = self.w[ln + "_w"].data_ptr(), self.w[ln + "_b"].data_ptr()
             a.ln_out_bf16, a.ln_counter = self.dxn.data_ptr(), self.ln_cnt.data_ptr()
@@ -351,7 +378,7 @@ class WhisperEngine:
                   "fc1")
             check(lib.tw_dec_linear(C.byref(self._skinny(q + "fc2_w", self.dhid, q + "fc2_b", B, F, ln=nxt)), 2,
                                     p(self.dx), D, st), "fc2")
-        check(lib.tw_dec_lmhead(C.byref(self._skinny("tok_emb", self.dxn, None, B, D)), C.byref(self.grammar),
+        check(lib.tw_dec_lmhead(C.byref(self._skinny("tok_emb_frag", self.dxn, None, B, D)), C.byref(self.grammar),
                                 p(self.state), p(self.sup_bits), p(self.bsup_bits), p(self.part_val), p(self.part_idx),
                                 None if self.logits is None else p(self.logits), st), "tw_dec_lmhead")
         check(lib.tw_dec_finalize(p(self.part_val), p(self.part_idx), self.n_parts, p(self.tokens), self.max_len,
@@ -419,7 +446,7 @@ class WhisperEngine:
             self.state[:B].copy_(st0.to(dev))
             self.stats["h2d_bytes"] += 2 * B * max_len * 4 + B * ROWSTATE_INTS * 4
             steps = (max_len - 1) if n_steps is None else min(n_steps, max_len - 1)
-            _lib.load().tw_set_pdl(0 if self.use_graphs else 1)   # PDL only pays off for eager stepping
+            _lib.load().tw_set_pdl(0 if (self.use_graphs or os.environ.get("TWB200_NO_PDL")) else 1)   # PDL only pays off for eager stepping
             graph = self._graph_for(B) if self.use_graphs else None
             for s in range(steps):
                 if graph is not None:
