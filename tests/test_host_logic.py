@@ -60,7 +60,7 @@ class FakeEngine:
     def __init__(self, device, max_batch=4):
         self.device, self.max_batch, self.calls = device, max_batch, []
 
-    def generate_from_pcm(self, clips, task="transcribe", language=None):
+    def generate_from_pcm(self, clips, task="transcribe", language=None, return_timestamps=True):
         assert len(clips) <= self.max_batch
         self.calls.append(len(clips))
         return [[len(c) % 1000, int(round(float(c[0]) * 1000))] for c in clips]
