@@ -146,3 +146,26 @@ def test_resample_filter_bank_is_torchaudios(orig, new):
     nz = np.abs(got) > 1e-30
     assert float(np.abs(got[~nz]).sum()) < 1e-25          # what the span skips is numerically nothing
     assert int(nz.sum(axis=1).max()) <= 2 * w + 2          # ~2*width useful taps per phase, not 2*width + orig
+
+
+def test_fragment_major_weight_packing_matches_kernel_addressing():
+    """engine.pack_skinny_weight vs the address formula of csrc/decode.cu (frag_ptr): element
+    W[16*slab + 8*half + g][32*kstep + 8*tg + e] sits at ((slab*K/32 + kstep)*512 + half*256 + (g*4 + tg)*8 + e);
+    rows beyond N are zero padding."""
+    import random
+    import torch
+    from turbo_whisper_workspace_b200.engine import pack_skinny_weight
+    N, K = 906, 256                       # N not a multiple of 16 (like the 51866-row LM head)
+    W = torch.arange(N * K, dtype=torch.float32).view(N, K)
+    P = pack_skinny_weight(W)
+    assert tuple(P.shape) == (912, K)
+    flat = P.reshape(-1)
+    rng = random.Random(0)
+    for _ in range(3000):
+        slab, ks, half, g, tg, e = (rng.randrange((N + 15) // 16), rng.randrange(K // 32), rng.randrange(2),
+                                    rng.randrange(8), rng.randrange(4), rng.randrange(8))
+        off = (slab * (K // 32) + ks) * 512 + half * 256 + (g * 4 + tg) * 8 + e
+        row, col = 16 * slab + 8 * half + g, 32 * ks + 8 * tg + e
+        assert flat[off].item() == (W[row, col].item() if row < N else 0.0)
+    with pytest.raises(ValueError):
+        pack_skinny_weight(torch.zeros(16, 40))
