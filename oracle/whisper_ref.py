@@ -261,6 +261,84 @@ class WhisperRef:
             logits = self.decode(nxt[:, None], enc_out, cache, tokens.shape[1] - 1)[:, -1]
         return tokens[:, P:]
 
+
+    def beam_search(self, enc_out: torch.Tensor, prompt: torch.Tensor, gc: GenConfig, num_beams: int = 5,
+                    length_penalty: float = 1.0, timestamps: bool = True) -> torch.Tensor:
+        """GenerationMixin._beam_search ($TF/generation/utils.py:3076-3400 and its helpers :2876-3075) for the
+        Whisper decoder, early_stopping=False, do_sample=False, one returned sequence per row.
+
+        Per step: fp32 log-softmax of the logits over the whole vocabulary, THEN the logits processors (they mask
+        log-probabilities here, not logits), accumulated onto the running beam scores; the best 2*num_beams of the
+        num_beams*vocab continuations are kept, those that hit a stopping criterion (eos, max_length) compete —
+        divided by (generated length)**length_penalty — for the num_beams finished slots, the best num_beams
+        others continue (the self-attention cache rows are re-gathered by their beam of origin).  The loop ends when
+        the best running score over (current generated length)**length_penalty cannot beat the worst finished one.
+        Returns the best finished sequence per row without the prompt, right-padded with pad_token_id."""
+        B, P = prompt.shape
+        K, V, L = num_beams, self.dims.vocab, gc.max_length
+        NEG = -1.0e9
+        enc = enc_out.repeat_interleave(K, dim=0)
+        running = torch.full((B, K, L), gc.pad_token_id, dtype=torch.long)
+        running[:, :, :P] = prompt[:, None, :]
+        finished_seq = running.clone()
+        running_scores = torch.zeros(B, K)
+        running_scores[:, 1:] = NEG
+        beam_scores = torch.full((B, K), NEG)
+        is_finished = torch.zeros(B, K, dtype=torch.bool)
+        gen_len = torch.zeros(B, K, dtype=torch.long)          # generated length of the finished slots
+        improvable = torch.ones(B, 1, dtype=torch.bool)
+        top_mask = torch.cat([torch.ones(K, dtype=torch.bool), torch.zeros(K, dtype=torch.bool)])
+        cache = self.new_cache()
+        cur = P
+        logits = self.decode(running[:, :, :P].reshape(B * K, P), enc, cache, 0)[:, -1]
+        batch_off = (torch.arange(B) * K)[:, None]
+        while True:
+            flat = running[:, :, :cur].reshape(B * K, cur)
+            logp = torch.log_softmax(logits.float(), dim=-1)
+            logp = self.process_logits(logp, [flat[r, P:].tolist() for r in range(B * K)], gc, timestamps=timestamps)
+            acc = (logp.view(B, K, V) + running_scores[:, :, None]).reshape(B, K * V)
+            top_lp, top_idx = torch.topk(acc, k=2 * K)
+            origin = top_idx // V
+            cand = torch.gather(running, 1, origin[:, :, None].expand(-1, -1, L)).clone()
+            cand[:, :, cur] = top_idx % V
+            hits = (cand[:, :, cur] == gc.eos_token_id) | (cur + 1 >= L)
+            # beams that continue
+            run_lp = top_lp + hits.float() * NEG
+            nxt = torch.topk(run_lp, k=K)[1]
+            running = torch.gather(cand, 1, nxt[:, :, None].expand(-1, -1, L))
+            running_scores = torch.gather(run_lp, 1, nxt)
+            next_origin = torch.gather(origin, 1, nxt)
+            # finished slots
+            just = hits & top_mask[None, :]
+            fin_lp = top_lp / float((cur + 1 - P) ** length_penalty)
+            fin_lp = fin_lp + (~improvable).float() * NEG
+            fin_lp = fin_lp + (~just).float() * NEG
+            m_seq = torch.cat([finished_seq, cand], dim=1)
+            m_lp = torch.cat([beam_scores, fin_lp], dim=1)
+            m_fin = torch.cat([is_finished, just], dim=1)
+            m_len = torch.cat([gen_len, torch.full((B, 2 * K), cur + 1 - P, dtype=torch.long)], dim=1)
+            keep = torch.topk(m_lp, k=K)[1]
+            finished_seq = torch.gather(m_seq, 1, keep[:, :, None].expand(-1, -1, L))
+            beam_scores = torch.gather(m_lp, 1, keep)
+            is_finished = torch.gather(m_fin, 1, keep)
+            gen_len = torch.gather(m_len, 1, keep)
+            # re-gather the self-attention cache rows of the surviving beams
+            rows = (next_origin + batch_off).reshape(-1)
+            for layer in cache:
+                for kind in ("self", "cross"):
+                    for name in ("k", "v"):
+                        if name in layer[kind]:
+                            layer[kind][name] = layer[kind][name].index_select(0, rows)
+            cur += 1
+            best_possible = running_scores[:, :1] / float((cur - P) ** length_penalty)
+            worst_finished = torch.where(is_finished, beam_scores.min(dim=1, keepdim=True)[0], torch.tensor(NEG))
+            improvable = improvable & (best_possible > worst_finished).any(dim=-1, keepdim=True)
+            if not (bool(improvable.any()) and not bool(hits.all())):
+                break
+            logits = self.decode(running[:, :, cur - 1:cur].reshape(B * K, 1), enc, cache, cur - 1)[:, -1]
+        n = int(gen_len[:, 0].max())
+        return finished_seq[:, 0, P:P + n]
+
     @staticmethod
     def retrieve_segment(seq: List[int], seek_num_frames: int, TB: int):
         """_retrieve_segment: returns (list of token lists, seek advance in mel frames)."""
@@ -283,7 +361,7 @@ class WhisperRef:
         return [list(seq)], seek_num_frames
 
     def generate(self, feats: torch.Tensor, task: str = "transcribe", gc: Optional[GenConfig] = None,
-                 trace: Optional[dict] = None, return_timestamps: bool = True) -> List[List[int]]:
+                 trace: Optional[dict] = None, return_timestamps: bool = True, num_beams: int = 1) -> List[List[int]]:
         """WhisperGenerationMixin.generate for a batch of <=30 s windows (short-form), greedy, timestamps on.
         feats [B, n_mels, 3000] fp32.  Returns the generated ids per row (segments concatenated, no padding)."""
         gc = gc or GenConfig()
@@ -312,7 +390,10 @@ class WhisperRef:
                 seg[i, :, :nfr[b]] = feats[b, :, seek[b]:seek[b] + nfr[b]]
             enc = enc0 if (guard == 1) else self.encode(seg)
             rec = [] if trace is not None else None
-            toks = self.greedy(enc, init[rows], gc, record=rec, timestamps=return_timestamps)
+            if num_beams > 1:
+                toks = self.beam_search(enc, init[rows], gc, num_beams=num_beams, timestamps=return_timestamps)
+            else:
+                toks = self.greedy(enc, init[rows], gc, record=rec, timestamps=return_timestamps)
             if trace is not None:
                 trace["iterations"].append({"rows": rows, "seek": [seek[b] for b in rows], "tokens": toks.clone(),
                                             "record": rec, "enc": enc})

@@ -102,7 +102,6 @@ def test_generate_oracle_vs_hf_golden(model_gold, variant):
 def test_generate_without_timestamps_oracle_vs_hf_golden(variant):
     """generate(return_timestamps=False): <|notimestamps|> in the prompt, suppress lists only — token-exact with
     transformers, including the extra seek iterations the (unmasked) timestamp ids of these random models cause."""
-    import json
     gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "notimestamps_tiny.json")))
     _, fb = _clips_feats()
     dims = R.WhisperDims(**helpers.TINY)
@@ -110,6 +109,24 @@ def test_generate_without_timestamps_oracle_vs_hf_golden(variant):
     got = ref.generate(fb, return_timestamps=False)
     for b, row in enumerate(got):
         want = list(gold[f"{variant}_generate"][b])
+        while want and want[-1] == 50257:
+            want.pop()
+        assert row == want, f"row {b}"
+
+
+@pytest.mark.parametrize("variant", ["decisive", "varied"])
+def test_beam_search_oracle_vs_hf_golden(variant):
+    """generate(num_beams=5) — SURVEY.md §8f rank 1, the mode the reference's literal pipeline call runs under
+    transformers >= 4.53: the oracle's restatement of GenerationMixin._beam_search (log-softmax before the processors,
+    2*num_beams candidates, length-penalised finished slots, early-stop heuristic, cache re-gather) is token-exact with
+    transformers on both fixture models, seek loop included.  Groundwork for the GPU beam path of the next round."""
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "beams_tiny.json")))
+    _, fb = _clips_feats()
+    dims = R.WhisperDims(**helpers.TINY)
+    ref = R.WhisperRef(dims, helpers.variant_state_dict(dims, variant))
+    got = ref.generate(fb, num_beams=5)
+    for b, row in enumerate(got):
+        want = list(gold[f"{variant}_generate_beams5"][b])
         while want and want[-1] == 50257:
             want.pop()
         assert row == want, f"row {b}"
