@@ -165,6 +165,64 @@ def test_generate_without_timestamps_matches_oracle(setup, variant):
     assert eng.generate(B)[0][0] >= 50365
 
 
+def _oracle_sequence_score(ref, gc, enc_row, prompt_row, seq):
+    """Sum of the processed log-probabilities the fp32 oracle assigns to `seq` (teacher-forced) after `prompt_row`."""
+    from oracle import whisper_ref as R
+    ids = torch.tensor([list(prompt_row) + list(seq)])
+    logits = ref.decode(ids, enc_row)[0]
+    P, tot = len(prompt_row), 0.0
+    for t, tok in enumerate(seq):
+        lp = torch.log_softmax(logits[P - 1 + t].float()[None], -1)
+        lp = R.WhisperRef.process_logits(lp, [list(seq[:t])], gc)
+        tot += float(lp[0, tok])
+    return tot
+
+
+def test_beam_search_against_oracle(setup, cuda_device):
+    """generate(num_beams=5) on the GPU: decode kernels (raw logits of windows x beams rows, shared cross K/V) +
+    beam.BeamSearch + KV-cache re-gather.  Beam search ranks accumulated scores of competing hypotheses, so bf16 noise
+    legitimately sends it down other near-equal trajectories than the fp32 oracle (whose search is pinned token-exact
+    to transformers on CPU, as is the bookkeeping module).  What must hold on the GPU: every returned hypothesis is
+    grammatical for the oracle (finite score), the search's own accumulated log-probability of it agrees with the
+    oracle's teacher-forced score of the same tokens within the bf16 logit tolerance (this is what breaks if a
+    history, a cross-K/V row or a re-gathered cache line were wrong), and at least one window reproduces the oracle's
+    best hypothesis exactly."""
+    from oracle import whisper_ref as R
+    from turbo_whisper_workspace_b200.config import WhisperDims
+    from turbo_whisper_workspace_b200.engine import WhisperEngine
+    clips, feats, out = setup
+    ref, _ = out["decisive"]
+    gc = R.GenConfig()
+    fb = feats.to(torch.bfloat16).float()
+    enc = ref.encode(fb)
+    langs = ref.detect_language(enc, gc)
+    prompt = torch.tensor([[gc.decoder_start_token_id, langs[b], gc.task_to_id["transcribe"]] for b in range(3)])
+    want = ref.beam_search(enc, prompt, gc, num_beams=5)
+    eng = WhisperEngine(WhisperDims(**helpers.TINY), helpers.variant_state_dict(ref.dims, "decisive"), device=cuda_device,
+                        max_batch=16)      # 3 windows x 5 beams = 15 decode rows
+    B = eng.load_pcm(clips)
+    eng.features(B)
+    eng.encode(B)
+    got = eng.decode_beams(3, prompt.to(torch.int32), 5).cpu()
+    exact = 0
+    for b in range(3):
+        n = int(eng.last_beam["length"][b])
+        seq = got[b, :n].tolist()
+        oracle_score = _oracle_sequence_score(ref, gc, enc[b:b + 1], prompt[b].tolist(), seq)
+        own = float(eng.last_beam["sum_logprob"][b])
+        assert oracle_score > -1e8, f"window {b}: hypothesis violates the timestamp grammar"
+        assert abs(own - oracle_score) < 0.02 * n + 0.5, (b, own, oracle_score, n)
+        w = want[b].tolist()
+        while w and w[-1] == gc.pad_token_id and len(w) > n:
+            w.pop()
+        exact += seq == w[:n] and n == len(w)
+    assert exact >= 1
+    # the seek loop with beams, then greedy again on the same engine (identity enc_row restored, other graph)
+    rows = eng.generate(B, num_beams=5)
+    assert len(rows) == 3 and all(r and r[0] >= 50365 for r in rows)
+    assert eng.generate(B)[0][0] >= 50365
+
+
 def test_generate_matches_oracle_varied_prefix(setup):
     """Free-running on the low-margin model: identical up to the first non-decisive oracle step."""
     clips, feats, out = setup

@@ -108,6 +108,12 @@ def test_pipeline_short_clip_and_errors(pipes):
         p(pcm, return_timestamps="word")
     r2 = p(pcm)                      # HF default: no timestamps -> {"text"} only
     assert set(r2) == {"text"} and isinstance(r2["text"], str)
+    # beam search through the pipeline: every window occupies num_beams decode rows (4-row engine: 2 windows x 2 beams)
+    r3 = p(np.concatenate([pcm, pcm, pcm]), chunk_length_s=3, stride_length_s=0, batch_size=8, return_timestamps=True,
+           generate_kwargs={"num_beams": 2})
+    assert set(r3) == {"text", "chunks"} and len(r3["chunks"]) >= 1
+    with pytest.raises(ValueError):
+        p(pcm, return_timestamps=True, generate_kwargs={"num_beams": 5})   # 5 rows do not fit the 4-row fixture engine
     # explicit language / translate task use the forced-prompt path (no language detection step)
     gen = p.generation
     gen.lang_to_id = {"<|en|>": 50259, "<|fr|>": 50265}

@@ -230,6 +230,8 @@ class WhisperEngine:
             self.cross_part = z(Bm, dims.heads, cross_splits, 66, dtype=f32)
             self.cross_cnt = z(Bm, dims.heads, dtype=i32)
             self.ln_cnt = z(1, dtype=i32)
+            # decode row -> window of the encoder batch whose cross K/V it reads (identity; beams of one window share a row)
+            self.enc_row = torch.arange(Bm, dtype=i32, device=dev)
             self.logits = None   # optional [Bm, vocab] fp32 raw-logit tap for parity tests
             self.choices = None  # optional [Bm, max_len] int32 tap of the un-forced picks
             self.sup_bits = torch.from_numpy(_bitmap(self.gen.suppress_tokens, dims.vocab).view(np.int32)).to(dev)
@@ -370,7 +372,7 @@ class WhisperEngine:
                   "cross q_proj")
             kptr = C.c_void_p(self.ckv.data_ptr() + ((i * 2 + 0) * H) * blk * 2)
             vptr = C.c_void_p(self.ckv.data_ptr() + ((i * 2 + 1) * H) * blk * 2)
-            check(lib.tw_dec_cross_attn(p(self.dq), p(self.datt), kptr, vptr, 64, S * 64, blk, None, S, B, H,
+            check(lib.tw_dec_cross_attn(p(self.dq), p(self.datt), kptr, vptr, 64, S * 64, blk, p(self.enc_row), S, B, H,
                                         self.cross_splits, p(self.cross_part), p(self.cross_cnt), st), "tw_dec_cross_attn")
             check(lib.tw_dec_linear(C.byref(self._skinny(q + "cout_w", self.datt, q + "cout_b", B, D, ln=q + "ln3")), 2,
                                     p(self.dx), D, st), "cross out_proj")
@@ -464,19 +466,89 @@ class WhisperEngine:
             self.stats["launches"] += steps * self.launches_per_step
             return self.tokens[:B]
 
+    def decode_beams(self, n: int, prompts: torch.Tensor, num_beams: int, timestamps: bool = True) -> torch.Tensor:
+        """Beam search ($TF/generation/utils.py:3076 `_beam_search`, early_stopping=False) for n windows against the
+        encoder state left by encode(): n * num_beams decode rows share the windows' cross K/V through `enc_row`, the
+        decode kernels produce the raw fp32 logits of every row (tap), :class:`beam.BeamSearch` picks the
+        continuations on the device, and the paged self-attention cache rows are re-gathered by beam of origin.
+        prompts: int [n, 3] with the language resolved.  Returns int64 [n, T]: best hypothesis per window without
+        the prompt, right-padded with pad_token_id."""
+        from .beam import BeamConfig, BeamSearch
+        K, R = int(num_beams), n * int(num_beams)
+        if R > self.max_batch:
+            raise ValueError(f"{n} windows x {K} beams exceed max_batch {self.max_batch}")
+        dev, gen, d = self.device, self.gen, self.dims
+        if self.logits is None:
+            self.enable_taps()
+        with torch.cuda.device(dev):
+            tail = [] if timestamps else [gen.no_timestamps_token_id]
+            prompt = torch.cat([prompts.to(torch.long).cpu(), torch.tensor([tail] * n, dtype=torch.long).view(n, len(tail))], dim=1)
+            P = prompt.shape[1]
+            rows_prompt = prompt.repeat_interleave(K, dim=0)                      # [R, P]
+            tok0 = torch.full((R, self.max_len), gen.pad_token_id, dtype=torch.int32)
+            tok0[:, :P] = rows_prompt.to(torch.int32)
+            frc = torch.full((R, self.max_len), -1, dtype=torch.int32)
+            frc[:, 1:P] = rows_prompt[:, 1:].to(torch.int32)
+            st0 = torch.zeros(R, ROWSTATE_INTS, dtype=torch.int32)
+            st0[:, 2] = -1
+            st0[:, 7] = 2      # "flat" mode: the grammar is applied by BeamSearch on the tapped logits, not by the LM head
+            self.tokens[:R].copy_(tok0.to(dev))
+            self.forced[:R].copy_(frc.to(dev))
+            self.state[:R].copy_(st0.to(dev))
+            self.enc_row[:R].copy_((torch.arange(R, dtype=torch.int32) // K).to(dev))
+            self.grammar.begin_index = P
+            _lib.load().tw_set_pdl(0 if self.use_graphs else 1)
+            graph = self._graph_for(R) if self.use_graphs else None
+
+            def step():
+                if graph is not None:
+                    graph.replay()
+                else:
+                    self._decode_step(R)
+
+            try:
+                for _ in range(P):          # feed the prompt; the last of these steps yields the first real logits
+                    step()
+                cfg = BeamConfig(num_beams=K, vocab=d.vocab, max_length=self.max_len, eos_id=gen.eos_token_id,
+                                 pad_id=gen.pad_token_id, no_timestamps_id=gen.no_timestamps_token_id,
+                                 suppress=gen.suppress_tokens, begin_suppress=gen.begin_suppress_tokens,
+                                 max_initial_timestamp_index=gen.max_initial_timestamp_index, timestamps=timestamps)
+                bs = BeamSearch(cfg, prompt.to(dev))
+                L = d.dec_layers
+                ppr = self.pages_per_row
+                pool = self.kv_pool.view(L, 2, self.max_batch, ppr * PAGE, d.d_model)   # block_table is the identity layout
+                steps = P
+                while True:
+                    origin = bs.step(self.logits[:R])
+                    if bs.done:
+                        break
+                    cached = bs.cur - 1                                   # positions 0 .. cached-1 hold the histories
+                    pool[:, :, :R, :cached] = pool[:, :, :R, :cached].index_select(2, origin)
+                    self.tokens[:R, :bs.cur].copy_(bs.rows().to(torch.int32))
+                    step()
+                    steps += 1
+                self.stats["dec_steps"] += steps
+                self.stats["launches"] += steps * self.launches_per_step
+                # the search's own accounting of the returned hypotheses (sum of processed log-probabilities, length)
+                self.last_beam = {"sum_logprob": (bs.beam_scores[:, 0] * bs.gen_len[:, 0].float() ** bs.cfg.length_penalty).cpu(),
+                                  "length": bs.gen_len[:, 0].cpu()}
+                return bs.result()
+            finally:
+                self.enc_row.copy_(torch.arange(self.max_batch, dtype=torch.int32, device=dev))
+
     # ------------------------------------------------------------------------------------ generate
     def generate_from_pcm(self, clips: Sequence[np.ndarray], task: str = "transcribe",
-                          language: Optional[str] = None, return_timestamps: bool = True) -> List[List[int]]:
+                          language: Optional[str] = None, return_timestamps: bool = True, num_beams: int = 1) -> List[List[int]]:
         """PCM windows (<= 30 s each) -> generated token ids per window (segments concatenated), the
         output contract of ``WhisperGenerationMixin.generate(..., return_timestamps=True)`` minus padding."""
         if self.stream is not None:
             with torch.cuda.stream(self.stream):
                 B = self.load_pcm(clips)
                 self.features(B)
-                return self.generate(B, task=task, language=language, return_timestamps=return_timestamps)
+                return self.generate(B, task=task, language=language, return_timestamps=return_timestamps, num_beams=num_beams)
         B = self.load_pcm(clips)
         self.features(B)
-        return self.generate(B, task=task, language=language, return_timestamps=return_timestamps)
+        return self.generate(B, task=task, language=language, return_timestamps=return_timestamps, num_beams=num_beams)
 
     def _strip(self, row: List[int]) -> List[int]:
         """generate_with_fallback's pad / eos stripping ($TF/...generation_whisper.py:1063-1086)."""
@@ -493,7 +565,7 @@ class WhisperEngine:
         return s
 
     def generate(self, B: int, task: str = "transcribe", language: Optional[str] = None,
-                 trace: Optional[dict] = None, return_timestamps: bool = True) -> List[List[int]]:
+                 trace: Optional[dict] = None, return_timestamps: bool = True, num_beams: int = 1) -> List[List[int]]:
         """Short-form seek loop over the features in self.mel_t[:B] (greedy; timestamp grammar on unless
         ``return_timestamps`` is False, in which case <|notimestamps|> joins the prompt)."""
         gen = self.gen
@@ -531,7 +603,20 @@ class WhisperEngine:
                 self.encode(n, mel)
                 prompts = torch.tensor([[gen.decoder_start_token_id, langs[b], gen.task_to_id[task]] for b in rows],
                                        dtype=torch.int32)
-                toks = self.decode(n, prompts, timestamps=bool(return_timestamps)).cpu().tolist()
+                if num_beams > 1:
+                    if any(l < 0 for l in (langs[b] for b in rows)):
+                        # language detection first (one decoder position), as detect_language does before generate
+                        first = self.decode(n, prompts, n_steps=1, timestamps=bool(return_timestamps))[:, 1].cpu().tolist()
+                        for i, b in enumerate(rows):
+                            if langs[b] < 0:
+                                langs[b] = int(first[i])
+                        prompts = torch.tensor([[gen.decoder_start_token_id, langs[b], gen.task_to_id[task]] for b in rows],
+                                               dtype=torch.int32)
+                    best = self.decode_beams(n, prompts, num_beams, timestamps=bool(return_timestamps)).cpu().tolist()
+                    head = [gen.decoder_start_token_id, 0, gen.task_to_id[task]] + ([] if return_timestamps else [gen.no_timestamps_token_id])
+                    toks = [[head[0], langs[b]] + head[2:] + best[i] for i, b in enumerate(rows)]
+                else:
+                    toks = self.decode(n, prompts, timestamps=bool(return_timestamps)).cpu().tolist()
                 self.stats["d2h_bytes"] += n * self.max_len * 4
                 if trace is not None:
                     trace.setdefault("iterations", []).append({"rows": list(rows), "seek": [seek[b] for b in rows],

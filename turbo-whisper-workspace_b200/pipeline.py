@@ -186,6 +186,9 @@ class B200WhisperPipeline:
             scheduler = WindowScheduler(state_dict, dims, self.generation, devices, max_batch,
                                         contexts_per_device=contexts_per_device)
         self.scheduler = scheduler
+        # default beam count of a call (generate_kwargs={"num_beams": k} overrides).  1 = greedy, the mode the north star
+        # names; transformers >= 4.53 pipelines default to 5, which `num_beams=5` reproduces
+        self.num_beams = 1
         # device of the audio-ingest kernel (resampling of inputs that are not at 16 kHz); none with an injected scheduler
         self.ingest_device = None if not hasattr(scheduler, "devices") else scheduler.devices[0]
         from .decode_asr import AsrDecoder
@@ -211,8 +214,7 @@ class B200WhisperPipeline:
         generate_kwargs = dict(generate_kwargs or {})
         task = generate_kwargs.pop("task", None) or "transcribe"
         language = generate_kwargs.pop("language", None)
-        if generate_kwargs.pop("num_beams", 1) not in (1, None):
-            raise NotImplementedError("beam search is not implemented by the B200 engine (greedy only)")
+        num_beams = int(generate_kwargs.pop("num_beams", None) or self.num_beams or 1)
         if return_timestamps == "word":
             raise NotImplementedError('return_timestamps="word" is not implemented by the B200 engine')
         if return_timestamps == "char":
@@ -245,10 +247,12 @@ class B200WhisperPipeline:
         clips = [audio[s:e][:N_SAMPLES] for (s, e, _, _) in windows]
         # return_timestamps falsy (the HF default): generate runs with <|notimestamps|> in the prompt and without the
         # timestamp grammar, and the windows are merged on their overlapping text only
-        if return_timestamps:
-            token_rows = self.scheduler.run(clips, task=task, language=language)
-        else:
-            token_rows = self.scheduler.run(clips, task=task, language=language, return_timestamps=False)
+        run_kw: Dict[str, Any] = {}
+        if not return_timestamps:
+            run_kw["return_timestamps"] = False
+        if num_beams > 1:
+            run_kw["num_beams"] = num_beams      # beam search: every window occupies num_beams decode rows
+        token_rows = self.scheduler.run(clips, task=task, language=language, **run_kw)
         self.last_stats = dict(self.scheduler.last_stats, windows=len(windows), audio_seconds=audio.shape[0] / sr)
 
         # HF batches `batch_size` consecutive windows per generate call and right-pads each batch to its

@@ -34,13 +34,24 @@ def partition(n_items: int, n_workers: int) -> List[Tuple[int, int]]:
     return out
 
 
+def _extra(return_timestamps: bool, num_beams: int) -> Dict[str, Any]:
+    """Keyword arguments beyond (task, language), passed only when they differ from the defaults so that simple
+    engine stand-ins keep working."""
+    kw: Dict[str, Any] = {}
+    if not return_timestamps:
+        kw["return_timestamps"] = False
+    if num_beams > 1:
+        kw["num_beams"] = int(num_beams)
+    return kw
+
+
 def run_in_microbatches(engine, clips: Sequence[np.ndarray], task: str, language: Optional[str],
-                        return_timestamps: bool = True) -> List[List[int]]:
+                        return_timestamps: bool = True, num_beams: int = 1) -> List[List[int]]:
     rows: List[List[int]] = []
-    mb = engine.max_batch
+    mb = max(1, engine.max_batch // max(1, num_beams))      # every window occupies num_beams decode rows
     for i in range(0, len(clips), mb):
         rows.extend(engine.generate_from_pcm(clips[i:i + mb], task=task, language=language,
-                                             return_timestamps=return_timestamps))
+                                             **_extra(return_timestamps, num_beams)))
     return rows
 
 
@@ -74,7 +85,7 @@ class WindowScheduler:
         return [e for ctxs in self.engines for e in ctxs]
 
     def run(self, clips: Sequence[np.ndarray], task: str = "transcribe", language: Optional[str] = None,
-            return_timestamps: bool = True) -> List[List[int]]:
+            return_timestamps: bool = True, num_beams: int = 1) -> List[List[int]]:
         t0 = time.perf_counter()
         n = len(clips)
         ranges = partition(n, len(self.devices))
@@ -84,7 +95,7 @@ class WindowScheduler:
         threads = []
         for di, (s, e) in enumerate(ranges):
             ctxs = self.engines[di]
-            mb = ctxs[0].max_batch
+            mb = max(1, ctxs[0].max_batch // max(1, num_beams))   # every window occupies num_beams decode rows
             queue = [(i, min(i + mb, e)) for i in range(s, e, mb)]   # micro-batches of this device, in order
 
             def work(engine, queue=queue):
@@ -95,7 +106,7 @@ class WindowScheduler:
                                 return
                             a, b = queue.pop(0)
                         rows = engine.generate_from_pcm(clips[a:b], task=task, language=language,
-                                                        return_timestamps=return_timestamps)
+                                                        **_extra(return_timestamps, num_beams))
                         results[a:b] = rows
                 except BaseException as ex:  # surfaced on the calling thread
                     with lock:
@@ -132,9 +143,9 @@ class DistributedWindowScheduler:
         return partition(n, self.world_size)[self.rank]
 
     def run_local(self, clips: Sequence[np.ndarray], task: str = "transcribe", language: Optional[str] = None,
-                  return_timestamps: bool = True) -> List[List[int]]:
+                  return_timestamps: bool = True, num_beams: int = 1) -> List[List[int]]:
         s, e = self.local_range(len(clips))
-        return run_in_microbatches(self.engine, clips[s:e], task, language, return_timestamps) if e > s else []
+        return run_in_microbatches(self.engine, clips[s:e], task, language, return_timestamps, num_beams) if e > s else []
 
     def gather(self, local_rows: List[List[int]]) -> List[List[int]]:
         if self.world_size == 1:
@@ -148,5 +159,5 @@ class DistributedWindowScheduler:
         return rows
 
     def run(self, clips: Sequence[np.ndarray], task: str = "transcribe", language: Optional[str] = None,
-            return_timestamps: bool = True) -> List[List[int]]:
-        return self.gather(self.run_local(clips, task, language, return_timestamps))
+            return_timestamps: bool = True, num_beams: int = 1) -> List[List[int]]:
+        return self.gather(self.run_local(clips, task, language, return_timestamps, num_beams))
