@@ -196,6 +196,27 @@ int tw_dec_finalize(const float* part_val, const int32_t* part_idx, int32_t n_pa
                     int32_t tokens_ld, const int32_t* forced, int32_t* choices, void* row_state,
                     const tw_grammar* g, int32_t batch, void* stream);
 
+/* ---- word-level timestamps (return_timestamps="word") --------------------------------------------------------
+ * Replaces the `output_attentions` plumbing + WhisperGenerationMixin._extract_token_timestamps
+ * ($TF/models/whisper/generation_whisper.py:241-381; _median_filter :43-61, _dynamic_time_warping :64-112).
+ * tw_dec_align_tap runs inside the decode step of an alignment layer, right after the cross-attention query
+ * projection: for the layer's alignment heads it writes softmax(q_h K_h^T) (fp32, all src_len encoder positions) of
+ * every decode row to probs[row][slot0 + i][pos_row][:]  (probs: fp32 [batch][n_slots][max_len][src_len]; pos_row =
+ * row_state[row][0]).  K addressing as in tw_dec_cross_attn.  heads_dev: device int32 [n_heads]. */
+int tw_dec_align_tap(const void* q_bf16, int32_t q_ld, const void* k_bf16, int64_t kv_row_stride,
+                     int64_t kv_batch_stride, int64_t kv_head_stride, const int32_t* enc_row, const void* row_state,
+                     const int32_t* heads_dev, int32_t n_heads, int32_t slot0, int32_t n_slots, int32_t max_len,
+                     int32_t src_len, int32_t batch, float* probs, void* stream);
+/* matrix[row][t][f] = mean over slots of median_filter_f((probs[row][slot][t0 + t][f] - mean_t) / std_t) for
+ * t < n_tok, f < n_frames_dev[row] (population std over the n_tok token positions; reflect-padded median of odd
+ * width <= 15).  stats: scratch fp32 [batch][n_slots][src_len][2]; matrix: fp32 [batch][max_len][src_len]. */
+int tw_align_matrix(const float* probs, const int32_t* n_frames_dev, int32_t batch, int32_t n_slots, int32_t max_len,
+                    int32_t src_len, int32_t t0, int32_t n_tok, int32_t filter_width, float* stats, float* matrix,
+                    void* stream);
+/* host: dynamic time warping over -matrix (fp32 [n_tok][ld], n_frames columns used) with HF's float32 cost table and
+ * tie rules; token_frame[t] = first encoder frame of token t's run on the warping path (timestamp = frame * 0.02 s). */
+int tw_dtw_token_frames(const float* matrix, int64_t ld, int32_t n_tok, int32_t n_frames, int32_t* token_frame);
+
 /* ---- audio ingest: format conversion + channel down-mix + polyphase windowed-sinc resampling ---------------
  * Replaces torchaudio.functional.resample (sinc_interp_hann, lowpass_filter_width 6, rolloff 0.99) in the pipeline's
  * preprocess ($TF/pipelines/automatic_speech_recognition.py:394-407) and the sample conversion / `-ac 1` down-mix

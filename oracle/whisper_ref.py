@@ -95,7 +95,7 @@ class WhisperRef:
 
     # -------------------------------------------------------------------------------- attention
     def _attn(self, pfx: str, x: torch.Tensor, kv_src: Optional[torch.Tensor] = None, causal: bool = False,
-              cache: Optional[dict] = None) -> torch.Tensor:
+              cache: Optional[dict] = None, probs_out: Optional[list] = None) -> torch.Tensor:
         """Multi-head attention; q is scaled by head_dim**-0.5 after the bias ($TF ...:310)."""
         sd, H, dh = self.sd, self.dims.heads, self.dims.head_dim
         B, T, _ = x.shape
@@ -120,6 +120,8 @@ class WhisperRef:
             mask = torch.ones(T, S, dtype=torch.bool, device=s.device).tril(diagonal=S - T)
             s = s.masked_fill(~mask, float("-inf"))
         p = torch.softmax(s, dim=-1)
+        if probs_out is not None:
+            probs_out.append(p)     # eager-attention `attn_weights` [B, H, T, S] (what output_attentions returns)
         o = (p @ v).transpose(1, 2).reshape(B, T, H * dh)
         return F.linear(o, sd[pfx + "out_proj.weight"], sd[pfx + "out_proj.bias"])
 
@@ -155,8 +157,9 @@ class WhisperRef:
         return [{"self": {}, "cross": {}} for _ in range(self.dims.dec_layers)]
 
     def decode(self, tokens: torch.Tensor, enc_out: torch.Tensor, cache: Optional[List[dict]] = None,
-               past_len: int = 0) -> torch.Tensor:
-        """tokens [B, T] (new positions only when a cache is given) -> fp32 logits [B, T, vocab]."""
+               past_len: int = 0, cross: Optional[List[list]] = None) -> torch.Tensor:
+        """tokens [B, T] (new positions only when a cache is given) -> fp32 logits [B, T, vocab].
+        ``cross``: one list per decoder layer; receives that layer's cross-attention weights [B, H, T, S]."""
         sd = self.sd
         B, T = tokens.shape
         x = sd["model.decoder.embed_tokens.weight"][tokens] + sd["model.decoder.embed_positions.weight"][past_len:past_len + T]
@@ -165,7 +168,7 @@ class WhisperRef:
             c = cache[i] if cache is not None else {"self": None, "cross": None}
             x = x + self._attn(p + "self_attn.", self._ln(p + "self_attn_layer_norm.", x), causal=True, cache=c["self"])
             x = x + self._attn(p + "encoder_attn.", self._ln(p + "encoder_attn_layer_norm.", x), kv_src=enc_out,
-                               cache=c["cross"])
+                               cache=c["cross"], probs_out=None if cross is None else cross[i])
             x = x + self._mlp(p, self._ln(p + "final_layer_norm.", x))
         x = self._ln("model.decoder.layer_norm.", x)
         return F.linear(x, sd["model.decoder.embed_tokens.weight"])  # tied proj_out, no bias
@@ -226,14 +229,14 @@ class WhisperRef:
         return logits.argmax(-1).tolist()
 
     def greedy(self, enc_out: torch.Tensor, prompt: torch.Tensor, gc: GenConfig, record: Optional[list] = None,
-               timestamps: bool = True):
+               timestamps: bool = True, cross: Optional[List[list]] = None):
         """GenerationMixin._sample, greedy: returns generated tokens per row, [B, <=max_length-len(prompt)];
         finished rows keep emitting pad (= eos).  ``record`` collects (raw fp32 logits, processed scores)."""
         B, P = prompt.shape
         cache = self.new_cache()
         tokens = prompt.clone()
         finished = torch.zeros(B, dtype=torch.bool)
-        logits = self.decode(prompt, enc_out, cache, 0)[:, -1]
+        logits = self.decode(prompt, enc_out, cache, 0, cross=cross)[:, -1]
         while True:
             gen = [tokens[k, P:].tolist() for k in range(B)]
             scores = self.process_logits(logits, gen, gc, timestamps=timestamps)
@@ -258,8 +261,83 @@ class WhisperRef:
             finished = finished | (nxt == gc.eos_token_id)
             if bool(finished.all()) or tokens.shape[1] >= gc.max_length:
                 break
-            logits = self.decode(nxt[:, None], enc_out, cache, tokens.shape[1] - 1)[:, -1]
+            logits = self.decode(nxt[:, None], enc_out, cache, tokens.shape[1] - 1, cross=cross)[:, -1]
         return tokens[:, P:]
+
+    # -------------------------------------------------------------------------------- token timestamps
+    @staticmethod
+    def median_filter(x: torch.Tensor, width: int) -> torch.Tensor:
+        """_median_filter ($TF/models/whisper/generation_whisper.py:43-61): reflect-padded median along the last axis."""
+        pad = width // 2
+        if x.shape[-1] <= pad:
+            return x
+        x = F.pad(x, (pad, pad, 0, 0), mode="reflect")
+        return x.unfold(-1, width, 1).sort()[0][..., pad]
+
+    @staticmethod
+    def dtw_token_frames(matrix) -> List[int]:
+        """_dynamic_time_warping (:64-112) on ``matrix`` (float64 numpy [tokens, frames], already negated) followed by
+        the jump extraction of _extract_token_timestamps (:367-369): first frame of every token's run on the path.
+        Cost table in float32, each cell the float64 sum rounded to float32; anti-diagonal sweep (cell (i, j) only
+        needs diagonals i+j-1 and i+j-2), same values as HF's double loop."""
+        import numpy as np
+        n, m = matrix.shape
+        cost = np.full((n + 1, m + 1), np.inf, dtype=np.float32)
+        trace = -np.ones((n + 1, m + 1), dtype=np.int8)
+        cost[0, 0] = 0
+        for d in range(2, n + m + 1):
+            i = np.arange(max(1, d - m), min(n, d - 1) + 1)
+            j = d - i
+            c0, c1, c2 = cost[i - 1, j - 1], cost[i - 1, j], cost[i, j - 1]
+            t = np.where((c0 < c1) & (c0 < c2), 0, np.where((c1 < c0) & (c1 < c2), 1, 2)).astype(np.int8)
+            c = np.where(t == 0, c0, np.where(t == 1, c1, c2))
+            cost[i, j] = (matrix[i - 1, j - 1] + c.astype(np.float64)).astype(np.float32)
+            trace[i, j] = t
+        trace[0, :] = 2
+        trace[:, 0] = 1
+        i, j = n, m
+        text, time = [], []
+        while i > 0 or j > 0:
+            text.append(i - 1)
+            time.append(j - 1)
+            t = trace[i, j]
+            if t == 0:
+                i, j = i - 1, j - 1
+            elif t == 1:
+                i -= 1
+            else:
+                j -= 1
+        text, time = np.array(text)[::-1], np.array(time)[::-1]
+        jumps = np.pad(np.diff(text), (1, 0), constant_values=1).astype(bool)
+        return time[jumps].tolist()
+
+    def alignment_matrix(self, cross: List[list], alignment_heads, row: int, n_prompt: int, num_frames: int,
+                         median_width: int = 7) -> torch.Tensor:
+        """The per-row branch of _extract_token_timestamps (:352-365): stack the alignment (layer, head) pairs, crop to
+        num_frames // 2 encoder positions, drop the prompt positions, standardise over the token axis (population
+        std), median-filter along frames, average the heads.  -> fp32 [tokens, frames]."""
+        w = torch.stack([torch.cat(cross[l], dim=2)[row, h] for l, h in alignment_heads])      # [heads, T, S]
+        w = w[..., : num_frames // 2][:, n_prompt:, :]
+        std = torch.std(w, dim=-2, keepdim=True, unbiased=False)
+        mean = torch.mean(w, dim=-2, keepdim=True)
+        w = self.median_filter((w - mean) / std, median_width)
+        return w.mean(dim=0)
+
+    def token_timestamps(self, cross: List[list], alignment_heads, n_rows: int, n_prompt: int, num_frames: Sequence[int],
+                         time_precision: float = 0.02, median_width: int = 7) -> torch.Tensor:
+        """_extract_token_timestamps for a greedy batch: fp32 [rows, prompt + generated]: 0 for the prompt positions,
+        the DTW jump time of every generated token, the last one repeated for the final token (its cross-attention
+        is never computed)."""
+        T = sum(p.shape[2] for p in cross[0])
+        out = torch.zeros(n_rows, T + 1, dtype=torch.float32)
+        if T - n_prompt <= 0:
+            return out
+        for b in range(n_rows):
+            m = self.alignment_matrix(cross, alignment_heads, b, n_prompt, int(num_frames[b]), median_width)
+            frames = self.dtw_token_frames(-m.double().numpy())
+            jt = torch.tensor([f * time_precision for f in frames], dtype=torch.float64)
+            out[b] = torch.cat([torch.zeros(n_prompt, dtype=torch.float64), jt, jt[-1:]]).to(torch.float32)
+        return out
 
 
     def beam_search(self, enc_out: torch.Tensor, prompt: torch.Tensor, gc: GenConfig, num_beams: int = 5,
@@ -361,9 +439,17 @@ class WhisperRef:
         return [list(seq)], seek_num_frames
 
     def generate(self, feats: torch.Tensor, task: str = "transcribe", gc: Optional[GenConfig] = None,
-                 trace: Optional[dict] = None, return_timestamps: bool = True, num_beams: int = 1) -> List[List[int]]:
+                 trace: Optional[dict] = None, return_timestamps: bool = True, num_beams: int = 1,
+                 alignment_heads=None, num_frames: Optional[Sequence[int]] = None, median_width: int = 7,
+                 token_ts: Optional[dict] = None) -> List[List[int]]:
         """WhisperGenerationMixin.generate for a batch of <=30 s windows (short-form), greedy, timestamps on.
-        feats [B, n_mels, 3000] fp32.  Returns the generated ids per row (segments concatenated, no padding)."""
+        feats [B, n_mels, 3000] fp32.  Returns the generated ids per row (segments concatenated, no padding).
+
+        ``alignment_heads`` + ``num_frames`` (attention_mask.sum(-1) per row) + ``token_ts`` = the
+        return_token_timestamps=True path (greedy only): token_ts["segments"][b] receives the per-token times of the
+        returned ids as the `segments` carry them (seek offset added, _retrieve_segment :2036-2039, what the ASR
+        pipeline reads) and token_ts["sequences"][b] the ones of the padded `token_timestamps` output (no offset,
+        _pad_to_max_length :188-193)."""
         gc = gc or GenConfig()
         TB = gc.no_timestamps_token_id + 1
         B = feats.shape[0]
@@ -390,10 +476,20 @@ class WhisperRef:
                 seg[i, :, :nfr[b]] = feats[b, :, seek[b]:seek[b] + nfr[b]]
             enc = enc0 if (guard == 1) else self.encode(seg)
             rec = [] if trace is not None else None
+            cross = [[] for _ in range(self.dims.dec_layers)] if alignment_heads is not None else None
             if num_beams > 1:
                 toks = self.beam_search(enc, init[rows], gc, num_beams=num_beams, timestamps=return_timestamps)
             else:
-                toks = self.greedy(enc, init[rows], gc, record=rec, timestamps=return_timestamps)
+                toks = self.greedy(enc, init[rows], gc, record=rec, timestamps=return_timestamps, cross=cross)
+            if cross is not None:
+                # num_frames - seek per active row (_postprocess_outputs :1146-1151); negative values crop from the
+                # end exactly as the tensor slice `[..., : n // 2]` does
+                P = init.shape[1]
+                tt = self.token_timestamps(cross, alignment_heads, len(rows), P,
+                                           [int(num_frames[b]) - seek[b] for b in rows], median_width=median_width)
+                if token_ts is not None:
+                    token_ts.setdefault("segments", [[] for _ in range(B)])
+                    token_ts.setdefault("sequences", [[] for _ in range(B)])
             if trace is not None:
                 trace["iterations"].append({"rows": rows, "seek": [seek[b] for b in rows], "tokens": toks.clone(),
                                             "record": rec, "enc": enc})
@@ -408,6 +504,12 @@ class WhisperRef:
                 if s[-1] == gc.eos_token_id:
                     s = s[:-1]
                 segs, adv = self.retrieve_segment(s, nfr[b], TB)
+                if cross is not None and token_ts is not None:
+                    n_kept = sum(len(sg) for sg in segs)
+                    raw = tt[i, P:P + n_kept]
+                    off = torch.tensor(seek[b], dtype=torch.float64) * 0.02 / 2       # time_offset (:800-802)
+                    token_ts["sequences"][b].extend(raw.tolist())
+                    token_ts["segments"][b].extend((raw + off).tolist())
                 seek[b] += adv
                 for sg in segs:
                     out[b].extend(sg)

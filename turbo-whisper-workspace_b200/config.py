@@ -5,7 +5,7 @@ Mirrors the fields of ``WhisperConfig`` / ``generation_config.json`` that the ho
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import Dict, List
+from typing import Dict, List, Optional
 
 N_SAMPLES = 480000   # 30 s at 16 kHz
 N_FRAMES = 3000      # mel frames per window
@@ -73,6 +73,10 @@ class GenerationSettings:
     lang_last: int = 50358
     task_to_id: Dict[str, int] = field(default_factory=lambda: {"transcribe": 50360, "translate": 50359})
     lang_to_id: Dict[str, int] = field(default_factory=dict)  # "<|en|>" -> id, optional (explicit language)
+    # word-level timestamps: (decoder layer, head) pairs of generation_config.alignment_heads (None: not available, as
+    # for a generation config without the field) and WhisperConfig.median_filter_width
+    alignment_heads: Optional[List[List[int]]] = None
+    median_filter_width: int = 7
 
     @property
     def timestamp_begin(self) -> int:
@@ -99,4 +103,6 @@ class GenerationSettings:
             if ids != list(range(ids[0], ids[-1] + 1)):
                 raise ValueError("language ids must be contiguous")
             s.lang_first, s.lang_last = ids[0], ids[-1]
+        if getattr(gc, "alignment_heads", None) is not None:
+            s.alignment_heads = [[int(l), int(h)] for l, h in gc.alignment_heads]
         return s

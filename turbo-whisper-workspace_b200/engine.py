@@ -232,6 +232,8 @@ class WhisperEngine:
             self.ln_cnt = z(1, dtype=i32)
             # decode row -> window of the encoder batch whose cross K/V it reads (identity; beams of one window share a row)
             self.enc_row = torch.arange(Bm, dtype=i32, device=dev)
+            self.align = None    # word-timestamp workspaces (enable_alignment)
+            self._align_on = False
             self.logits = None   # optional [Bm, vocab] fp32 raw-logit tap for parity tests
             self.choices = None  # optional [Bm, max_len] int32 tap of the un-forced picks
             self.sup_bits = torch.from_numpy(_bitmap(self.gen.suppress_tokens, dims.vocab).view(np.int32)).to(dev)
@@ -264,6 +266,89 @@ class WhisperEngine:
             self.logits = torch.zeros(self.max_batch, self.dims.vocab, dtype=torch.float32, device=self.device)
             self.choices = torch.zeros(self.max_batch, self.max_len, dtype=torch.int32, device=self.device)
             self._graphs.clear()
+
+    def enable_alignment(self):
+        """Workspaces of the word-timestamp path (return_timestamps="word"): the alignment-head cross-attention tap
+        fp32 [max_batch][slots][max_len][1500], the column statistics and the token x frame matrix."""
+        heads = self.gen.alignment_heads
+        if not heads:
+            raise ValueError("Model generation config has no `alignment_heads`, token-level timestamps not available. "
+                             "See https://gist.github.com/hollance/42e32852f24243b748ae6bc1f985b13a on how to add this "
+                             "property to the generation config.")
+        if self.align is not None:
+            return
+        d, dev, Bm, S = self.dims, self.device, self.max_batch, self.dims.max_source_positions
+        for l, h in heads:
+            if not (0 <= l < d.dec_layers and 0 <= h < d.heads):
+                raise ValueError(f"alignment head ({l}, {h}) is outside the decoder ({d.dec_layers} layers x {d.heads} heads)")
+        # slots keep the order of generation_config.alignment_heads (the head mean is order-sensitive in fp32)
+        by_layer: Dict[int, List[tuple]] = {}
+        for slot, (l, h) in enumerate(heads):
+            by_layer.setdefault(int(l), []).append((slot, int(h)))
+        layers = {}
+        with torch.cuda.device(dev):
+            for l, items in by_layer.items():
+                # consecutive slots of one layer share a launch
+                runs, cur = [], [items[0]]
+                for it in items[1:]:
+                    if it[0] == cur[-1][0] + 1:
+                        cur.append(it)
+                    else:
+                        runs.append(cur)
+                        cur = [it]
+                runs.append(cur)
+                layers[l] = [(r[0][0], torch.tensor([h for _, h in r], dtype=torch.int32, device=dev)) for r in runs]
+            n = len(heads)
+            self.align = {
+                "layers": layers, "n_slots": n,
+                "probs": torch.zeros(Bm, n, self.max_len, S, dtype=torch.float32, device=dev),
+                "stats": torch.zeros(Bm, n, S, 2, dtype=torch.float32, device=dev),
+                "matrix": torch.zeros(Bm, self.max_len, S, dtype=torch.float32, device=dev),
+                "n_frames": torch.zeros(Bm, dtype=torch.int32, device=dev),
+                "host": torch.zeros(Bm, self.max_len, S, dtype=torch.float32).pin_memory(),
+            }
+
+    def token_frames(self, B: int, tokens: List[List[int]], n_prompt: int, n_frames: Sequence[int]) -> List[List[int]]:
+        """_extract_token_timestamps ($TF/models/whisper/generation_whisper.py:241-381) for the B rows just decoded
+        with the alignment tap on: per row the encoder frame of every token position >= n_prompt of the batch's
+        sequence (HF's `sequences` of this generate call: as long as the longest row, eos included) but the last.
+        ``tokens``: the rows of decode(); ``n_frames[b]``: encoder frames kept for row b (the `[..., : num_frames // 2]`
+        crop, already resolved to a count).  Frame -1 where HF's path leaves the table (no frames / NaN costs)."""
+        a, lib, S = self.align, _lib.load(), self.dims.max_source_positions
+        eos = self.gen.eos_token_id
+        total = 0
+        for row in tokens:
+            L = len(row)
+            for i in range(n_prompt, len(row)):
+                if row[i] == eos:
+                    L = i + 1
+                    break
+            total = max(total, L)
+        n_tok = total - 1 - n_prompt          # cross-attention exists for every position but the last
+        if n_tok <= 0:
+            return [[] for _ in range(B)]
+        nf = [max(0, min(int(f), S)) for f in n_frames]
+        p = lambda t: C.c_void_p(t.data_ptr())
+        with torch.cuda.device(self.device):
+            a["n_frames"][:B].copy_(torch.tensor(nf, dtype=torch.int32), non_blocking=False)
+            check(lib.tw_align_matrix(p(a["probs"]), p(a["n_frames"]), B, a["n_slots"], self.max_len, S, n_prompt, n_tok,
+                                      int(self.gen.median_filter_width), p(a["stats"]), p(a["matrix"]), self._stream()),
+                  "tw_align_matrix")
+            self.stats["launches"] += 2
+            host = a["host"]
+            host[:B, :n_tok].copy_(a["matrix"][:B, :n_tok], non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            self.stats["d2h_bytes"] += B * n_tok * S * 4
+        out = []
+        frames = np.empty(n_tok, dtype=np.int32)
+        for b in range(B):
+            if nf[b] == 0:
+                out.append([-1] * n_tok)
+                continue
+            check(lib.tw_dtw_token_frames(C.c_void_p(host[b].data_ptr()), S, n_tok, nf[b],
+                                          frames.ctypes.data_as(C.c_void_p)), "tw_dtw_token_frames")
+            out.append(frames.tolist())
+        return out
 
     # ------------------------------------------------------------------------------------ front end
     def load_pcm(self, clips: Sequence[np.ndarray]) -> int:
@@ -372,6 +457,12 @@ class WhisperEngine:
                   "cross q_proj")
             kptr = C.c_void_p(self.ckv.data_ptr() + ((i * 2 + 0) * H) * blk * 2)
             vptr = C.c_void_p(self.ckv.data_ptr() + ((i * 2 + 1) * H) * blk * 2)
+            if self._align_on and i in self.align["layers"]:
+                al = self.align
+                for slot0, heads_dev in al["layers"][i]:
+                    check(lib.tw_dec_align_tap(p(self.dq), D, kptr, 64, S * 64, blk, p(self.enc_row), p(self.state),
+                                               p(heads_dev), int(heads_dev.numel()), slot0, al["n_slots"], self.max_len,
+                                               S, B, p(al["probs"]), st), "tw_dec_align_tap")
             check(lib.tw_dec_cross_attn(p(self.dq), p(self.datt), kptr, vptr, 64, S * 64, blk, p(self.enc_row), S, B, H,
                                         self.cross_splits, p(self.cross_part), p(self.cross_cnt), st), "tw_dec_cross_attn")
             check(lib.tw_dec_linear(C.byref(self._skinny(q + "cout_w", self.datt, q + "cout_b", B, D, ln=q + "ln3")), 2,
@@ -389,11 +480,12 @@ class WhisperEngine:
 
     @property
     def launches_per_step(self) -> int:
-        return 1 + 8 * self.dims.dec_layers + 2
+        taps = sum(len(r) for r in self.align["layers"].values()) if self._align_on else 0
+        return 1 + 8 * self.dims.dec_layers + 2 + taps
 
     def _graph_for(self, B: int) -> torch.cuda.CUDAGraph:
         # the K/V block stride depends on the encoder batch; begin_index (3 / 4 with <|notimestamps|>) is a kernel argument
-        key = (B, self._ckv_batch, int(self.grammar.begin_index))
+        key = (B, self._ckv_batch, int(self.grammar.begin_index), self._align_on)
         g = self._graphs.get(key)
         if g is None:
             # a warm-up step outside capture (sets kernel attributes); state is re-initialised afterwards
@@ -538,17 +630,28 @@ class WhisperEngine:
 
     # ------------------------------------------------------------------------------------ generate
     def generate_from_pcm(self, clips: Sequence[np.ndarray], task: str = "transcribe",
-                          language: Optional[str] = None, return_timestamps: bool = True, num_beams: int = 1) -> List[List[int]]:
+                          language: Optional[str] = None, return_timestamps: bool = True, num_beams: int = 1,
+                          token_timestamps: bool = False):
         """PCM windows (<= 30 s each) -> generated token ids per window (segments concatenated), the
-        output contract of ``WhisperGenerationMixin.generate(..., return_timestamps=True)`` minus padding."""
+        output contract of ``WhisperGenerationMixin.generate(..., return_timestamps=True)`` minus padding.
+        ``token_timestamps``: every window becomes ``(ids, times)`` with one fp32 time per id — the per-segment
+        `token_timestamps` of generate(return_token_timestamps=True, return_segments=True), which the ASR pipeline
+        reads for return_timestamps="word"."""
+        def run():
+            B = self.load_pcm(clips)
+            self.features(B)
+            if not token_timestamps:
+                return self.generate(B, task=task, language=language, return_timestamps=return_timestamps,
+                                     num_beams=num_beams)
+            # attention_mask.sum(-1) of the feature extractor: the sample mask taken every hop (160) samples
+            nf = [min(N_FRAMES, -(-min(len(np.asarray(c).reshape(-1)), N_SAMPLES) // 160)) for c in clips]
+            rows = self.generate(B, task=task, language=language, return_timestamps=return_timestamps,
+                                 num_beams=num_beams, token_timestamps=True, num_frames=nf)
+            return list(zip(rows, self.last_token_ts))
         if self.stream is not None:
             with torch.cuda.stream(self.stream):
-                B = self.load_pcm(clips)
-                self.features(B)
-                return self.generate(B, task=task, language=language, return_timestamps=return_timestamps, num_beams=num_beams)
-        B = self.load_pcm(clips)
-        self.features(B)
-        return self.generate(B, task=task, language=language, return_timestamps=return_timestamps, num_beams=num_beams)
+                return run()
+        return run()
 
     def _strip(self, row: List[int]) -> List[int]:
         """generate_with_fallback's pad / eos stripping ($TF/...generation_whisper.py:1063-1086)."""
@@ -565,10 +668,24 @@ class WhisperEngine:
         return s
 
     def generate(self, B: int, task: str = "transcribe", language: Optional[str] = None,
-                 trace: Optional[dict] = None, return_timestamps: bool = True, num_beams: int = 1) -> List[List[int]]:
+                 trace: Optional[dict] = None, return_timestamps: bool = True, num_beams: int = 1,
+                 token_timestamps: bool = False, num_frames: Optional[Sequence[int]] = None) -> List[List[int]]:
         """Short-form seek loop over the features in self.mel_t[:B] (greedy; timestamp grammar on unless
-        ``return_timestamps`` is False, in which case <|notimestamps|> joins the prompt)."""
+        ``return_timestamps`` is False, in which case <|notimestamps|> joins the prompt).
+
+        ``token_timestamps`` (greedy only; ``num_frames[b]`` = valid mel frames of row b, the attention-mask sum):
+        the decode steps also tap the alignment heads' cross-attention, and ``self.last_token_ts[b]`` receives one
+        fp32 time per returned id (seek offset added, as `segments[...]["token_timestamps"]` of HF's generate;
+        ``self.last_token_ts_raw[b]`` = the padded `token_timestamps` output, no offset)."""
         gen = self.gen
+        if token_timestamps:
+            if num_beams > 1:
+                raise NotImplementedError("token timestamps with beam search are not implemented by the B200 engine")
+            if num_frames is None or len(num_frames) != B:
+                raise ValueError("token_timestamps needs num_frames for every row")
+            self.enable_alignment()
+        ts_out: List[List[float]] = [[] for _ in range(B)]
+        ts_raw: List[List[float]] = [[] for _ in range(B)]
         if task not in gen.task_to_id:
             raise ValueError(f"The `{task}` task is not supported. The task should be one of {list(gen.task_to_id)}")
         lang_id = -1
@@ -616,8 +733,18 @@ class WhisperEngine:
                     head = [gen.decoder_start_token_id, 0, gen.task_to_id[task]] + ([] if return_timestamps else [gen.no_timestamps_token_id])
                     toks = [[head[0], langs[b]] + head[2:] + best[i] for i, b in enumerate(rows)]
                 else:
-                    toks = self.decode(n, prompts, timestamps=bool(return_timestamps)).cpu().tolist()
+                    self._align_on = bool(token_timestamps)
+                    try:
+                        toks = self.decode(n, prompts, timestamps=bool(return_timestamps)).cpu().tolist()
+                    finally:
+                        self._align_on = False
                 self.stats["d2h_bytes"] += n * self.max_len * 4
+                tok_frames = None
+                if token_timestamps:
+                    # weights[..., : (num_frames - seek) // 2] (_postprocess_outputs :1146-1151, :354): python slice rules
+                    S = self.dims.max_source_positions
+                    keep = [len(range(S)[: (int(num_frames[b]) - seek[b]) // 2]) for b in rows]
+                    tok_frames = self.token_frames(n, toks, P, keep)
                 if trace is not None:
                     trace.setdefault("iterations", []).append({"rows": list(rows), "seek": [seek[b] for b in rows],
                                                                "tokens": [list(t) for t in toks]})
@@ -626,9 +753,20 @@ class WhisperEngine:
                         langs[b] = toks[i][1]
                     s = self._strip(toks[i][P:])
                     segs, adv = retrieve_segment(s, nfr[b], ts_begin)
+                    if tok_frames is not None:
+                        # token_timestamps row = [0] * prompt + jump times + [last jump time]; the segments keep the
+                        # slice of their tokens (+ the seek offset in seconds, added in fp32)
+                        n_kept = sum(len(sg) for sg in segs)
+                        jt = (np.asarray(tok_frames[i], dtype=np.float64) * 0.02).astype(np.float32)
+                        full = np.concatenate([jt, jt[-1:]]) if jt.size else np.zeros(len(toks[i]), dtype=np.float32)
+                        raw = full[:n_kept]
+                        off = np.float32(np.float64(seek[b]) * 0.02 / 2)
+                        ts_raw[b].extend(float(x) for x in raw)
+                        ts_out[b].extend(float(x) for x in (raw + off).astype(np.float32))
                     seek[b] += adv
                     for sg in segs:
                         out[b].extend(sg)
         if trace is not None:
             trace["langs"] = langs
+        self.last_token_ts, self.last_token_ts_raw = ts_out, ts_raw
         return out
