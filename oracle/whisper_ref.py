@@ -312,11 +312,13 @@ class WhisperRef:
         return time[jumps].tolist()
 
     def alignment_matrix(self, cross: List[list], alignment_heads, row: int, n_prompt: int, num_frames: int,
-                         median_width: int = 7) -> torch.Tensor:
+                         median_width: int = 7, pre_crop: Optional[int] = None) -> torch.Tensor:
         """The per-row branch of _extract_token_timestamps (:352-365): stack the alignment (layer, head) pairs, crop to
         num_frames // 2 encoder positions, drop the prompt positions, standardise over the token axis (population
         std), median-filter along frames, average the heads.  -> fp32 [tokens, frames]."""
         w = torch.stack([torch.cat(cross[l], dim=2)[row, h] for l, h in alignment_heads])      # [heads, T, S]
+        if pre_crop is not None:
+            w = w[..., : pre_crop // 2]      # the whole-batch crop taken when every row has the same num_frames (:316-323)
         w = w[..., : num_frames // 2][:, n_prompt:, :]
         std = torch.std(w, dim=-2, keepdim=True, unbiased=False)
         mean = torch.mean(w, dim=-2, keepdim=True)
@@ -332,8 +334,11 @@ class WhisperRef:
         out = torch.zeros(n_rows, T + 1, dtype=torch.float32)
         if T - n_prompt <= 0:
             return out
+        # num_frames is a tensor here: when all rows agree the batch is cropped once up front AND per row again
+        # (:322-323, :354) — the same thing for a non-negative count, a double crop from the end for a negative one
+        pre = int(num_frames[0]) if len(set(int(f) for f in num_frames)) == 1 else None
         for b in range(n_rows):
-            m = self.alignment_matrix(cross, alignment_heads, b, n_prompt, int(num_frames[b]), median_width)
+            m = self.alignment_matrix(cross, alignment_heads, b, n_prompt, int(num_frames[b]), median_width, pre)
             frames = self.dtw_token_frames(-m.double().numpy())
             jt = torch.tensor([f * time_precision for f in frames], dtype=torch.float64)
             out[b] = torch.cat([torch.zeros(n_prompt, dtype=torch.float64), jt, jt[-1:]]).to(torch.float32)

@@ -132,6 +132,50 @@ def test_beam_search_oracle_vs_hf_golden(variant):
         assert row == want, f"row {b}"
 
 
+@pytest.mark.parametrize("variant", ["decisive", "varied"])
+def test_token_timestamps_oracle_vs_hf_golden(variant):
+    """generate(return_token_timestamps=True, return_segments=True, attention_mask=...) — SURVEY.md §8f rank 4: the
+    oracle's eager cross-attention tap, per-row crop to (num_frames - seek) // 2 frames (python slice rules, negative
+    counts included), population-std normalisation, median filter, head mean, float32-cost DTW and jump extraction
+    give the SAME token ids and the same fp32 time for every token as transformers, for both the padded
+    `token_timestamps` output and the per-segment values the ASR pipeline reads, across seek iterations."""
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "word_tiny.json")))
+    _, fb = _clips_feats()
+    dims = R.WhisperDims(**helpers.TINY)
+    ref = R.WhisperRef(dims, helpers.variant_state_dict(dims, variant))
+    ts = {}
+    got = ref.generate(fb, alignment_heads=gold["alignment_heads"], num_frames=gold["num_frames"], token_ts=ts)
+    g = gold[f"{variant}_generate"]
+    for b, row in enumerate(got):
+        assert row == g["segment_tokens"][b], f"row {b}"
+        np.testing.assert_array_equal(np.asarray(ts["segments"][b], dtype=np.float32),
+                                      np.asarray(g["segment_token_timestamps"][b], dtype=np.float32))
+        np.testing.assert_array_equal(np.asarray(ts["sequences"][b], dtype=np.float32),
+                                      np.asarray(g["token_timestamps"][b][:len(row)], dtype=np.float32))
+
+
+def test_dtw_oracle_and_native_match_transformers_function():
+    """The oracle's anti-diagonal DTW and the C library's tw_dtw_token_frames against transformers'
+    _dynamic_time_warping + jump extraction on random matrices, tie-heavy integer matrices included."""
+    import ctypes as C
+    from transformers.models.whisper.generation_whisper import _dynamic_time_warping
+    from turbo_whisper_workspace_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    for trial in range(60):
+        n, m = int(rng.integers(1, 40)), int(rng.integers(1, 80))
+        mat = (rng.integers(-2, 3, size=(n, m)) if trial % 4 == 0 else rng.standard_normal((n, m))).astype(np.float32)
+        ld = m + int(rng.integers(0, 5))
+        buf = np.zeros((n, ld), dtype=np.float32)
+        buf[:, :m] = mat
+        out = np.empty(n, dtype=np.int32)
+        assert lib.tw_dtw_token_frames(buf.ctypes.data_as(C.c_void_p), ld, n, m, out.ctypes.data_as(C.c_void_p)) == 0
+        ti, tj = _dynamic_time_warping(-mat.astype(np.float64))
+        want = tj[np.pad(np.diff(ti), (1, 0), constant_values=1).astype(bool)].tolist()
+        assert out.tolist() == want and R.WhisperRef.dtw_token_frames(-mat.astype(np.float64)) == want, trial
+    assert lib.tw_dtw_token_frames(None, 4, 2, 4, None) != 0 and b"tw_dtw_token_frames" in lib.tw_last_error()
+
+
 def test_retrieve_segment_cases():
     TB = R.TIMESTAMP_BEGIN
     f = R.WhisperRef.retrieve_segment

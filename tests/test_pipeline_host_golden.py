@@ -16,6 +16,7 @@ from oracle import whisper_ref as R
 from turbo_whisper_workspace_b200.config import WhisperDims
 from turbo_whisper_workspace_b200.pipeline import B200WhisperPipeline
 
+WORD_HEADS = [[0, 1], [1, 0], [1, 3]]      # tests/golden/make_golden_word.py
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
@@ -25,9 +26,20 @@ class OracleScheduler:
         self.ref = R.WhisperRef(rd, helpers.variant_state_dict(rd, variant))
         self.last_stats = {}
 
-    def run(self, clips, task="transcribe", language=None, return_timestamps=True):
+    def run(self, clips, task="transcribe", language=None, return_timestamps=True, token_timestamps=False, group=None):
         feats = torch.stack([torch.from_numpy(L.log_mel(c)) for c in clips])
-        return self.ref.generate(feats, task=task, return_timestamps=return_timestamps)
+        if not token_timestamps:
+            return self.ref.generate(feats, task=task, return_timestamps=return_timestamps)
+        # word timestamps: one generate call per HF batch of `group` consecutive windows; num_frames = the feature
+        # extractor's attention-mask sum
+        rows = []
+        for g0 in range(0, len(clips), group):
+            sub = clips[g0:g0 + group]
+            nf = [min(3000, -(-len(c) // 160)) for c in sub]
+            ts = {}
+            ids = self.ref.generate(feats[g0:g0 + group], task=task, alignment_heads=WORD_HEADS, num_frames=nf, token_ts=ts)
+            rows += [(ids[b], ts["segments"][b]) for b in range(len(sub))]
+        return rows
 
 
 @pytest.fixture(scope="module")
@@ -68,3 +80,21 @@ def test_host_pipeline_without_timestamps_matches_hf_golden(wav, variant, cl, st
     r = pipe(wav, chunk_length_s=cl, stride_length_s=st, batch_size=bs, generate_kwargs={"task": "transcribe"})
     g = gold[f"{variant}_{cl}_{st}_{bs}"]
     assert sorted(r.keys()) == g["keys"] and r["text"] == g["text"]
+
+
+@pytest.mark.parametrize("variant", ["varied", "decisive"])
+def test_host_pipeline_word_timestamps_match_hf_golden(wav, variant):
+    """return_timestamps="word": per-token times of the oracle (pinned time-exact to generate(return_token_timestamps=
+    True) in tests/test_oracle_golden.py) through the pipeline's stride plumbing and the word-level _decode_asr
+    restatement -> the {"text", "chunks"} of the transformers pipeline, chunked (30 / 5) and for a single short clip."""
+    gold = json.load(open(os.path.join(GOLD, "word_tiny.json")))
+    pipe = B200WhisperPipeline(None, WhisperDims(**helpers.TINY), helpers.build_tokenizer(),
+                               scheduler=OracleScheduler(variant))
+    r = pipe(wav, chunk_length_s=30, stride_length_s=5, batch_size=24, generate_kwargs={"task": "transcribe"},
+             return_timestamps="word")
+    assert _norm(r) == gold[f"{variant}_30_5_24"]
+    r = pipe(helpers.synth_clip(2, seconds=11.3, kind="mod"), generate_kwargs={"task": "transcribe"},
+             return_timestamps="word")
+    assert _norm(r) == gold[f"{variant}_single"]
+    with pytest.raises(NotImplementedError):
+        pipe(wav, chunk_length_s=30, generate_kwargs={"num_beams": 5}, return_timestamps="word")

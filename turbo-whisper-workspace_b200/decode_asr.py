@@ -9,7 +9,10 @@ The timestamp / stride state machine and the overlap merge run in the C library 
 csrc/decode_asr.cpp); the tokenizer is only read once, at construction, for its vocabulary: every id is turned into
 its byte string (byte-level BPE: each vocabulary character stands for one byte, the GPT-2 table), so a chunk's text is
 ``b"".join(...)`` decoded as UTF-8 with replacement — no tokenizer call per chunk.
-``return_timestamps="word"`` is not covered (it needs cross-attention weights the engine does not export yet).
+``return_timestamps="word"`` (records also carry ``token_timestamps``, one time per id, from the engine's alignment
+path) is host Python below: the same state machine with per-token (start, end) pairs, the timestamp-aware overlap
+merge, and the grouping of tokens into words (_collate_word_timestamps / _combine_tokens_into_words / _split_tokens_on_*
+/ _merge_punctuations, $TF/models/whisper/tokenization_whisper.py:1153-1408).
 """
 from __future__ import annotations
 
@@ -98,6 +101,8 @@ class AsrDecoder:
             else:
                 lang_idx.append(len(self.languages))
                 self.languages.append(name)
+        self.eos_token_id = int(tokenizer.eos_token_id) if getattr(tokenizer, "eos_token_id", None) is not None else self.decoder_start_token_id - 1
+        self.default_language = getattr(tokenizer, "language", None)     # word splitting falls back to it, then to english
         self._special = np.asarray(special, dtype=np.int32)
         self._special_lang = np.asarray(lang_idx, dtype=np.int32)
         self.last_flags = 0
@@ -109,7 +114,7 @@ class AsrDecoder:
     def __call__(self, model_outputs: Sequence[Dict[str, Any]], *, return_timestamps, return_language=None,
                  time_precision: float) -> Tuple[str, Dict[str, Any]]:
         if return_timestamps == "word":
-            raise NotImplementedError("word timestamps are not implemented by the native _decode_asr")
+            return self._decode_words(model_outputs, return_language=return_language, time_precision=time_precision)
         lib = _lib.load()
         wins = (AsrWindow * max(1, len(model_outputs)))()
         keep = []
@@ -156,3 +161,204 @@ class AsrDecoder:
         text = "".join(ch["text"] for ch in chunks)
         optional = {"chunks": chunks} if (return_timestamps or return_language) else {}
         return text, optional
+
+    # ------------------------------------------------------------------------------------------------ word mode
+    _NO_SPACE_LANGUAGES = {"chinese", "japanese", "thai", "lao", "myanmar", "cantonese"}
+    _PREPEND = "\"'“¡¿([{-"
+    _APPEND = "\"'.。,，!！?？:：”)]}、"
+    _PUNCT = "!\"#$%&'()*+,-./:;<=>?@[\\]^_`{|}~"
+
+    def _split_on_unicode(self, tokens: Sequence[int]):
+        """_split_tokens_on_unicode (:1315-1343): cut wherever the bytes so far decode to complete code points."""
+        full = self.text_of(tokens)
+        rep = "\ufffd"
+        words, word_tokens, indices = [], [], []
+        cur_t, cur_i, off = [], [], 0
+        for i, t in enumerate(tokens):
+            cur_t.append(t)
+            cur_i.append(i)
+            dec = self.text_of(cur_t)
+            if rep not in dec or full[off + dec.index(rep)] == rep:
+                words.append(dec)
+                word_tokens.append(cur_t)
+                indices.append(cur_i)
+                cur_t, cur_i = [], []
+                off += len(dec)
+        return words, word_tokens, indices
+
+    def _split_on_spaces(self, tokens: Sequence[int]):
+        """_split_tokens_on_spaces (:1346-1367)."""
+        sub, sub_t, sub_i = self._split_on_unicode(tokens)
+        words, word_tokens, indices = [], [], []
+        for w, t, ix in zip(sub, sub_t, sub_i):
+            special = t[0] >= self.eos_token_id
+            if special or w.startswith(" ") or (w.strip() in self._PUNCT) or not words:
+                words.append(w)
+                word_tokens.append(t)
+                indices.append(ix)
+            else:
+                words[-1] = words[-1] + w
+                word_tokens[-1].extend(t)
+                indices[-1].extend(ix)
+        return words, word_tokens, indices
+
+    def _merge_punctuations(self, words, tokens, indices):
+        """_merge_punctuations (:1370-1405), in place."""
+        i, j = len(words) - 2, len(words) - 1
+        while i >= 0:
+            if words[i].startswith(" ") and words[i].strip() in self._PREPEND:
+                words[j] = words[i] + words[j]
+                tokens[j] = tokens[i] + tokens[j]
+                indices[j] = indices[i] + indices[j]
+                words[i], tokens[i], indices[i] = "", [], []
+            else:
+                j = i
+            i -= 1
+        i, j = 0, 1
+        while j < len(words):
+            if not words[i].endswith(" ") and words[j] in self._APPEND:
+                words[i] += words[j]
+                tokens[i] += tokens[j]
+                indices[i] += indices[j]
+                words[j], tokens[j], indices[j] = "", [], []
+            else:
+                i = j
+            j += 1
+        words[:] = [w for w in words if w]
+        tokens[:] = [t for t in tokens if t]
+        indices[:] = [ix for ix in indices if ix]
+
+    def _collate_words(self, tokens, token_times, language, return_language):
+        """_collate_word_timestamps (:1273-1286)."""
+        lang = language if language is not None else (self.default_language or "english")
+        split = self._split_on_unicode if lang in self._NO_SPACE_LANGUAGES else self._split_on_spaces
+        words, word_tokens, indices = split(tokens)
+        self._merge_punctuations(words, word_tokens, indices)
+        extra = {"language": language} if return_language else {}
+        return [{"text": w, "timestamp": (token_times[ix[0]][0], token_times[ix[-1]][1]), **extra}
+                for w, ix in zip(words, indices)]
+
+    @staticmethod
+    def _merge_with_times(sequences, time_sequences):
+        """_find_longest_common_sequence with token_timestamp_sequences (:1153-1270): a position only counts as a
+        match when the ids agree AND the left token's (start, end) pair is <= the right token's."""
+        left, left_t = sequences[0], time_sequences[0]
+        total, total_t = [], []
+        for k, right in enumerate(sequences[1:]):
+            right_t = time_sequences[k + 1]
+            ll, rl = len(left), len(right)
+            best, best_idx = 0.0, (ll, ll, 0, 0)
+            for i in range(1, ll + rl):
+                ls, le = max(0, ll - i), min(ll, ll + rl - i)
+                rs, re_ = max(0, i - ll), min(rl, i)
+                matches = 0
+                for d in range(le - ls):
+                    if left[ls + d] == right[rs + d] and left_t[ls + d] <= right_t[rs + d]:
+                        matches += 1
+                matching = matches / i + i / 10000.0
+                if matches > 1 and matching > best:
+                    best, best_idx = matching, (ls, le, rs, re_)
+            ls, le, rs, re_ = best_idx
+            lm, rm = (le + ls) // 2, (re_ + rs) // 2
+            total.extend(left[:lm])
+            total_t.extend(left_t[:lm])
+            left, left_t = right[rm:], right_t[rm:]
+        total.extend(left)
+        total_t.extend(left_t)
+        return total, total_t
+
+    def _decode_words(self, model_outputs, *, return_language, time_precision):
+        """tokenizer._decode_asr(..., return_timestamps="word") (:901-1150)."""
+        tb = self.timestamp_begin
+        special = {int(i): int(l) for i, l in zip(self._special, self._special_lang)}
+        last_language = None
+        new_chunk = lambda: {"language": last_language, "timestamp": [None, None], "text": ""}
+        chunks, chunk = [], new_chunk()
+        time_offset = 0.0
+        previous_tokens, previous_times = [], []
+        skip = False
+        right_stride_start = None
+        self.last_flags = 0
+
+        def close(cur_chunk):
+            toks, times = self._merge_with_times(previous_tokens, previous_times)
+            cur_chunk["text"] = self.text_of(toks)
+            cur_chunk["words"] = self._collate_words(toks, times, last_language, return_language)
+            chunks.append(cur_chunk)
+
+        for output in model_outputs:
+            toks0 = output["tokens"][0]
+            token_ids = [int(t) for t in (toks0.tolist() if hasattr(toks0, "tolist") else toks0)]
+            if token_ids and token_ids[0] == self.prompt_token_id:      # _strip_prompt (:725-741)
+                token_ids = (token_ids[token_ids.index(self.decoder_start_token_id):]
+                             if self.decoder_start_token_id in token_ids else [])
+            tt0 = output["token_timestamps"][0]
+            token_times = [float(x) for x in (tt0.tolist() if hasattr(tt0, "tolist") else tt0)]
+            last_timestamp, first_timestamp = None, tb
+            cur_max, prev_len, penultimate = 0.0, 0.0, 0.0
+            if "stride" in output:
+                chunk_len, stride_left, stride_right = output["stride"]
+                time_offset -= stride_left
+                right_stride_start = chunk_len - stride_right
+                if stride_left:
+                    first_timestamp = stride_left / time_precision + tb
+                if stride_right:
+                    for token in reversed(token_ids):
+                        if token >= tb:
+                            if last_timestamp is not None and (token - tb) * time_precision < right_stride_start:
+                                break
+                            last_timestamp = token
+            current_tokens, current_times = [], []
+            for i, token in enumerate(token_ids):
+                if token in special:
+                    li = special[token]
+                    if li >= 0:
+                        chunk["language"] = self.languages[li]
+                        last_language = self.languages[li]
+                elif token >= tb:
+                    timestamp = float((token - tb) * time_precision)
+                    if timestamp < cur_max:
+                        single_ending = i >= 2 and not (token_ids[i - 1] >= tb and token_ids[i - 2] >= tb)
+                        if single_ending:
+                            prev_len += time_precision * self.segment_size
+                        else:
+                            cur_max = penultimate
+                            prev_len += penultimate
+                    penultimate = cur_max
+                    cur_max = timestamp
+                    time = round((token - tb) * time_precision + time_offset + prev_len, 2)
+                    if last_timestamp and token >= last_timestamp:
+                        skip = True
+                    elif skip or (previous_tokens and token < first_timestamp):
+                        skip = False
+                    elif chunk["timestamp"][0] is None:
+                        chunk["timestamp"][0] = time
+                    elif time != chunk["timestamp"][0]:
+                        chunk["timestamp"][1] = time
+                        previous_tokens.append(current_tokens)
+                        previous_times.append(current_times)
+                        close(chunk)
+                        previous_tokens, current_tokens = [], []
+                        previous_times, current_times = [], []
+                        chunk = new_chunk()
+                else:
+                    current_tokens.append(token)
+                    start = round(0.0 + time_offset, 2) if i == 0 else round(token_times[i - 1] + time_offset, 2)
+                    current_times.append((start, round(token_times[i] + time_offset, 2)))
+            if "stride" in output:
+                time_offset += chunk_len - stride_right
+            if current_tokens:
+                previous_tokens.append(current_tokens)
+                previous_times.append(current_times)
+            elif not any(p for p in previous_tokens):
+                chunk = new_chunk()
+                previous_tokens, current_tokens = [], []
+                previous_times, current_times = [], []
+        if previous_tokens:
+            self.last_flags |= 1
+            close(chunk)
+        text = "".join(c["text"] for c in chunks)
+        words = []
+        for c in chunks:
+            words.extend(c["words"])
+        return text, {"chunks": words}

@@ -742,8 +742,12 @@ class WhisperEngine:
                 tok_frames = None
                 if token_timestamps:
                     # weights[..., : (num_frames - seek) // 2] (_postprocess_outputs :1146-1151, :354): python slice rules
+                    # and, when every active row has the same value, cropped once more up front (:322-323) — a no-op for
+                    # non-negative counts, a second crop from the end for negative ones
                     S = self.dims.max_source_positions
-                    keep = [len(range(S)[: (int(num_frames[b]) - seek[b]) // 2]) for b in rows]
+                    left = [int(num_frames[b]) - seek[b] for b in rows]
+                    twice = len(set(left)) == 1
+                    keep = [len((range(S)[: v // 2] if twice else range(S))[: v // 2]) for v in left]
                     tok_frames = self.token_frames(n, toks, P, keep)
                 if trace is not None:
                     trace.setdefault("iterations", []).append({"rows": list(rows), "seek": [seek[b] for b in rows],

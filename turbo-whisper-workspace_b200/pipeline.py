@@ -215,8 +215,9 @@ class B200WhisperPipeline:
         task = generate_kwargs.pop("task", None) or "transcribe"
         language = generate_kwargs.pop("language", None)
         num_beams = int(generate_kwargs.pop("num_beams", None) or self.num_beams or 1)
-        if return_timestamps == "word":
-            raise NotImplementedError('return_timestamps="word" is not implemented by the B200 engine')
+        if return_timestamps == "word" and num_beams > 1:
+            raise NotImplementedError('return_timestamps="word" with beam search is not implemented by the B200 engine; '
+                                      'pass generate_kwargs={"num_beams": 1}')
         if return_timestamps == "char":
             raise ValueError("Whisper cannot return `char` timestamps, only word level or segment level timestamps. "
                              "Use `return_timestamps='word'` or `return_timestamps=True` respectively.")
@@ -252,12 +253,21 @@ class B200WhisperPipeline:
             run_kw["return_timestamps"] = False
         if num_beams > 1:
             run_kw["num_beams"] = num_beams      # beam search: every window occupies num_beams decode rows
+        bs = max(1, int(batch_size or 1))
+        token_times = None
+        if return_timestamps == "word":
+            # generate(return_token_timestamps=True, return_segments=True): the engine taps the alignment heads'
+            # cross-attention; micro-batches follow HF's batches of `batch_size` consecutive windows (capped by the
+            # engine's max_batch) because a row's DTW spans the decode steps of its batch's longest row
+            run_kw.update(token_timestamps=True, group=bs)
         token_rows = self.scheduler.run(clips, task=task, language=language, **run_kw)
+        if return_timestamps == "word":
+            token_times = [np.asarray(t, dtype=np.float32) for _, t in token_rows]
+            token_rows = [r for r, _ in token_rows]
         self.last_stats = dict(self.scheduler.last_stats, windows=len(windows), audio_seconds=audio.shape[0] / sr)
 
         # HF batches `batch_size` consecutive windows per generate call and right-pads each batch to its
         # longest row with pad_token_id; _decode_asr ignores the padding, so the grouping only affects shapes.
-        bs = max(1, int(batch_size or 1))
         pad = self.generation.pad_token_id
         model_outputs = []
         for g0 in range(0, len(windows), bs):
@@ -267,6 +277,8 @@ class B200WhisperPipeline:
                 arr = np.full((1, width), pad, dtype=np.int64)
                 arr[0, :len(r)] = r
                 item: Dict[str, Any] = {"tokens": arr}
+                if token_times is not None:
+                    item["token_timestamps"] = token_times[g0 + i][None, :]
                 if with_stride:
                     ln, sl, srr = windows[g0 + i][2]
                     item["stride"] = (ln / sr, sl / sr, srr / sr)

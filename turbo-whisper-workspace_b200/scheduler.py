@@ -34,7 +34,7 @@ def partition(n_items: int, n_workers: int) -> List[Tuple[int, int]]:
     return out
 
 
-def _extra(return_timestamps: bool, num_beams: int) -> Dict[str, Any]:
+def _extra(return_timestamps: bool, num_beams: int, token_timestamps: bool = False) -> Dict[str, Any]:
     """Keyword arguments beyond (task, language), passed only when they differ from the defaults so that simple
     engine stand-ins keep working."""
     kw: Dict[str, Any] = {}
@@ -42,16 +42,33 @@ def _extra(return_timestamps: bool, num_beams: int) -> Dict[str, Any]:
         kw["return_timestamps"] = False
     if num_beams > 1:
         kw["num_beams"] = int(num_beams)
+    if token_timestamps:
+        kw["token_timestamps"] = True
     return kw
 
 
+def microbatch_size(max_batch: int, num_beams: int = 1, group: Optional[int] = None) -> int:
+    """Windows per engine call: every window occupies num_beams decode rows; ``group`` (word timestamps) caps it at
+    the HF pipeline's batch_size so that a micro-batch is exactly one of HF's generate batches."""
+    mb = max(1, max_batch // max(1, num_beams))
+    return mb if not group else max(1, min(mb, int(group)))
+
+
+def group_ranges(n_items: int, n_workers: int, mb: int) -> List[Tuple[int, int]]:
+    """:func:`partition` over whole micro-batches of ``mb`` consecutive items (micro-batch k = items k*mb ..), so the
+    micro-batch boundaries do not depend on the number of workers."""
+    n_groups = (n_items + mb - 1) // mb
+    return [(min(n_items, a * mb), min(n_items, b * mb)) for a, b in partition(n_groups, n_workers)]
+
+
 def run_in_microbatches(engine, clips: Sequence[np.ndarray], task: str, language: Optional[str],
-                        return_timestamps: bool = True, num_beams: int = 1) -> List[List[int]]:
-    rows: List[List[int]] = []
-    mb = max(1, engine.max_batch // max(1, num_beams))      # every window occupies num_beams decode rows
+                        return_timestamps: bool = True, num_beams: int = 1, token_timestamps: bool = False,
+                        group: Optional[int] = None) -> List[Any]:
+    rows: List[Any] = []
+    mb = microbatch_size(engine.max_batch, num_beams, group)
     for i in range(0, len(clips), mb):
         rows.extend(engine.generate_from_pcm(clips[i:i + mb], task=task, language=language,
-                                             **_extra(return_timestamps, num_beams)))
+                                             **_extra(return_timestamps, num_beams, token_timestamps)))
     return rows
 
 
@@ -85,17 +102,22 @@ class WindowScheduler:
         return [e for ctxs in self.engines for e in ctxs]
 
     def run(self, clips: Sequence[np.ndarray], task: str = "transcribe", language: Optional[str] = None,
-            return_timestamps: bool = True, num_beams: int = 1) -> List[List[int]]:
+            return_timestamps: bool = True, num_beams: int = 1, token_timestamps: bool = False,
+            group: Optional[int] = None) -> List[Any]:
+        """Token rows per window, in order.  ``token_timestamps``: every row is ``(ids, times)`` (word timestamps);
+        ``group`` = the HF pipeline's batch_size: micro-batches then are HF's generate batches (the per-token times of
+        a row depend on the longest row of its batch, $TF/models/whisper/generation_whisper.py:241-381)."""
         t0 = time.perf_counter()
         n = len(clips)
-        ranges = partition(n, len(self.devices))
+        mb0 = microbatch_size(self.engines[0][0].max_batch, num_beams, group) if (group and self.engines) else None
+        ranges = group_ranges(n, len(self.devices), mb0) if mb0 else partition(n, len(self.devices))
         results: List[Optional[List[int]]] = [None] * n
         errors: List[BaseException] = []
         lock = threading.Lock()
         threads = []
         for di, (s, e) in enumerate(ranges):
             ctxs = self.engines[di]
-            mb = max(1, ctxs[0].max_batch // max(1, num_beams))   # every window occupies num_beams decode rows
+            mb = mb0 or microbatch_size(ctxs[0].max_batch, num_beams)
             queue = [(i, min(i + mb, e)) for i in range(s, e, mb)]   # micro-batches of this device, in order
 
             def work(engine, queue=queue):
@@ -106,7 +128,7 @@ class WindowScheduler:
                                 return
                             a, b = queue.pop(0)
                         rows = engine.generate_from_pcm(clips[a:b], task=task, language=language,
-                                                        **_extra(return_timestamps, num_beams))
+                                                        **_extra(return_timestamps, num_beams, token_timestamps))
                         results[a:b] = rows
                 except BaseException as ex:  # surfaced on the calling thread
                     with lock:
@@ -139,13 +161,16 @@ class DistributedWindowScheduler:
         self.engine, self.rank, self.world_size, self.group = engine, rank, world_size, group
         self.last_stats: Dict[str, Any] = {}
 
-    def local_range(self, n: int) -> Tuple[int, int]:
-        return partition(n, self.world_size)[self.rank]
+    def local_range(self, n: int, mb: Optional[int] = None) -> Tuple[int, int]:
+        return (group_ranges(n, self.world_size, mb) if mb else partition(n, self.world_size))[self.rank]
 
     def run_local(self, clips: Sequence[np.ndarray], task: str = "transcribe", language: Optional[str] = None,
-                  return_timestamps: bool = True, num_beams: int = 1) -> List[List[int]]:
-        s, e = self.local_range(len(clips))
-        return run_in_microbatches(self.engine, clips[s:e], task, language, return_timestamps, num_beams) if e > s else []
+                  return_timestamps: bool = True, num_beams: int = 1, token_timestamps: bool = False,
+                  group: Optional[int] = None) -> List[Any]:
+        mb = microbatch_size(self.engine.max_batch, num_beams, group) if group else None
+        s, e = self.local_range(len(clips), mb)
+        return run_in_microbatches(self.engine, clips[s:e], task, language, return_timestamps, num_beams,
+                                   token_timestamps, group) if e > s else []
 
     def gather(self, local_rows: List[List[int]]) -> List[List[int]]:
         if self.world_size == 1:
@@ -159,5 +184,6 @@ class DistributedWindowScheduler:
         return rows
 
     def run(self, clips: Sequence[np.ndarray], task: str = "transcribe", language: Optional[str] = None,
-            return_timestamps: bool = True, num_beams: int = 1) -> List[List[int]]:
-        return self.gather(self.run_local(clips, task, language, return_timestamps, num_beams))
+            return_timestamps: bool = True, num_beams: int = 1, token_timestamps: bool = False,
+            group: Optional[int] = None) -> List[Any]:
+        return self.gather(self.run_local(clips, task, language, return_timestamps, num_beams, token_timestamps, group))
