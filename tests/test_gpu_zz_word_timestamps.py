@@ -135,3 +135,76 @@ def test_token_timestamps_of_the_seek_loop(setup, cuda_device):
     close = float((absdiff <= TS_CLOSE_S).mean())
     print(f"[word] share of token times within {TS_CLOSE_S} s of the oracle: {close:.3f}")
     assert close >= TS_CLOSE_FRAC and equal >= 0.85 * total
+
+
+def test_pipeline_word_timestamps(cuda_device, tmp_path):
+    """B200WhisperPipeline(..., return_timestamps="word") on the 71.3 s fixture file (chunk 30 / stride 5, two engine
+    contexts).  (1) plumbing, exact: the engine's own (ids, times) rows replayed through transformers'
+    tokenizer._decode_asr give the pipeline's output dict; (2) "decisive" model: a long common text prefix with the
+    transformers pipeline golden.  Word TIMES are compared with the HF-exact oracle at the engine level (previous
+    test): once a greedy path leaves HF's (near-tie picks under bf16), every later DTW row of that window changes, so
+    pipeline-level times are only checked through (1)."""
+    from oracle import whisper_ref as R
+    from turbo_whisper_workspace_b200.config import GenerationSettings, WhisperDims
+    from turbo_whisper_workspace_b200.pipeline import B200WhisperPipeline, chunk_windows
+    gold = json.load(open(os.path.join(HERE, "golden", "word_tiny.json")))
+    pcm = np.concatenate([helpers.synth_clip(0), helpers.synth_clip(1, kind="mod"),
+                          helpers.synth_clip(2, seconds=11.3, kind="mod")])
+    path = tmp_path / "golden_71s.wav"
+    helpers.write_wav16(path, pcm)
+    tok = helpers.build_tokenizer()
+    kw = dict(chunk_length_s=30, stride_length_s=5, batch_size=24, generate_kwargs={"task": "transcribe"})
+    for variant in ("varied", "decisive"):
+        sd = helpers.variant_state_dict(R.WhisperDims(**helpers.TINY), variant)
+        pipe = B200WhisperPipeline(sd, WhisperDims(**helpers.TINY), tok, GenerationSettings(alignment_heads=HEADS),
+                                   devices=[cuda_device], max_batch=4, contexts_per_device=2)
+        try:
+            seen = {}
+            run = pipe.scheduler.run
+
+            def spy(clips, **k):
+                seen["rows"] = run(clips, **k)
+                return seen["rows"]
+            pipe.scheduler.run = spy
+            r = pipe(str(path), return_timestamps="word", **kw)
+            pipe.scheduler.run = run
+            assert set(r) == {"text", "chunks"} and all(set(c) == {"timestamp", "text"} for c in r["chunks"])
+            # (1) replay through transformers' _decode_asr
+            wins = chunk_windows(len(pcm), 30 * 16000, 5 * 16000, 5 * 16000)
+            assert len(wins) == len(seen["rows"])
+            width = max(len(ids) for ids, _ in seen["rows"])
+            outs = []
+            for (ids, times), (_, _, (ln, sl, sr), _) in zip(seen["rows"], wins):
+                assert len(ids) == len(times)
+                arr = np.full((1, width), 50257, dtype=np.int64)
+                arr[0, :len(ids)] = ids
+                outs.append({"tokens": arr, "token_timestamps": np.asarray([times], dtype=np.float32),
+                             "stride": (ln / 16000, sl / 16000, sr / 16000)})
+            text, opt = tok._decode_asr(outs, return_timestamps="word", return_language=None, time_precision=0.02)
+            assert r["text"] == text
+            assert [dict(c) for c in r["chunks"]] == [dict(c) for c in opt["chunks"]]
+            g = gold[f"{variant}_30_5_24"]
+            n_same = 0
+            for a, b in zip(r["chunks"], g["chunks"]):
+                if a["text"] != b["text"]:
+                    break
+                n_same += 1
+            print(f"\n[word] pipeline {variant}: {len(r['chunks'])} words, {n_same}/{len(g['chunks'])} leading words "
+                  f"identical to the transformers pipeline")
+            if variant == "decisive":
+                # as in tests/test_gpu_pipeline.py: HF's fp32 pipeline has a few near-tie picks on these windows, after
+                # which the greedy paths may legitimately part — a long common prefix and the first word's start
+                n = 0
+                for x, y in zip(r["text"], g["text"]):
+                    if x != y:
+                        break
+                    n += 1
+                print(f"[word] pipeline decisive: text identical to transformers for {n}/{len(g['text'])} characters")
+                assert n >= min(len(g["text"]), 200)
+                assert r["chunks"][0]["timestamp"][0] == g["chunks"][0]["timestamp"][0]
+            # plain segment timestamps still work on the same pipeline object afterwards (the tap is off again)
+            r2 = pipe(str(path), return_timestamps=True, **kw)
+            assert r2["chunks"] and all(set(c) == {"timestamp", "text"} for c in r2["chunks"])
+            assert pipe.scheduler.flat_engines[0]._align_on is False
+        finally:
+            pipe.close()
