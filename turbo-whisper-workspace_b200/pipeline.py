@@ -201,6 +201,7 @@ class B200WhisperPipeline:
         """Build from a ``transformers.WhisperForConditionalGeneration`` (weights, config, generation_config)."""
         dims = WhisperDims.from_hf_config(model.config)
         gen = GenerationSettings.from_hf(model.generation_config)
+        gen.median_filter_width = int(getattr(model.config, "median_filter_width", 7))
         return cls(model.state_dict(), dims, tokenizer, gen, devices, max_batch, contexts_per_device=contexts_per_device)
 
     # -------------------------------------------------------------------------------- call
