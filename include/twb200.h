@@ -216,6 +216,10 @@ int tw_align_matrix(const float* probs, const int32_t* n_frames_dev, int32_t bat
 /* host: dynamic time warping over -matrix (fp32 [n_tok][ld], n_frames columns used) with HF's float32 cost table and
  * tie rules; token_frame[t] = first encoder frame of token t's run on the warping path (timestamp = frame * 0.02 s). */
 int tw_dtw_token_frames(const float* matrix, int64_t ld, int32_t n_tok, int32_t n_frames, int32_t* token_frame);
+/* the same for `batch` independent windows (matrix b at matrices + b*batch_stride, n_frames[b] columns used, 0 allowed:
+ * every token then gets frame -1 as in HF) on up to n_threads host threads; token_frames: int32 [batch][n_tok]. */
+int tw_dtw_token_frames_batch(const float* matrices, int64_t batch_stride, int64_t ld, int32_t batch, int32_t n_tok,
+                              const int32_t* n_frames, int32_t* token_frames, int32_t n_threads);
 
 /* ---- audio ingest: format conversion + channel down-mix + polyphase windowed-sinc resampling ---------------
  * Replaces torchaudio.functional.resample (sinc_interp_hann, lowpass_filter_width 6, rolloff 0.99) in the pipeline's

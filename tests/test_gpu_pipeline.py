@@ -104,8 +104,10 @@ def test_pipeline_short_clip_and_errors(pipes):
         p(pcm, chunk_length_s=10, stride_length_s=6, return_timestamps=True)
     with pytest.raises(ValueError):
         p(pcm, return_timestamps=True, generate_kwargs={"task": "summarize"})
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError, match="alignment_heads"):     # HF's error for a generation config without them
         p(pcm, return_timestamps="word")
+    with pytest.raises(NotImplementedError):
+        p(pcm, return_timestamps="word", generate_kwargs={"num_beams": 2})
     r2 = p(pcm)                      # HF default: no timestamps -> {"text"} only
     assert set(r2) == {"text"} and isinstance(r2["text"], str)
     # beam search through the pipeline: every window occupies num_beams decode rows (4-row engine: 2 windows x 2 beams)

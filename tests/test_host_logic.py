@@ -81,6 +81,31 @@ def test_window_scheduler_orders_and_microbatches():
     assert S.WindowScheduler(None, None, None, devices=["d0"], engine_factory=lambda d: FakeEngine(d)).run([]) == []
 
 
+def test_word_mode_microbatches_follow_hf_batches():
+    """return_timestamps="word": micro-batches are the HF pipeline's batches of `batch_size` consecutive windows
+    (capped at the engine's rows) whatever the number of devices / contexts, and rows come back as (ids, times)."""
+    class WordEngine(FakeEngine):
+        def generate_from_pcm(self, clips, task="transcribe", language=None, token_timestamps=False):
+            assert token_timestamps and len(clips) <= self.max_batch
+            self.calls.append([int(round(float(c[0]) * 1000)) for c in clips])
+            return [([len(c) % 1000], [0.5 * len(clips)]) for c in clips]
+    clips = [np.full(100 + i, i / 1000.0, dtype=np.float32) for i in range(23)]
+    assert S.group_ranges(23, 3, 4) == [(0, 8), (8, 16), (16, 23)] and S.group_ranges(3, 4, 24)[0] == (0, 3)
+    assert S.microbatch_size(32, 1, 24) == 24 and S.microbatch_size(4, 1, 24) == 4 and S.microbatch_size(32, 5) == 6
+    for devices, ctxs in ((["d0"], 1), (["d0", "d1", "d2"], 1), (["d0", "d1"], 2)):
+        sch = S.WindowScheduler(None, None, None, devices=devices, engine_factory=lambda d: WordEngine(d, 8),
+                                contexts_per_device=ctxs)
+        rows = sch.run(clips, token_timestamps=True, group=5)
+        assert [r[0] for r in rows] == [[(100 + i) % 1000] for i in range(23)]
+        batches = sorted(b for e in sch.flat_engines for b in e.calls)
+        assert batches == [list(range(k, min(k + 5, 23))) for k in range(0, 23, 5)]
+        # the per-batch value (here: the batch size) reaches every row of that batch
+        assert [r[1] for r in rows] == [[2.5]] * 20 + [[1.5]] * 3
+    d = S.DistributedWindowScheduler(WordEngine("r1", 8), rank=1, world_size=2)
+    assert d.local_range(23, 5) == (15, 23) and [r[0] for r in d.run_local(clips, token_timestamps=True, group=5)] == \
+        [[(100 + i) % 1000] for i in range(15, 23)]
+
+
 def test_window_scheduler_propagates_worker_errors():
     class Boom(FakeEngine):
         def generate_from_pcm(self, clips, **kw):

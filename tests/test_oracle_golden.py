@@ -174,6 +174,16 @@ def test_dtw_oracle_and_native_match_transformers_function():
         want = tj[np.pad(np.diff(ti), (1, 0), constant_values=1).astype(bool)].tolist()
         assert out.tolist() == want and R.WhisperRef.dtw_token_frames(-mat.astype(np.float64)) == want, trial
     assert lib.tw_dtw_token_frames(None, 4, 2, 4, None) != 0 and b"tw_dtw_token_frames" in lib.tw_last_error()
+    # the threaded batch entry point: same frames as the single-window call, -1 everywhere for an empty frame axis
+    B, T, S, n = 5, 12, 40, 9
+    mats = rng.standard_normal((B, T, S)).astype(np.float32)
+    nf = np.array([40, 0, 17, 1, 40], dtype=np.int32)
+    got = np.empty((B, n), dtype=np.int32)
+    assert lib.tw_dtw_token_frames_batch(mats.ctypes.data_as(C.c_void_p), T * S, S, B, n, nf.ctypes.data_as(C.c_void_p),
+                                         got.ctypes.data_as(C.c_void_p), 3) == 0
+    for b in range(B):
+        want = [-1] * n if nf[b] == 0 else R.WhisperRef.dtw_token_frames(-mats[b, :n, :nf[b]].astype(np.float64))
+        assert got[b].tolist() == want, b
 
 
 def test_retrieve_segment_cases():

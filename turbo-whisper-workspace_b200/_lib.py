@@ -72,6 +72,7 @@ SIGNATURES = {
     "tw_align_matrix": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                                   c_void_p, c_void_p, c_void_p]),
     "tw_dtw_token_frames": (C.c_int, [c_void_p, c_int64, c_int32, c_int32, c_void_p]),
+    "tw_dtw_token_frames_batch": (C.c_int, [c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_int32]),
     # host-only: (tw_asr_window*, n, tw_asr_config*, out_tokens, cap, offsets, t0, t1, lang, max_chunks, n_chunks*, flags*)
     "tw_decode_asr": (C.c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_int32, c_void_p, c_void_p]),

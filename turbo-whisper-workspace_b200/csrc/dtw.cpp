@@ -6,16 +6,16 @@
 // predecessor is chosen with the same strict comparisons (diagonal, then up, else left).
 #include "twb200_internal.h"
 
+#include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdint>
 #include <limits>
+#include <thread>
 #include <vector>
 
-extern "C" int tw_dtw_token_frames(const float* matrix, int64_t ld, int32_t n_tok, int32_t n_frames,
-                                   int32_t* token_frame) {
-    using tw::set_error;
-    if (!matrix || !token_frame) { set_error("tw_dtw_token_frames: null argument"); return 2; }
-    if (n_tok < 1 || n_frames < 1 || ld < n_frames) { set_error("tw_dtw_token_frames: bad shape %d x %d (ld %lld)", n_tok, n_frames, (long long)ld); return 2; }
+// one window; returns 0, or 3 on an unexpected trace value
+static int dtw_one(const float* matrix, int64_t ld, int32_t n_tok, int32_t n_frames, int32_t* token_frame) {
     const int64_t W = (int64_t)n_frames + 1;
     std::vector<float> cost((size_t)(n_tok + 1) * W, std::numeric_limits<float>::infinity());
     std::vector<int8_t> trace((size_t)(n_tok + 1) * W, -1);
@@ -49,7 +49,48 @@ extern "C" int tw_dtw_token_frames(const float* matrix, int64_t ld, int32_t n_to
         if (t == 0) { --i; --j; }
         else if (t == 1) { --i; }
         else if (t == 2) { --j; }
-        else { set_error("tw_dtw_token_frames: unexpected trace at (%d, %d)", i, j); return 3; }
+        else return 3;
     }
+    return 0;
+}
+
+extern "C" int tw_dtw_token_frames(const float* matrix, int64_t ld, int32_t n_tok, int32_t n_frames,
+                                   int32_t* token_frame) {
+    using tw::set_error;
+    if (!matrix || !token_frame) { set_error("tw_dtw_token_frames: null argument"); return 2; }
+    if (n_tok < 1 || n_frames < 1 || ld < n_frames) { set_error("tw_dtw_token_frames: bad shape %d x %d (ld %lld)", n_tok, n_frames, (long long)ld); return 2; }
+    if (dtw_one(matrix, ld, n_tok, n_frames, token_frame)) { set_error("tw_dtw_token_frames: unexpected trace value"); return 3; }
+    return 0;
+}
+
+// batch of windows on up to n_threads host threads (windows are independent); rows with n_frames[b] == 0 get frame -1
+// for every token, which is what HF's backtrace yields on an empty frame axis
+extern "C" int tw_dtw_token_frames_batch(const float* matrices, int64_t batch_stride, int64_t ld, int32_t batch,
+                                         int32_t n_tok, const int32_t* n_frames, int32_t* token_frames,
+                                         int32_t n_threads) {
+    using tw::set_error;
+    if (!matrices || !n_frames || !token_frames) { set_error("tw_dtw_token_frames_batch: null argument"); return 2; }
+    if (batch < 0 || n_tok < 1) { set_error("tw_dtw_token_frames_batch: bad batch %d / tokens %d", batch, n_tok); return 2; }
+    for (int32_t b = 0; b < batch; ++b)
+        if (n_frames[b] < 0 || n_frames[b] > ld) { set_error("tw_dtw_token_frames_batch: row %d has %d frames (ld %lld)", b, n_frames[b], (long long)ld); return 2; }
+    std::atomic<int32_t> next(0), failed(0);
+    auto work = [&]() {
+        for (;;) {
+            const int32_t b = next.fetch_add(1);
+            if (b >= batch) return;
+            int32_t* out = token_frames + (int64_t)b * n_tok;
+            if (n_frames[b] == 0) {
+                for (int32_t t = 0; t < n_tok; ++t) out[t] = -1;
+            } else if (dtw_one(matrices + (int64_t)b * batch_stride, ld, n_tok, n_frames[b], out)) {
+                failed.store(1);
+            }
+        }
+    };
+    const int32_t nt = std::max(1, std::min(n_threads, batch));
+    std::vector<std::thread> pool;
+    for (int32_t i = 1; i < nt; ++i) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+    if (failed.load()) { set_error("tw_dtw_token_frames_batch: unexpected trace value"); return 3; }
     return 0;
 }

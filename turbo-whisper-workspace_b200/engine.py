@@ -339,16 +339,12 @@ class WhisperEngine:
             host[:B, :n_tok].copy_(a["matrix"][:B, :n_tok], non_blocking=True)
             torch.cuda.current_stream(self.device).synchronize()
             self.stats["d2h_bytes"] += B * n_tok * S * 4
-        out = []
-        frames = np.empty(n_tok, dtype=np.int32)
-        for b in range(B):
-            if nf[b] == 0:
-                out.append([-1] * n_tok)
-                continue
-            check(lib.tw_dtw_token_frames(C.c_void_p(host[b].data_ptr()), S, n_tok, nf[b],
-                                          frames.ctypes.data_as(C.c_void_p)), "tw_dtw_token_frames")
-            out.append(frames.tolist())
-        return out
+        frames = np.empty((B, n_tok), dtype=np.int32)
+        nf_host = np.asarray(nf, dtype=np.int32)
+        check(lib.tw_dtw_token_frames_batch(C.c_void_p(host.data_ptr()), self.max_len * S, S, B, n_tok,
+                                            nf_host.ctypes.data_as(C.c_void_p), frames.ctypes.data_as(C.c_void_p),
+                                            min(B, max(1, (os.cpu_count() or 1) // 2))), "tw_dtw_token_frames_batch")
+        return frames.tolist()
 
     # ------------------------------------------------------------------------------------ front end
     def load_pcm(self, clips: Sequence[np.ndarray]) -> int:
