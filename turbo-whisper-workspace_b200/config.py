@@ -21,6 +21,14 @@ _SUPPRESS = [
 ]
 
 
+# generation_config.alignment_heads of the two checkpoints (from memory of the hub files, as the suppress list above —
+# verify when a checkpoint is available; GenerationSettings.from_hf copies the real field).  Used by tools/ only.
+ALIGNMENT_HEADS = {
+    "large-v3-turbo": [[2, 4], [2, 11], [3, 3], [3, 6], [3, 11], [3, 14]],
+    "large-v3": [[7, 0], [10, 17], [12, 18], [13, 12], [16, 1], [17, 14], [19, 11], [21, 4], [24, 1], [25, 6]],
+}
+
+
 @dataclass
 class WhisperDims:
     d_model: int = 1280
