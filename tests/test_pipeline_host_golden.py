@@ -98,3 +98,29 @@ def test_host_pipeline_word_timestamps_match_hf_golden(wav, variant):
     assert _norm(r) == gold[f"{variant}_single"]
     with pytest.raises(NotImplementedError):
         pipe(wav, chunk_length_s=30, generate_kwargs={"num_beams": 5}, return_timestamps="word")
+
+
+def test_host_pipeline_edge_inputs_match_hf_golden():
+    """Edge cases of the call the reference makes (tests/golden/make_golden_edges.py): empty audio without chunking is
+    one zero-padded 30 s window, 100 samples with chunking likewise, a last window that ends exactly at the end of the
+    audio, and the StopIteration transformers raises for empty audio with chunk_length_s."""
+    gold = json.load(open(os.path.join(GOLD, "edges_tiny.json")))
+    pipe = B200WhisperPipeline(None, WhisperDims(**helpers.TINY), helpers.build_tokenizer(),
+                               scheduler=OracleScheduler("varied"))
+    cases = [("empty_plain", np.zeros(0, np.float32), {}),
+             ("tiny_chunked", np.zeros(100, np.float32), dict(chunk_length_s=30, stride_length_s=5)),
+             ("exact_multiple", helpers.synth_clip(5, seconds=40.0), dict(chunk_length_s=30, stride_length_s=5)),
+             ("empty_chunked", np.zeros(0, np.float32), dict(chunk_length_s=30, stride_length_s=5))]
+    for name, x, kw in cases:
+        for rt in (True, None):
+            g = gold[f"{name}_{'ts' if rt else 'nots'}"]
+            call = lambda: pipe(x.copy(), batch_size=4, return_timestamps=rt, generate_kwargs={"task": "transcribe"}, **kw)
+            if "raises" in g:
+                assert g["raises"] == "StopIteration"
+                with pytest.raises(StopIteration):
+                    call()
+                continue
+            r = call()
+            assert sorted(r.keys()) == g["keys"] and r["text"] == g["text"], (name, rt)
+            if rt:
+                assert _norm(r)["chunks"] == g["chunks"], (name, rt)

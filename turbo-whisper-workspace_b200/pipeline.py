@@ -237,6 +237,11 @@ class B200WhisperPipeline:
                 raise ValueError("Chunk length must be superior to stride length")
             windows = chunk_windows(audio.shape[0], chunk_len, stride_left, stride_right)
             with_stride = True
+            if not windows:
+                # HF's chunk_iter yields nothing for empty audio and the pipeline's iterator chain ends in a bare
+                # StopIteration ($TF/pipelines/pt_utils.py); same exception here, so that the reference's
+                # `transcribe` turns it into its {"error": ...} dict exactly as it does today
+                raise StopIteration
         else:
             if audio.shape[0] > N_SAMPLES:
                 raise NotImplementedError(
