@@ -232,6 +232,19 @@ int tw_resample(const void* in, int32_t in_is_int16, int32_t channels, int64_t n
                 const float* filt, const int32_t* span, int32_t orig_rate, int32_t new_rate, int32_t width,
                 void* stream);
 
+/* ---- host: native FLAC reader (the reference's example input is FLAC; HF spawns ffmpeg per file) --------------
+ * Replaces the container decode of ffmpeg_read ($TF/pipelines/audio_utils.py:9-45) for FLAC streams (RFC 9639:
+ * CONSTANT / VERBATIM / FIXED / LPC subframes, Rice residuals, stereo decorrelation; frame CRC-8 / CRC-16 verified).
+ * The decoded interleaved PCM goes to tw_resample for conversion, down-mix and resampling on the GPU. */
+typedef struct tw_flac_info {
+    int32_t sample_rate, channels, bits_per_sample, max_block;
+    int64_t total_samples;      /* per channel; 0 = unknown (count with tw_flac_decode(out = NULL)) */
+    uint8_t md5[16];            /* of the decoded little-endian interleaved samples; all zero = not recorded */
+} tw_flac_info;
+int tw_flac_info_read(const uint8_t* data, int64_t n, tw_flac_info* out);
+/* out: int32 [out_cap_samples][channels] interleaved, or NULL to count only; n_decoded = samples per channel. */
+int tw_flac_decode(const uint8_t* data, int64_t n, int32_t* out, int64_t out_cap_samples, int64_t* n_decoded);
+
 /* ---- host: per-window token streams -> timestamped chunks ------------------------------------------------
  * Replaces tokenizer._decode_asr / _find_longest_common_sequence for return_timestamps in {False, True}
  * ($TF/models/whisper/tokenization_whisper.py:901-1150, 1153-1270; called from the pipeline's postprocess,

@@ -31,6 +31,11 @@ class SkinnyArgs(C.Structure):
                 ("ln_counter", c_void_p)]
 
 
+class FlacInfo(C.Structure):
+    _fields_ = [("sample_rate", c_int32), ("channels", c_int32), ("bits_per_sample", c_int32), ("max_block", c_int32),
+                ("total_samples", c_int64), ("md5", C.c_uint8 * 16)]
+
+
 class Grammar(C.Structure):
     _fields_ = [(n, c_int32) for n in ("eos", "pad", "no_timestamps", "ts_begin", "vocab", "lang_first", "lang_last",
                                        "max_initial_ts", "begin_index")]
@@ -73,6 +78,8 @@ SIGNATURES = {
                                   c_void_p, c_void_p, c_void_p]),
     "tw_dtw_token_frames": (C.c_int, [c_void_p, c_int64, c_int32, c_int32, c_void_p]),
     "tw_dtw_token_frames_batch": (C.c_int, [c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_int32]),
+    "tw_flac_info_read": (C.c_int, [c_void_p, c_int64, c_void_p]),
+    "tw_flac_decode": (C.c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
     # host-only: (tw_asr_window*, n, tw_asr_config*, out_tokens, cap, offsets, t0, t1, lang, max_chunks, n_chunks*, flags*)
     "tw_decode_asr": (C.c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_int32, c_void_p, c_void_p]),

@@ -52,6 +52,46 @@ def _read_wav(payload: bytes) -> Optional[Tuple[np.ndarray, int]]:
     return x.reshape(-1, ch), sr
 
 
+def _read_flac(payload: bytes, verify_md5: bool = True) -> Optional[Tuple[np.ndarray, int]]:
+    """Native FLAC reader (C library ``tw_flac_decode``): (samples [n, channels] int16 or float32, sample rate), or
+    None when the payload is not a FLAC stream.  Frame CRCs are checked by the decoder; the MD5 signature of
+    STREAMINFO (when recorded) is checked here.  Corrupt streams raise ValueError, as HF does for undecodable files."""
+    if not (payload[:4] == b"fLaC" or payload[:3] == b"ID3"):
+        return None
+    import ctypes as C
+    import hashlib
+    from . import _lib
+    lib = _lib.load()
+    buf = np.frombuffer(payload, dtype=np.uint8)
+    ptr = buf.ctypes.data_as(C.c_void_p)
+    info = _lib.FlacInfo()
+    if lib.tw_flac_info_read(ptr, len(payload), C.byref(info)) != 0:
+        if payload[:4] == b"fLaC":
+            raise ValueError("malformed FLAC stream: " + lib.tw_last_error().decode("utf-8", "replace"))
+        return None        # an ID3 tag in front of something else (e.g. mp3): not ours
+    n = C.c_int64(0)
+    total = int(info.total_samples)
+    if total == 0:         # unknown length: count first
+        _lib.check(lib.tw_flac_decode(ptr, len(payload), None, 0, C.byref(n)), "tw_flac_decode")
+        total = int(n.value)
+    out = np.empty((total, int(info.channels)), dtype=np.int32)
+    if lib.tw_flac_decode(ptr, len(payload), out.ctypes.data_as(C.c_void_p), total, C.byref(n)) != 0:
+        raise ValueError("Soundfile is either not in the correct format or is malformed: "
+                         + lib.tw_last_error().decode("utf-8", "replace"))
+    out = out[:int(n.value)]
+    bps = int(info.bits_per_sample)
+    if verify_md5 and any(info.md5):
+        width = (bps + 7) // 8
+        raw = (out.astype("<i2") if width == 2 else out.astype("i1") if width == 1 else out.astype("<i4")).tobytes()
+        if width == 3:
+            raw = np.frombuffer(raw, dtype=np.uint8).reshape(-1, 4)[:, :3].tobytes()
+        if hashlib.md5(raw).digest() != bytes(info.md5):
+            raise ValueError("FLAC stream decodes to samples that do not match its MD5 signature")
+    if bps == 16:
+        return out.astype(np.int16), int(info.sample_rate)
+    return out.astype(np.float32) / float(1 << (bps - 1)), int(info.sample_rate)
+
+
 _RESAMPLERS: Dict[Tuple[int, int, str], Any] = {}
 
 
@@ -69,10 +109,13 @@ def gpu_resample(x: np.ndarray, in_sr: int, out_sr: int, device) -> np.ndarray:
 
 
 def ffmpeg_read(payload: bytes, sampling_rate: int, device=None) -> np.ndarray:
-    """bytes -> mono fp32 at ``sampling_rate`` ($TF/pipelines/audio_utils.py:9-45).  WAV files are decoded
-    in-process — at the target rate on the host, at any other rate through the GPU ingest kernel when a device is
-    given; anything else goes through the same ``ffmpeg -i pipe:0 -ac 1 -ar SR -f f32le`` subprocess HF uses."""
+    """bytes -> mono fp32 at ``sampling_rate`` ($TF/pipelines/audio_utils.py:9-45).  WAV and FLAC files are decoded
+    in-process (FLAC by the C library's native reader) — at the target rate on the host, at any other rate through the
+    GPU ingest kernel when a device is given; anything else goes through the same
+    ``ffmpeg -i pipe:0 -ac 1 -ar SR -f f32le`` subprocess HF uses."""
     wav = _read_wav(payload)
+    if wav is None:
+        wav = _read_flac(payload)
     if wav is not None:
         x, sr = wav
         if sr == sampling_rate:
