@@ -259,3 +259,32 @@ def test_silent_windows_diverge_only_at_low_margin_steps(setup, cuda_device):
     agreed, identical_rows, first_diffs = helpers.compare_generate_traces(trace, etrace, margin_tol=0.30)
     print(f"\n[word] silent windows: {agreed} tokens agreed, identical rows {identical_rows}, first diffs {first_diffs}")
     assert 2 in identical_rows
+
+
+def test_flac_files_go_through_the_gpu_ingest(cuda_device, tmp_path):
+    """A 48 kHz stereo 16-bit FLAC (written by the test-side encoder) and the same samples as a WAV file decode to the
+    same integers, so the ingest kernel must give identical 16 kHz PCM for both — equal to torchaudio's resample of the
+    channel mean; a 192 kHz mono stream (the format of the reference's example file, 12:1) likewise.
+    (Added after the round's GPU budget was spent: the FLAC reader is CPU-verified in tests/test_flac.py, the
+    resampler at other ratios in tests/test_gpu_ops.py; this joins them.)"""
+    import wave
+    import torchaudio.functional as AF
+    import flac_writer as W
+    from turbo_whisper_workspace_b200 import pipeline as P
+    rng = np.random.default_rng(11)
+    xi = (rng.standard_normal((48000 * 2, 2)) * 0.1 * 32767).round().clip(-32768, 32767).astype("<i2")
+    flac_path, wav_path = tmp_path / "a.flac", tmp_path / "a.wav"
+    flac_path.write_bytes(W.encode(xi, 48000, 16, seed=1, blocksize=4096))
+    with wave.open(str(wav_path), "wb") as wf:
+        wf.setnchannels(2); wf.setsampwidth(2); wf.setframerate(48000); wf.writeframes(xi.tobytes())
+    a, _ = P.load_audio(str(flac_path), 16000, cuda_device)
+    b, _ = P.load_audio(str(wav_path), 16000, cuda_device)
+    np.testing.assert_array_equal(a, b)
+    want = AF.resample(torch.from_numpy(xi.astype(np.float32) / 32768.0).mean(dim=1), 48000, 16000).numpy()
+    assert a.shape == want.shape and float(np.abs(a - want).max()) < 1e-5
+    yi = (rng.standard_normal((192000, 1)) * 0.1 * 32767).round().astype("<i2")
+    p192 = tmp_path / "b.flac"
+    p192.write_bytes(W.encode(yi, 192000, 16, seed=2, blocksize=4096))
+    c, _ = P.load_audio(str(p192), 16000, cuda_device)
+    want = AF.resample(torch.from_numpy(yi[:, 0].astype(np.float32) / 32768.0), 192000, 16000).numpy()
+    assert c.shape == want.shape and float(np.abs(c - want).max()) < 1e-5
