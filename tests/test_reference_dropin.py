@@ -26,9 +26,16 @@ pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "vocalis")),
 
 @pytest.fixture(scope="module")
 def ap():
-    import transformers  # noqa: F401  (import the Whisper classes before stubbing the optional audio modules)
+    # import what transformers resolves lazily BEFORE stubbing the optional audio modules (its availability probes
+    # call importlib.util.find_spec on them)
+    import transformers
+    from transformers import pipeline, WhisperForConditionalGeneration, WhisperTokenizer  # noqa: F401
+    import importlib.machinery
     for m in ("librosa", "soundfile", "sherpa_onnx", "pydub"):
-        sys.modules.setdefault(m, types.ModuleType(m))
+        if m not in sys.modules:
+            stub = types.ModuleType(m)
+            stub.__spec__ = importlib.machinery.ModuleSpec(m, None)
+            sys.modules[m] = stub
     if not hasattr(sys.modules["pydub"], "AudioSegment"):
         sys.modules["pydub"].AudioSegment = type("AudioSegment", (), {})
     if REF not in sys.path:
@@ -72,3 +79,45 @@ def test_process_audio_with_the_b200_pipeline_object(ap, tmp_path):
     p.transcription_model = Boom()
     res = p.process_audio(str(wav), task="transcribe")
     assert "error" in res and "engine failure" in res["error"]
+
+
+def test_zero_touch_install_through_load_transcription_model(ap, tmp_path, monkeypatch):
+    """INTEGRATION.md §1 option (ii): `install()` patches `transformers.pipeline`, and the reference's UNMODIFIED
+    `load_transcription_model` (ref:vocalis/core/audio_pipeline.py:171-208) — reached through `process_audio` ->
+    `transcribe` with no model loaded — ends up holding the B200 pipeline object; other tasks are forwarded."""
+    import transformers
+    import turbo_whisper_workspace_b200.install as twb
+    gold = json.load(open(os.path.join(GOLD, "pipeline_tiny.json")))["reference_process_audio_varied"]
+    pcm = np.concatenate([helpers.synth_clip(0), helpers.synth_clip(1, kind="mod"),
+                          helpers.synth_clip(2, seconds=11.3, kind="mod")])
+    wav = tmp_path / "golden_71s.wav"
+    helpers.write_wav16(wav, pcm)
+    forwarded = []
+    monkeypatch.setattr(transformers, "pipeline", lambda task=None, model=None, *a, **k: forwarded.append((task, model)) or "lib")
+    loaded = []
+
+    def loader(model, tokenizer=None):
+        loaded.append(model)
+        return "hf-model-stand-in", helpers.build_tokenizer()
+
+    def builder(hf_model, tokenizer):
+        assert hf_model == "hf-model-stand-in"
+        return B200WhisperPipeline(None, WhisperDims(**helpers.TINY), tokenizer, scheduler=OracleScheduler("varied"))
+    monkeypatch.setitem(ap._PIPELINE_CACHE, "transcription_model", None)
+    twb.install(devices=["cuda:0"], loader=loader, builder=builder)
+    try:
+        assert transformers.pipeline("text-classification", model="bert") == "lib" and forwarded == [("text-classification", "bert")]
+        assert transformers.pipeline("automatic-speech-recognition", model="facebook/wav2vec2-base") == "lib"
+        p = ap.AudioProcessingPipeline()
+        assert p.transcription_model is None
+        p.diarize = lambda *a, **k: []
+        res = p.process_audio(str(wav), task="transcribe")
+        assert "error" not in res, res
+        assert isinstance(p.transcription_model, B200WhisperPipeline)
+        assert ap._PIPELINE_CACHE["transcription_model"] is p.transcription_model
+        assert loaded == ["openai/whisper-large-v3"]            # the reference's default model name
+        assert res["text"] == gold["text"]
+        assert [{"timestamp": list(c["timestamp"]), "text": c["text"]} for c in res["segments"]] == gold["segments"]
+    finally:
+        twb.uninstall()
+    assert transformers.pipeline("x", model="y") == "lib"       # the original factory is back
