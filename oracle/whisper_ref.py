@@ -1,8 +1,9 @@
 """Oracle: Whisper encoder / decoder / greedy generate, plain PyTorch fp32 on CPU
 (test infrastructure, see oracle/__init__.py).
 
-Restates, for the one configuration the reference's call reaches (greedy, timestamps on, no
-prompt, no temperature fallback, `condition_on_prev_tokens` off), the following functions of
+Restates, for the configuration the reference's call reaches (greedy, timestamps on, no
+prompt, no temperature fallback, `condition_on_prev_tokens` off) and the §8(f) "next" modes built
+on it (no timestamps, beam search, token timestamps), the following functions of
 transformers 5.5.0 (`$TF/`):
   * WhisperEncoder.forward / WhisperEncoderLayer      $TF/models/whisper/modeling_whisper.py:593-647, 380-414
   * WhisperAttention.forward                          $TF/models/whisper/modeling_whisper.py:284-357
@@ -14,6 +15,10 @@ transformers 5.5.0 (`$TF/`):
   * _retrieve_segment                                 $TF/models/whisper/generation_whisper.py:1976-2073
   * GenerationMixin._sample (greedy)                  $TF/generation/utils.py:2658-2841
   * Suppress*/WhisperTimeStamp logits processors      $TF/generation/logits_process.py:1812-2043
+  * GenerationMixin._beam_search                      $TF/generation/utils.py:3076-3400
+  * _extract_token_timestamps (word timestamps)       $TF/models/whisper/generation_whisper.py:241-381
+    with _median_filter :43-61, _dynamic_time_warping :64-112, the num_frames plumbing of
+    _postprocess_outputs :1133-1151 and the per-segment slices of _retrieve_segment :1976-2073
 The weights are read from an HF-layout ``state_dict`` (names as in SURVEY.md appendix B).
 """
 from __future__ import annotations
