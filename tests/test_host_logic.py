@@ -149,6 +149,59 @@ def test_load_audio_variants(tmp_path):
         P.load_audio(12)
 
 
+def _riff(fmt_tag, ch, sr, bits, body, extensible=False, extra_chunks=b"", data_size=None):
+    import struct
+    fmt = struct.pack("<HHIIHH", 0xFFFE if extensible else fmt_tag, ch, sr, sr * ch * bits // 8, ch * bits // 8, bits)
+    if extensible:
+        fmt += struct.pack("<HHI", 22, bits, 0) + struct.pack("<H", fmt_tag) + bytes(14)
+    chunks = b"fmt " + struct.pack("<I", len(fmt)) + fmt + extra_chunks
+    chunks += b"data" + struct.pack("<I", len(body) if data_size is None else data_size) + body
+    return b"RIFF" + struct.pack("<I", 4 + len(chunks)) + b"WAVE" + chunks
+
+
+def test_wav_reader_formats(tmp_path):
+    """The in-process RIFF reader: 8 / 16 / 24 / 32-bit PCM, 32-bit float, WAVE_FORMAT_EXTENSIBLE, chunks before the
+    data (odd-sized, padded), streamed files whose data size is 0 / 0xFFFFFFFF, stereo down-mix — and None (-> ffmpeg, as
+    in HF) for what it does not handle."""
+    rng = np.random.default_rng(5)
+    n, sr = 1600, 16000
+    f = rng.uniform(-0.9, 0.9, size=(n, 2))
+    i16 = (f * 32767).round().astype("<i2")
+    want16 = (i16.astype(np.float32) / 32768.0)
+    got, r = P._read_wav(_riff(1, 2, sr, 16, i16.tobytes()))
+    assert r == sr and got.dtype == np.int16 and (got == i16).all()
+    np.testing.assert_array_equal(P.ffmpeg_read(_riff(1, 2, sr, 16, i16.tobytes()), sr), want16.mean(axis=1))
+    np.testing.assert_array_equal(P.ffmpeg_read(_riff(1, 1, sr, 16, i16[:, 0].tobytes()), sr), want16[:, 0])
+    # odd-sized LIST chunk (padded to even) before the data, extensible header, streamed sizes
+    lst = b"LIST" + (5).to_bytes(4, "little") + b"abcde" + b"\x00"
+    for kw in (dict(extra_chunks=lst), dict(extensible=True), dict(data_size=0), dict(data_size=0xFFFFFFFF)):
+        got, _ = P._read_wav(_riff(1, 2, sr, 16, i16.tobytes(), **kw))
+        assert (got == i16).all(), kw
+    i24 = (f * 8388607).round().astype(np.int32)
+    b24 = np.stack([(i24 >> s) & 0xff for s in (0, 8, 16)], axis=-1).astype(np.uint8).tobytes()
+    got, _ = P._read_wav(_riff(1, 2, sr, 24, b24))
+    np.testing.assert_array_equal(got, i24.astype(np.float32) / 8388608.0)
+    i32 = (f * 2147483647).round().astype("<i4")
+    got, _ = P._read_wav(_riff(1, 2, sr, 32, i32.tobytes()))
+    np.testing.assert_array_equal(got, i32.astype(np.float32) / 2147483648.0)
+    u8 = ((f[:, :1] * 127).round() + 128).astype(np.uint8)
+    got, _ = P._read_wav(_riff(1, 1, sr, 8, u8.tobytes()))
+    np.testing.assert_array_equal(got, (u8.astype(np.float32) - 128.0) / 128.0)
+    f32 = f.astype("<f4")
+    got, _ = P._read_wav(_riff(3, 2, sr, 32, f32.tobytes()))
+    np.testing.assert_array_equal(got, f32)
+    assert P._read_wav(_riff(6, 1, sr, 8, bytes(100))) is None             # A-law: left to ffmpeg
+    assert P._read_wav(b"RIFF\x00\x00\x00\x00AVI ") is None and P._read_wav(b"") is None
+    # a file path goes through mmap and gives the same samples as the bytes
+    p = tmp_path / "s.wav"
+    p.write_bytes(_riff(1, 2, sr, 16, i16.tobytes()))
+    a, _ = P.load_audio(str(p))
+    np.testing.assert_array_equal(a, want16.mean(axis=1))
+    (tmp_path / "empty.wav").write_bytes(b"")
+    with pytest.raises(ValueError):
+        P.load_audio(str(tmp_path / "empty.wav"))
+
+
 def test_mel_filters_match_oracle():
     from oracle import logmel_ref as L
     from turbo_whisper_workspace_b200.ops import slaney_mel_filters

@@ -31,22 +31,53 @@ from .config import N_SAMPLES, SAMPLING_RATE, GenerationSettings, WhisperDims
 # ------------------------------------------------------------------------------------------------
 # audio ingest (host)
 # ------------------------------------------------------------------------------------------------
-def _read_wav(payload: bytes) -> Optional[Tuple[np.ndarray, int]]:
-    """RIFF/WAVE PCM reader (8 / 16 / 32-bit): (samples [n, channels] int16 or float32, sample rate), or None."""
-    if len(payload) < 12 or payload[:4] != b"RIFF" or payload[8:12] != b"WAVE":
+def _read_wav(payload) -> Optional[Tuple[np.ndarray, int]]:
+    """RIFF/WAVE reader over any bytes-like object, zero-copy for 16-bit PCM: (samples [n, channels] int16 or float32,
+    sample rate), or None when the payload is not a WAV file this reader handles (integer PCM of 8 / 16 / 24 / 32 bits
+    and 32-bit IEEE float, plain or WAVE_FORMAT_EXTENSIBLE; anything else is left to ffmpeg, as in HF)."""
+    buf = np.frombuffer(payload, dtype=np.uint8)
+    n = buf.size
+    if n < 12 or bytes(buf[:4]) != b"RIFF" or bytes(buf[8:12]) != b"WAVE":
         return None
-    try:
-        with wave.open(io.BytesIO(payload)) as wf:
-            sr, ch, sw, n = wf.getframerate(), wf.getnchannels(), wf.getsampwidth(), wf.getnframes()
-            raw = wf.readframes(n)
-    except wave.Error:
+    pos, fmt, data = 12, None, None
+    while pos + 8 <= n:
+        cid = bytes(buf[pos:pos + 4])
+        size = int(np.frombuffer(buf[pos + 4:pos + 8], dtype="<u4")[0])
+        body = pos + 8
+        if cid == b"fmt " and size >= 16 and body + 16 <= n:
+            tag, ch, sr, _, _, bits = np.frombuffer(buf[body:body + 16], dtype=[("t", "<u2"), ("c", "<u2"), ("r", "<u4"),
+                                                                                ("b", "<u4"), ("a", "<u2"), ("s", "<u2")])[0]
+            if int(tag) == 0xFFFE and size >= 26 and body + 26 <= n:      # extensible: the sub-format's first two bytes
+                tag = int(np.frombuffer(buf[body + 24:body + 26], dtype="<u2")[0])
+            fmt = (int(tag), int(ch), int(sr), int(bits))
+        elif cid == b"data":
+            if size == 0 or size == 0xFFFFFFFF or body + size > n:          # streamed / truncated files: to the end
+                size = n - body
+            data = (body, size)
+            break
+        pos = body + size + (size & 1)
+    if fmt is None or data is None:
         return None
-    if sw == 2:
-        x = np.frombuffer(raw, dtype="<i2")
-    elif sw == 4:
-        x = np.frombuffer(raw, dtype="<i4").astype(np.float32) / 2147483648.0
-    elif sw == 1:
-        x = (np.frombuffer(raw, dtype=np.uint8).astype(np.float32) - 128.0) / 128.0
+    tag, ch, sr, bits = fmt
+    if ch < 1 or sr < 1:
+        return None
+    body, size = data
+    frame = ch * (bits // 8)
+    if frame == 0:
+        return None
+    raw = buf[body:body + size - size % frame]
+    if tag == 1 and bits == 16:
+        x = raw.view("<i2")                                                 # zero-copy view of the payload
+    elif tag == 1 and bits == 32:
+        x = raw.view("<i4").astype(np.float32) / 2147483648.0
+    elif tag == 1 and bits == 24:
+        b3 = raw.reshape(-1, 3).astype(np.int32)
+        v = b3[:, 0] | (b3[:, 1] << 8) | (b3[:, 2] << 16)
+        x = ((v ^ 0x800000) - 0x800000).astype(np.float32) / 8388608.0
+    elif tag == 1 and bits == 8:
+        x = (raw.astype(np.float32) - 128.0) / 128.0
+    elif tag == 3 and bits == 32:
+        x = raw.view("<f4")
     else:
         return None
     return x.reshape(-1, ch), sr
@@ -108,7 +139,7 @@ def gpu_resample(x: np.ndarray, in_sr: int, out_sr: int, device) -> np.ndarray:
     return rs(t).cpu().numpy()
 
 
-def ffmpeg_read(payload: bytes, sampling_rate: int, device=None) -> np.ndarray:
+def ffmpeg_read(payload, sampling_rate: int, device=None) -> np.ndarray:
     """bytes -> mono fp32 at ``sampling_rate`` ($TF/pipelines/audio_utils.py:9-45).  WAV and FLAC files are decoded
     in-process (FLAC by the C library's native reader) — at the target rate on the host, at any other rate through the
     GPU ingest kernel when a device is given; anything else goes through the same
@@ -119,7 +150,8 @@ def ffmpeg_read(payload: bytes, sampling_rate: int, device=None) -> np.ndarray:
     if wav is not None:
         x, sr = wav
         if sr == sampling_rate:
-            x = x.astype(np.float32) / 32768.0 if x.dtype == np.int16 else x
+            # one pass; 1/32768 is a power of two, so the product equals the quotient bit for bit
+            x = np.multiply(x, np.float32(1.0 / 32768.0), dtype=np.float32) if x.dtype == np.int16 else x
             return np.ascontiguousarray(x[:, 0] if x.shape[1] == 1 else x.mean(axis=1), dtype=np.float32)
         if device is not None:
             return gpu_resample(x, sr, sampling_rate, device)
@@ -127,7 +159,7 @@ def ffmpeg_read(payload: bytes, sampling_rate: int, device=None) -> np.ndarray:
            "-loglevel", "quiet", "pipe:1"]
     try:
         with subprocess.Popen(cmd, stdin=subprocess.PIPE, stdout=subprocess.PIPE) as proc:
-            out = proc.communicate(payload)[0]
+            out = proc.communicate(bytes(payload))[0]
     except FileNotFoundError as e:
         raise ValueError("ffmpeg was not found but is required to load audio files from filename") from e
     audio = np.frombuffer(out, np.float32)
@@ -146,9 +178,13 @@ def load_audio(inputs: Any, sampling_rate: int = SAMPLING_RATE, device=None) -> 
     if isinstance(inputs, str):
         if inputs.startswith("http://") or inputs.startswith("https://"):
             raise ValueError("remote URLs are not supported by the offline engine; pass bytes or an array")
+        import mmap
         with open(inputs, "rb") as f:
-            inputs = f.read()
-    if isinstance(inputs, bytes):
+            try:
+                inputs = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)    # the readers work on the page cache directly
+            except (ValueError, OSError):                                      # empty file / no mmap support
+                inputs = f.read()
+    if isinstance(inputs, (bytes, bytearray, memoryview)) or type(inputs).__name__ == "mmap":
         inputs = ffmpeg_read(inputs, sampling_rate, device)
     if hasattr(inputs, "detach") and hasattr(inputs, "cpu"):  # torch.Tensor
         inputs = inputs.detach().cpu().numpy()
