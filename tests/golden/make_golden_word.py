@@ -63,6 +63,13 @@ def main():
                  return_timestamps="word")
         res[f"{variant}_30_5_24"] = {"text": r["text"], "chunks": [{"text": c["text"], "timestamp": list(c["timestamp"])}
                                                                  for c in r["chunks"]]}
+        if variant == "varied":
+            # the reference's literal chunking (chunk_length_s=60: every window is truncated to its first 30 s by the
+            # feature extractor while the stride bookkeeping keeps 60 s) with word timestamps
+            r = pipe(wav_path, chunk_length_s=60, stride_length_s=5, batch_size=32, generate_kwargs={"task": "transcribe"},
+                     return_timestamps="word")
+            res[f"{variant}_60_5_32"] = {"text": r["text"], "chunks": [{"text": c["text"], "timestamp": list(c["timestamp"])}
+                                                                     for c in r["chunks"]]}
         r = pipe(clips[2].copy(), generate_kwargs={"task": "transcribe"}, return_timestamps="word")
         res[f"{variant}_single"] = {"text": r["text"], "chunks": [{"text": c["text"], "timestamp": list(c["timestamp"])}
                                                                 for c in r["chunks"]]}

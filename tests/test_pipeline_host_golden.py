@@ -96,6 +96,11 @@ def test_host_pipeline_word_timestamps_match_hf_golden(wav, variant):
     r = pipe(helpers.synth_clip(2, seconds=11.3, kind="mod"), generate_kwargs={"task": "transcribe"},
              return_timestamps="word")
     assert _norm(r) == gold[f"{variant}_single"]
+    if variant == "varied":
+        # the reference's literal chunking (60 / 5, batch 32; windows truncated to 30 s) with word timestamps
+        r = pipe(wav, chunk_length_s=60, stride_length_s=5, batch_size=32, generate_kwargs={"task": "transcribe"},
+                 return_timestamps="word")
+        assert _norm(r) == gold["varied_60_5_32"]
     with pytest.raises(NotImplementedError):
         pipe(wav, chunk_length_s=30, generate_kwargs={"num_beams": 5}, return_timestamps="word")
 
