@@ -149,6 +149,32 @@ def test_load_audio_variants(tmp_path):
         P.load_audio(12)
 
 
+def test_from_hf_model_reads_config_and_generation_config():
+    """Everything the engine needs from an HF model object: dimensions from WhisperConfig, the Whisper fields of the
+    generation config (suppress lists, language / task ids, alignment heads) and median_filter_width."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden as G
+    model, _ = G.hf_model("varied")
+    model.generation_config.alignment_heads = [[0, 1], [1, 3]]
+    model.config.median_filter_width = 5
+
+    class NoEngines:
+        last_stats = {}
+
+        def run(self, clips, **kw):
+            return [[50365, 300, 50370] for _ in clips]
+    pipe = P.B200WhisperPipeline.from_hf_model(model, helpers.build_tokenizer(), scheduler=NoEngines())
+    d, g = pipe.dims, pipe.generation
+    assert (d.d_model, d.heads, d.ffn, d.enc_layers, d.dec_layers, d.vocab) == (256, 4, 1024, 2, 2, 51866)
+    assert g.alignment_heads == [[0, 1], [1, 3]] and g.median_filter_width == 5
+    assert g.eos_token_id == 50257 and g.decoder_start_token_id == 50258 and g.no_timestamps_token_id == 50364
+    assert g.task_to_id == {"transcribe": 50360, "translate": 50359} and g.lang_to_id["<|en|>"] == 50259
+    assert (g.lang_first, g.lang_last) == (50259, 50358) and len(g.suppress_tokens) == 88 and g.max_length == 448
+    r = pipe(np.zeros(16000, np.float32), return_timestamps=True)
+    assert r["chunks"] == [{"timestamp": (0.0, 0.1), "text": pipe.asr_decoder.text_of([300])}]
+
+
 def _riff(fmt_tag, ch, sr, bits, body, extensible=False, extra_chunks=b"", data_size=None):
     import struct
     fmt = struct.pack("<HHIIHH", 0xFFFE if extensible else fmt_tag, ch, sr, sr * ch * bits // 8, ch * bits // 8, bits)

@@ -276,12 +276,15 @@ class B200WhisperPipeline:
 
     @classmethod
     def from_hf_model(cls, model, tokenizer, devices=("cuda:0",), max_batch: int = 24,
-                      contexts_per_device: int = 4) -> "B200WhisperPipeline":
-        """Build from a ``transformers.WhisperForConditionalGeneration`` (weights, config, generation_config)."""
+                      contexts_per_device: int = 4, scheduler=None) -> "B200WhisperPipeline":
+        """Build from a ``transformers.WhisperForConditionalGeneration`` (weights, config, generation_config).
+        ``scheduler``: inject an engine stand-in instead of building GPU engines (tests)."""
         dims = WhisperDims.from_hf_config(model.config)
         gen = GenerationSettings.from_hf(model.generation_config)
         gen.median_filter_width = int(getattr(model.config, "median_filter_width", 7))
-        return cls(model.state_dict(), dims, tokenizer, gen, devices, max_batch, contexts_per_device=contexts_per_device)
+        sd = model.state_dict() if scheduler is None else None
+        return cls(sd, dims, tokenizer, gen, devices, max_batch, scheduler=scheduler,
+                   contexts_per_device=contexts_per_device)
 
     # -------------------------------------------------------------------------------- call
     def __call__(self, inputs, chunk_length_s: float = 0, stride_length_s=None, batch_size: Optional[int] = None,
