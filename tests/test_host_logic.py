@@ -9,6 +9,7 @@ import pytest
 import helpers
 from turbo_whisper_workspace_b200 import pipeline as P
 from turbo_whisper_workspace_b200 import scheduler as S
+from turbo_whisper_workspace_b200.config import WhisperDims
 from turbo_whisper_workspace_b200.engine import retrieve_segment, _bitmap
 
 
@@ -147,6 +148,42 @@ def test_load_audio_variants(tmp_path):
         P.load_audio({"raw": x})
     with pytest.raises(TypeError):
         P.load_audio(12)
+
+
+def test_list_inputs_share_one_window_stream():
+    """A list call sends the windows of ALL inputs to the engines in one scheduler run (HF's chunk pipeline batches
+    across inputs too) and gives exactly the per-input results of separate calls, in order, for every mode."""
+    class Sched:
+        last_stats = {}
+
+        def __init__(self):
+            self.runs = []
+
+        def run(self, clips, token_timestamps=False, group=None, **kw):
+            self.runs.append((len(clips), group))
+            rows = []
+            for c in clips:
+                k = int(abs(float(c[:8].sum())) * 1e4) % 1000 if len(c) else 0
+                ids = [50365, 300 + k, 301 + len(c) % 97, 50365 + 100 + k % 50]
+                rows.append((ids, [0.0, 0.5, 1.0, 1.5]) if token_timestamps else ids)
+            return rows
+    sch = Sched()
+    pipe = P.B200WhisperPipeline(None, WhisperDims(**helpers.TINY), helpers.build_tokenizer(), scheduler=sch)
+    files = [helpers.synth_clip(i, seconds=s) for i, s in enumerate((3.0, 71.0, 0.5, 30.0, 45.5))]
+    for kw in (dict(chunk_length_s=30, stride_length_s=5, batch_size=4, return_timestamps=True),
+               dict(chunk_length_s=30, stride_length_s=5, batch_size=4),
+               dict(chunk_length_s=30, stride_length_s=[4, 2], batch_size=3, return_timestamps="word")):
+        sch.runs.clear()
+        together = pipe(files, **kw)
+        st = kw["stride_length_s"] if isinstance(kw["stride_length_s"], list) else [kw["stride_length_s"]] * 2
+        n_win = sum(len(P.chunk_windows(len(f), 30 * 16000, st[0] * 16000, st[1] * 16000)) for f in files)
+        assert sch.runs == [(n_win, kw["batch_size"] if kw.get("return_timestamps") == "word" else None)]
+        apart = [pipe(f, **kw) for f in files]
+        assert together == apart and isinstance(together, list) and len(together) == 5
+        assert pipe.last_stats["windows"] == 2       # the last single call
+    assert pipe((), chunk_length_s=30) == [] and pipe([files[0]], chunk_length_s=30)[0] == pipe(files[0], chunk_length_s=30)
+    with pytest.raises(StopIteration):               # one empty input aborts the whole call before any GPU work
+        pipe([files[0], np.zeros(0, np.float32)], chunk_length_s=30)
 
 
 def test_from_hf_model_reads_config_and_generation_config():

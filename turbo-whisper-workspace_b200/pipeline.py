@@ -290,10 +290,12 @@ class B200WhisperPipeline:
     def __call__(self, inputs, chunk_length_s: float = 0, stride_length_s=None, batch_size: Optional[int] = None,
                  generate_kwargs: Optional[dict] = None, return_timestamps=None, return_language=None,
                  **unused) -> Union[Dict[str, Any], List[Dict[str, Any]]]:
-        if isinstance(inputs, (list, tuple)):
-            return [self(i, chunk_length_s=chunk_length_s, stride_length_s=stride_length_s, batch_size=batch_size,
-                         generate_kwargs=generate_kwargs, return_timestamps=return_timestamps,
-                         return_language=return_language) for i in inputs]
+        """One input -> one dict; a list / tuple of inputs -> a list of dicts.  As in HF's chunk pipeline
+        ($TF/pipelines/pt_utils.py:156-298: the windows of all inputs form ONE stream that is batched `batch_size` at
+        a time and regrouped per input afterwards) the windows of all files of a list call go to the engines together,
+        so many short files fill the GPUs as well as one long file does."""
+        many = isinstance(inputs, (list, tuple))
+        items = list(inputs) if many else [inputs]
         generate_kwargs = dict(generate_kwargs or {})
         task = generate_kwargs.pop("task", None) or "transcribe"
         language = generate_kwargs.pop("language", None)
@@ -304,7 +306,39 @@ class B200WhisperPipeline:
         if return_timestamps == "char":
             raise ValueError("Whisper cannot return `char` timestamps, only word level or segment level timestamps. "
                              "Use `return_timestamps='word'` or `return_timestamps=True` respectively.")
+        sr = self.sampling_rate
+        prepared = [self._prepare(x, chunk_length_s, stride_length_s) for x in items]
+        clips = [c for p in prepared for c in p["clips"]]
+        # return_timestamps falsy (the HF default): generate runs with <|notimestamps|> in the prompt and without the
+        # timestamp grammar, and the windows are merged on their overlapping text only
+        run_kw: Dict[str, Any] = {}
+        if not return_timestamps:
+            run_kw["return_timestamps"] = False
+        if num_beams > 1:
+            run_kw["num_beams"] = num_beams      # beam search: every window occupies num_beams decode rows
+        bs = max(1, int(batch_size or 1))
+        token_times = None
+        if return_timestamps == "word":
+            # generate(return_token_timestamps=True, return_segments=True): the engine taps the alignment heads'
+            # cross-attention; micro-batches follow HF's batches of `batch_size` consecutive windows (capped by the
+            # engine's max_batch) because a row's DTW spans the decode steps of its batch's longest row
+            run_kw.update(token_timestamps=True, group=bs)
+        token_rows = self.scheduler.run(clips, task=task, language=language, **run_kw) if clips else []
+        if return_timestamps == "word":
+            token_times = [np.asarray(t, dtype=np.float32) for _, t in token_rows]
+            token_rows = [r for r, _ in token_rows]
+        self.last_stats = dict(self.scheduler.last_stats, windows=len(clips), files=len(items),
+                               audio_seconds=sum(p["n_samples"] for p in prepared) / sr)
+        results, w0 = [], 0
+        for p in prepared:
+            n = len(p["windows"])
+            results.append(self._finish(p, token_rows[w0:w0 + n], None if token_times is None else token_times[w0:w0 + n],
+                                        bs, return_timestamps, return_language))
+            w0 += n
+        return results if many else results[0]
 
+    def _prepare(self, inputs, chunk_length_s, stride_length_s) -> Dict[str, Any]:
+        """preprocess ($TF/pipelines/automatic_speech_recognition.py:341-477) of one input: PCM, windows, clips."""
         audio, extra = load_audio(inputs, self.sampling_rate, self.ingest_device)
         sr = self.sampling_rate
         if chunk_length_s:
@@ -331,29 +365,14 @@ class B200WhisperPipeline:
                     "pass chunk_length_s as the reference does")
             windows = [(0, audio.shape[0], (audio.shape[0], 0, 0), True)]
             with_stride = False
-
         # the feature extractor truncates every window to its first 30 s (truncation=True, max_length=480000)
         clips = [audio[s:e][:N_SAMPLES] for (s, e, _, _) in windows]
-        # return_timestamps falsy (the HF default): generate runs with <|notimestamps|> in the prompt and without the
-        # timestamp grammar, and the windows are merged on their overlapping text only
-        run_kw: Dict[str, Any] = {}
-        if not return_timestamps:
-            run_kw["return_timestamps"] = False
-        if num_beams > 1:
-            run_kw["num_beams"] = num_beams      # beam search: every window occupies num_beams decode rows
-        bs = max(1, int(batch_size or 1))
-        token_times = None
-        if return_timestamps == "word":
-            # generate(return_token_timestamps=True, return_segments=True): the engine taps the alignment heads'
-            # cross-attention; micro-batches follow HF's batches of `batch_size` consecutive windows (capped by the
-            # engine's max_batch) because a row's DTW spans the decode steps of its batch's longest row
-            run_kw.update(token_timestamps=True, group=bs)
-        token_rows = self.scheduler.run(clips, task=task, language=language, **run_kw)
-        if return_timestamps == "word":
-            token_times = [np.asarray(t, dtype=np.float32) for _, t in token_rows]
-            token_rows = [r for r, _ in token_rows]
-        self.last_stats = dict(self.scheduler.last_stats, windows=len(windows), audio_seconds=audio.shape[0] / sr)
+        return {"windows": windows, "with_stride": with_stride, "clips": clips, "extra": extra,
+                "n_samples": int(audio.shape[0])}
 
+    def _finish(self, prep, token_rows, token_times, bs, return_timestamps, return_language) -> Dict[str, Any]:
+        """_forward's stride plumbing + postprocess (:479-656) for the windows of one input."""
+        sr, windows = self.sampling_rate, prep["windows"]
         # HF batches `batch_size` consecutive windows per generate call and right-pads each batch to its
         # longest row with pad_token_id; _decode_asr ignores the padding, so the grouping only affects shapes.
         pad = self.generation.pad_token_id
@@ -367,7 +386,7 @@ class B200WhisperPipeline:
                 item: Dict[str, Any] = {"tokens": arr}
                 if token_times is not None:
                     item["token_timestamps"] = token_times[g0 + i][None, :]
-                if with_stride:
+                if prep["with_stride"]:
                     ln, sl, srr = windows[g0 + i][2]
                     item["stride"] = (ln / sr, sl / sr, srr / sr)
                 model_outputs.append(item)
@@ -377,7 +396,7 @@ class B200WhisperPipeline:
             import logging
             logging.getLogger(__name__).warning(
                 "Whisper did not predict an ending timestamp, which can happen if audio is cut off in the middle of a word.")
-        return {"text": text, **optional, **{k: [v] for k, v in extra.items()}}
+        return {"text": text, **optional, **{k: [v] for k, v in prep["extra"].items()}}
 
     def close(self):
         self.scheduler.close()
