@@ -316,12 +316,28 @@ class WhisperRef:
         jumps = np.pad(np.diff(text), (1, 0), constant_values=1).astype(bool)
         return time[jumps].tolist()
 
-    def alignment_matrix(self, cross: List[list], alignment_heads, row: int, n_prompt: int, num_frames: int,
+    @staticmethod
+    def beam_weights(cross: List[list], alignment_heads, beam_indices: torch.Tensor, n_prompt: int) -> torch.Tensor:
+        """The beam-search branch of _extract_token_timestamps (:265-303): for every output position take the
+        alignment heads' cross-attention row of the beam that produced it (the first index is repeated for the prompt
+        positions of the prefill; -1 = past the end of the hypothesis -> row 0).  -> [B, heads, length, S]."""
+        w = torch.stack([torch.cat(cross[l], dim=2)[:, h] for l, h in alignment_heads]).permute(1, 0, 2, 3)
+        wl = int((beam_indices != -1).sum(-1).max())
+        bi = beam_indices[:, :wl]
+        if n_prompt > 1:
+            bi = torch.cat([bi[:, :1].expand(-1, n_prompt - 1), bi], dim=-1)
+        bi = bi.masked_fill(bi == -1, 0)
+        return torch.stack([torch.index_select(w[:, :, i, :], 0, bi[:, i]) for i in range(bi.shape[1])], dim=2)
+
+    def alignment_matrix(self, cross, alignment_heads, row: int, n_prompt: int, num_frames: int,
                          median_width: int = 7, pre_crop: Optional[int] = None) -> torch.Tensor:
         """The per-row branch of _extract_token_timestamps (:352-365): stack the alignment (layer, head) pairs, crop to
         num_frames // 2 encoder positions, drop the prompt positions, standardise over the token axis (population
         std), median-filter along frames, average the heads.  -> fp32 [tokens, frames]."""
-        w = torch.stack([torch.cat(cross[l], dim=2)[row, h] for l, h in alignment_heads])      # [heads, T, S]
+        if torch.is_tensor(cross):            # already gathered weights [B, heads, T, S] (beam search)
+            w = cross[row]
+        else:
+            w = torch.stack([torch.cat(cross[l], dim=2)[row, h] for l, h in alignment_heads])      # [heads, T, S]
         if pre_crop is not None:
             w = w[..., : pre_crop // 2]      # the whole-batch crop taken when every row has the same num_frames (:316-323)
         w = w[..., : num_frames // 2][:, n_prompt:, :]
@@ -335,7 +351,7 @@ class WhisperRef:
         """_extract_token_timestamps for a greedy batch: fp32 [rows, prompt + generated]: 0 for the prompt positions,
         the DTW jump time of every generated token, the last one repeated for the final token (its cross-attention
         is never computed)."""
-        T = sum(p.shape[2] for p in cross[0])
+        T = cross.shape[2] if torch.is_tensor(cross) else sum(p.shape[2] for p in cross[0])
         out = torch.zeros(n_rows, T + 1, dtype=torch.float32)
         if T - n_prompt <= 0:
             return out
@@ -351,7 +367,8 @@ class WhisperRef:
 
 
     def beam_search(self, enc_out: torch.Tensor, prompt: torch.Tensor, gc: GenConfig, num_beams: int = 5,
-                    length_penalty: float = 1.0, timestamps: bool = True) -> torch.Tensor:
+                    length_penalty: float = 1.0, timestamps: bool = True, cross: Optional[List[list]] = None,
+                    aux: Optional[dict] = None) -> torch.Tensor:
         """GenerationMixin._beam_search ($TF/generation/utils.py:3076-3400 and its helpers :2876-3075) for the
         Whisper decoder, early_stopping=False, do_sample=False, one returned sequence per row.
 
@@ -361,7 +378,10 @@ class WhisperRef:
         divided by (generated length)**length_penalty — for the num_beams finished slots, the best num_beams
         others continue (the self-attention cache rows are re-gathered by their beam of origin).  The loop ends when
         the best running score over (current generated length)**length_penalty cannot beat the worst finished one.
-        Returns the best finished sequence per row without the prompt, right-padded with pad_token_id."""
+        Returns the best finished sequence per row without the prompt, right-padded with pad_token_id.
+        ``cross`` collects the cross-attention weights of every forward (rows = batch x beams in their order at that
+        step); ``aux["beam_indices"]`` receives HF's `beam_indices` [B, generated]: for every generated position the
+        row (batch-offset beam) whose forward produced it, -1 beyond the hypothesis (:2984-2995, :3377-3386)."""
         B, P = prompt.shape
         K, V, L = num_beams, self.dims.vocab, gc.max_length
         NEG = -1.0e9
@@ -378,8 +398,10 @@ class WhisperRef:
         top_mask = torch.cat([torch.ones(K, dtype=torch.bool), torch.zeros(K, dtype=torch.bool)])
         cache = self.new_cache()
         cur = P
-        logits = self.decode(running[:, :, :P].reshape(B * K, P), enc, cache, 0)[:, -1]
+        logits = self.decode(running[:, :, :P].reshape(B * K, P), enc, cache, 0, cross=cross)[:, -1]
         batch_off = (torch.arange(B) * K)[:, None]
+        run_idx = torch.full((B, K, L - P), -1, dtype=torch.long)
+        fin_idx = run_idx.clone()
         while True:
             flat = running[:, :, :cur].reshape(B * K, cur)
             logp = torch.log_softmax(logits.float(), dim=-1)
@@ -389,11 +411,14 @@ class WhisperRef:
             origin = top_idx // V
             cand = torch.gather(running, 1, origin[:, :, None].expand(-1, -1, L)).clone()
             cand[:, :, cur] = top_idx % V
+            cand_idx = torch.gather(run_idx, 1, origin[:, :, None].expand(-1, -1, L - P)).clone()
+            cand_idx[:, :, cur - P] = origin + batch_off
             hits = (cand[:, :, cur] == gc.eos_token_id) | (cur + 1 >= L)
             # beams that continue
             run_lp = top_lp + hits.float() * NEG
             nxt = torch.topk(run_lp, k=K)[1]
             running = torch.gather(cand, 1, nxt[:, :, None].expand(-1, -1, L))
+            run_idx = torch.gather(cand_idx, 1, nxt[:, :, None].expand(-1, -1, L - P))
             running_scores = torch.gather(run_lp, 1, nxt)
             next_origin = torch.gather(origin, 1, nxt)
             # finished slots
@@ -407,6 +432,7 @@ class WhisperRef:
             m_len = torch.cat([gen_len, torch.full((B, 2 * K), cur + 1 - P, dtype=torch.long)], dim=1)
             keep = torch.topk(m_lp, k=K)[1]
             finished_seq = torch.gather(m_seq, 1, keep[:, :, None].expand(-1, -1, L))
+            fin_idx = torch.gather(torch.cat([fin_idx, cand_idx], dim=1), 1, keep[:, :, None].expand(-1, -1, L - P))
             beam_scores = torch.gather(m_lp, 1, keep)
             is_finished = torch.gather(m_fin, 1, keep)
             gen_len = torch.gather(m_len, 1, keep)
@@ -423,8 +449,11 @@ class WhisperRef:
             improvable = improvable & (best_possible > worst_finished).any(dim=-1, keepdim=True)
             if not (bool(improvable.any()) and not bool(hits.all())):
                 break
-            logits = self.decode(running[:, :, cur - 1:cur].reshape(B * K, 1), enc, cache, cur - 1)[:, -1]
+            logits = self.decode(running[:, :, cur - 1:cur].reshape(B * K, 1), enc, cache, cur - 1, cross=cross)[:, -1]
         n = int(gen_len[:, 0].max())
+        if aux is not None:
+            bi = fin_idx[:, 0, :]
+            aux["beam_indices"] = bi[:, :int(((bi + 1).bool()).sum(dim=1).max())]
         return finished_seq[:, 0, P:P + n]
 
     @staticmethod
@@ -488,7 +517,11 @@ class WhisperRef:
             rec = [] if trace is not None else None
             cross = [[] for _ in range(self.dims.dec_layers)] if alignment_heads is not None else None
             if num_beams > 1:
-                toks = self.beam_search(enc, init[rows], gc, num_beams=num_beams, timestamps=return_timestamps)
+                aux = {}
+                toks = self.beam_search(enc, init[rows], gc, num_beams=num_beams, timestamps=return_timestamps,
+                                        cross=cross, aux=aux)
+                if cross is not None:
+                    cross = self.beam_weights(cross, alignment_heads, aux["beam_indices"], init.shape[1])
             else:
                 toks = self.greedy(enc, init[rows], gc, record=rec, timestamps=return_timestamps, cross=cross)
             if cross is not None:

@@ -154,6 +154,28 @@ def test_token_timestamps_oracle_vs_hf_golden(variant):
                                       np.asarray(g["token_timestamps"][b][:len(row)], dtype=np.float32))
 
 
+@pytest.mark.parametrize("variant", ["varied"])
+def test_token_timestamps_under_beam_search_oracle_vs_hf_golden(variant):
+    """generate(num_beams=5, return_token_timestamps=True): the oracle's beam search also tracks HF's `beam_indices`
+    (same gathers as the sequences, batch-offset parent row per generated position, -1 beyond the hypothesis) and the
+    token-timestamp stage gathers every position's alignment rows from the beam that produced it — tokens and fp32
+    times identical to transformers.  Groundwork for word timestamps with beam search on the GPU path (the engine
+    raises NotImplementedError for that combination today)."""
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "word_beams_tiny.json")))
+    _, fb = _clips_feats()
+    dims = R.WhisperDims(**helpers.TINY)
+    ref = R.WhisperRef(dims, helpers.variant_state_dict(dims, variant))
+    ts = {}
+    got = ref.generate(fb, num_beams=5, alignment_heads=gold["alignment_heads"], num_frames=gold["num_frames"], token_ts=ts)
+    g = gold[f"{variant}_generate_beams5"]
+    for b, row in enumerate(got):
+        assert row == g["segment_tokens"][b], f"row {b}"
+        np.testing.assert_array_equal(np.asarray(ts["segments"][b], dtype=np.float32),
+                                      np.asarray(g["segment_token_timestamps"][b], dtype=np.float32))
+        np.testing.assert_array_equal(np.asarray(ts["sequences"][b], dtype=np.float32),
+                                      np.asarray(g["token_timestamps"][b][:len(row)], dtype=np.float32))
+
+
 def test_dtw_oracle_and_native_match_transformers_function():
     """The oracle's anti-diagonal DTW and the C library's tw_dtw_token_frames against transformers'
     _dynamic_time_warping + jump extraction on random matrices, tie-heavy integer matrices included."""
