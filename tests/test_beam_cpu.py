@@ -14,7 +14,7 @@ def _drive(ref, enc, prompt, gc, K):
     cfg = BeamConfig(num_beams=K, vocab=ref.dims.vocab, max_length=gc.max_length, eos_id=gc.eos_token_id,
                      pad_id=gc.pad_token_id, no_timestamps_id=gc.no_timestamps_token_id, suppress=gc.suppress_tokens,
                      begin_suppress=gc.begin_suppress_tokens, max_initial_timestamp_index=gc.max_initial_timestamp_index)
-    bs = BeamSearch(cfg, prompt)
+    bs = BeamSearch(cfg, prompt, track_indices=True)
     B, P = prompt.shape
     encK = enc.repeat_interleave(K, dim=0)
     cache = ref.new_cache()
@@ -29,7 +29,7 @@ def _drive(ref, enc, prompt, gc, K):
                     if name in layer[kind]:
                         layer[kind][name] = layer[kind][name].index_select(0, origin)
         logits = ref.decode(bs.rows()[:, -1:], encK, cache, bs.cur - 1)[:, -1]
-    return bs.result()
+    return bs.result(), bs.beam_indices()
 
 
 @pytest.mark.parametrize("variant", ["decisive", "varied"])
@@ -42,9 +42,13 @@ def test_beam_bookkeeping_matches_oracle(variant):
     enc = ref.encode(feats)
     langs = ref.detect_language(enc, gc)
     prompt = torch.tensor([[gc.decoder_start_token_id, langs[b], gc.task_to_id["transcribe"]] for b in range(2)])
-    want = ref.beam_search(enc, prompt, gc, num_beams=5)
-    got = _drive(ref, enc, prompt, gc, 5)
+    aux = {}
+    want = ref.beam_search(enc, prompt, gc, num_beams=5, aux=aux)
+    got, idx = _drive(ref, enc, prompt, gc, 5)
     assert got.shape == want.shape and torch.equal(got, want)
+    # HF's `beam_indices` of the returned hypotheses (the oracle's are pinned through the token timestamps they select,
+    # tests/test_oracle_golden.py::test_token_timestamps_under_beam_search_oracle_vs_hf_golden)
+    assert torch.equal(idx, aux["beam_indices"])
 
 
 def test_process_scores_matches_oracle_processors():

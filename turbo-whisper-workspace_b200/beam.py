@@ -79,8 +79,10 @@ class BeamConfig:
 class BeamSearch:
     """State of one beam search over ``n`` windows x ``num_beams`` rows (row = window * num_beams + beam)."""
 
-    def __init__(self, cfg: BeamConfig, prompt: torch.Tensor):
-        """prompt: int64 [n, P] on the device the logits will live on."""
+    def __init__(self, cfg: BeamConfig, prompt: torch.Tensor, track_indices: bool = False):
+        """prompt: int64 [n, P] on the device the logits will live on.  ``track_indices``: also keep HF's
+        `beam_indices` ($TF/generation/utils.py:2984-2995, 3065-3070) — for every generated position the row whose
+        forward produced it — which word timestamps under beam search gather the cross-attention rows by."""
         self.cfg = cfg
         dev = prompt.device
         n, P = prompt.shape
@@ -100,6 +102,15 @@ class BeamSearch:
         self.begin_suppress = torch.as_tensor(list(cfg.begin_suppress), dtype=torch.long, device=dev)
         self.batch_off = (torch.arange(n, device=dev) * K)[:, None]
         self.done = False
+        self.run_idx = self.fin_idx = None
+        if track_indices:
+            self.run_idx = torch.full((n, K, L - P), -1, dtype=torch.long, device=dev)
+            self.fin_idx = self.run_idx.clone()
+
+    def beam_indices(self) -> torch.Tensor:
+        """HF's `beam_indices` of the returned hypotheses: int64 [n, longest generated], -1 beyond a hypothesis."""
+        bi = self.fin_idx[:, 0, :]
+        return bi[:, :int(((bi + 1).bool()).sum(dim=1).max())]
 
     def rows(self) -> torch.Tensor:
         """Current token matrix of the running rows, [n * num_beams, cur]."""
@@ -137,6 +148,11 @@ class BeamSearch:
         m_len = torch.cat([self.gen_len, torch.full((n, 2 * K), cur + 1 - P, dtype=torch.long, device=logits.device)], dim=1)
         keep = torch.topk(m_lp, k=K)[1]
         self.finished_seq = torch.gather(m_seq, 1, keep[:, :, None].expand(-1, -1, L))
+        if self.run_idx is not None:
+            cand_idx = torch.gather(self.run_idx, 1, origin[:, :, None].expand(-1, -1, L - P)).clone()
+            cand_idx[:, :, cur - P] = origin + self.batch_off
+            self.run_idx = torch.gather(cand_idx, 1, nxt[:, :, None].expand(-1, -1, L - P))
+            self.fin_idx = torch.gather(torch.cat([self.fin_idx, cand_idx], dim=1), 1, keep[:, :, None].expand(-1, -1, L - P))
         self.beam_scores = torch.gather(m_lp, 1, keep)
         self.is_finished = torch.gather(m_fin, 1, keep)
         self.gen_len = torch.gather(m_len, 1, keep)
