@@ -288,3 +288,37 @@ def test_flac_files_go_through_the_gpu_ingest(cuda_device, tmp_path):
     c, _ = P.load_audio(str(p192), 16000, cuda_device)
     want = AF.resample(torch.from_numpy(yi[:, 0].astype(np.float32) / 32768.0), 192000, 16000).numpy()
     assert c.shape == want.shape and float(np.abs(c - want).max()) < 1e-5
+
+
+@pytest.mark.xfail(strict=False, reason="EXPERIMENTAL path written after the round's GPU budget was spent (never run on a "
+                   "GPU): token timestamps under beam search on the engine (decode_beams(frames_keep=...), gated by "
+                   "TWB200_EXPERIMENTAL_BEAM_WORD).  The oracle side is pinned time-exact to transformers "
+                   "(tests/test_oracle_golden.py) and BeamSearch's beam_indices to the oracle (tests/test_beam_cpu.py)")
+def test_experimental_token_timestamps_under_beam_search(cuda_device, monkeypatch):
+    from oracle import logmel_ref as L
+    from oracle import whisper_ref as R
+    from turbo_whisper_workspace_b200.config import GenerationSettings, WhisperDims
+    from turbo_whisper_workspace_b200.engine import WhisperEngine
+    monkeypatch.setenv("TWB200_EXPERIMENTAL_BEAM_WORD", "1")
+    clips = [helpers.synth_clip(0), helpers.synth_clip(2, seconds=11.3, kind="mod")]
+    nf = [3000, 1130]
+    feats = torch.stack([torch.from_numpy(L.log_mel(c)) for c in clips]).to(torch.bfloat16).float()
+    rd = R.WhisperDims(**helpers.TINY)
+    sd = helpers.variant_state_dict(rd, "decisive")
+    eng = WhisperEngine(WhisperDims(**helpers.TINY), sd, device=cuda_device, max_batch=10,
+                        gen=GenerationSettings(alignment_heads=HEADS))
+    B = eng.load_pcm(clips)
+    eng.features(B)
+    got = eng.generate(B, num_beams=5, token_timestamps=True, num_frames=nf)
+    ts = eng.last_token_ts
+    ots = {}
+    want = R.WhisperRef(rd, sd).generate(feats, num_beams=5, alignment_heads=HEADS, num_frames=nf, token_ts=ots)
+    same = [b for b in range(B) if got[b] == want[b]]
+    assert same, "no window decoded identically to the oracle's beam search"
+    for b in same:
+        a, o = np.asarray(ts[b]), np.asarray(ots["segments"][b])
+        assert a.shape == o.shape
+        close = float((np.abs(a - o) <= TS_CLOSE_S).mean())
+        print(f"\n[word] beam search, window {b}: {int((np.abs(a - o) < 1e-6).sum())}/{a.size} token times identical, "
+              f"{close:.3f} within {TS_CLOSE_S} s")
+        assert close >= TS_CLOSE_FRAC

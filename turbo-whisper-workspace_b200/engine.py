@@ -308,30 +308,34 @@ class WhisperEngine:
                 "host": torch.zeros(Bm, self.max_len, S, dtype=torch.float32).pin_memory(),
             }
 
-    def token_frames(self, B: int, tokens: List[List[int]], n_prompt: int, n_frames: Sequence[int]) -> List[List[int]]:
+    def token_frames(self, B: int, tokens: List[List[int]], n_prompt: int, n_frames: Sequence[int],
+                     probs: Optional[torch.Tensor] = None, n_tok: Optional[int] = None) -> List[List[int]]:
         """_extract_token_timestamps ($TF/models/whisper/generation_whisper.py:241-381) for the B rows just decoded
         with the alignment tap on: per row the encoder frame of every token position >= n_prompt of the batch's
         sequence (HF's `sequences` of this generate call: as long as the longest row, eos included) but the last.
         ``tokens``: the rows of decode(); ``n_frames[b]``: encoder frames kept for row b (the `[..., : num_frames // 2]`
-        crop, already resolved to a count).  Frame -1 where HF's path leaves the table (no frames / NaN costs)."""
+        crop, already resolved to a count).  Frame -1 where HF's path leaves the table (no frames / NaN costs).
+        ``probs`` / ``n_tok``: alternative source with the layout of the tap buffer and its number of generated
+        positions (beam search: rows gathered by beam index; ``tokens`` is then ignored)."""
         a, lib, S = self.align, _lib.load(), self.dims.max_source_positions
         eos = self.gen.eos_token_id
-        total = 0
-        for row in tokens:
-            L = len(row)
-            for i in range(n_prompt, len(row)):
-                if row[i] == eos:
-                    L = i + 1
-                    break
-            total = max(total, L)
-        n_tok = total - 1 - n_prompt          # cross-attention exists for every position but the last
+        if n_tok is None:
+            total = 0
+            for row in tokens:
+                L = len(row)
+                for i in range(n_prompt, len(row)):
+                    if row[i] == eos:
+                        L = i + 1
+                        break
+                total = max(total, L)
+            n_tok = total - 1 - n_prompt      # cross-attention exists for every position but the last
         if n_tok <= 0:
             return [[] for _ in range(B)]
         nf = [max(0, min(int(f), S)) for f in n_frames]
         p = lambda t: C.c_void_p(t.data_ptr())
         with torch.cuda.device(self.device):
             a["n_frames"][:B].copy_(torch.tensor(nf, dtype=torch.int32), non_blocking=False)
-            check(lib.tw_align_matrix(p(a["probs"]), p(a["n_frames"]), B, a["n_slots"], self.max_len, S, n_prompt, n_tok,
+            check(lib.tw_align_matrix(p(a["probs"] if probs is None else probs), p(a["n_frames"]), B, a["n_slots"], self.max_len, S, n_prompt, n_tok,
                                       int(self.gen.median_filter_width), p(a["stats"]), p(a["matrix"]), self._stream()),
                   "tw_align_matrix")
             self.stats["launches"] += 2
@@ -554,13 +558,18 @@ class WhisperEngine:
             self.stats["launches"] += steps * self.launches_per_step
             return self.tokens[:B]
 
-    def decode_beams(self, n: int, prompts: torch.Tensor, num_beams: int, timestamps: bool = True) -> torch.Tensor:
+    def decode_beams(self, n: int, prompts: torch.Tensor, num_beams: int, timestamps: bool = True,
+                     frames_keep: Optional[Sequence[int]] = None) -> torch.Tensor:
         """Beam search ($TF/generation/utils.py:3076 `_beam_search`, early_stopping=False) for n windows against the
         encoder state left by encode(): n * num_beams decode rows share the windows' cross K/V through `enc_row`, the
         decode kernels produce the raw fp32 logits of every row (tap), :class:`beam.BeamSearch` picks the
         continuations on the device, and the paged self-attention cache rows are re-gathered by beam of origin.
         prompts: int [n, 3] with the language resolved.  Returns int64 [n, T]: best hypothesis per window without
-        the prompt, right-padded with pad_token_id."""
+        the prompt, right-padded with pad_token_id.
+        ``frames_keep`` (EXPERIMENTAL, never run on a GPU — see generate()): per window the encoder frames kept for
+        the token-timestamp DTW; the alignment tap runs in every step, BeamSearch tracks HF's `beam_indices`, the
+        tapped rows of every position are gathered from the beam that produced it
+        ($TF/models/whisper/generation_whisper.py:265-303) and ``self.last_beam_frames`` receives the frames."""
         from .beam import BeamConfig, BeamSearch
         K, R = int(num_beams), n * int(num_beams)
         if R > self.max_batch:
@@ -586,7 +595,16 @@ class WhisperEngine:
             self.enc_row[:R].copy_((torch.arange(R, dtype=torch.int32) // K).to(dev))
             self.grammar.begin_index = P
             _lib.load().tw_set_pdl(0 if self.use_graphs else 1)
-            graph = self._graph_for(R) if self.use_graphs else None
+
+            want_frames = frames_keep is not None
+            if want_frames:
+                self.enable_alignment()
+            self._align_on = want_frames
+            try:
+                graph = self._graph_for(R) if self.use_graphs else None
+            except BaseException:
+                self._align_on = False
+                raise
 
             def step():
                 if graph is not None:
@@ -601,7 +619,7 @@ class WhisperEngine:
                                  pad_id=gen.pad_token_id, no_timestamps_id=gen.no_timestamps_token_id,
                                  suppress=gen.suppress_tokens, begin_suppress=gen.begin_suppress_tokens,
                                  max_initial_timestamp_index=gen.max_initial_timestamp_index, timestamps=timestamps)
-                bs = BeamSearch(cfg, prompt.to(dev))
+                bs = BeamSearch(cfg, prompt.to(dev), track_indices=want_frames)
                 L = d.dec_layers
                 ppr = self.pages_per_row
                 pool = self.kv_pool.view(L, 2, self.max_batch, ppr * PAGE, d.d_model)   # block_table is the identity layout
@@ -620,8 +638,21 @@ class WhisperEngine:
                 # the search's own accounting of the returned hypotheses (sum of processed log-probabilities, length)
                 self.last_beam = {"sum_logprob": (bs.beam_scores[:, 0] * bs.gen_len[:, 0].float() ** bs.cfg.length_penalty).cpu(),
                                   "length": bs.gen_len[:, 0].cpu()}
+                if want_frames:
+                    bi = bs.beam_indices()                                   # [n, longest generated]
+                    if P > 1:
+                        bi = torch.cat([bi[:, :1].expand(-1, P - 1), bi], dim=-1)
+                    bi = bi.masked_fill(bi == -1, 0)                         # [n, wl]
+                    wl, al = int(bi.shape[1]), self.align
+                    slots = torch.arange(al["n_slots"], device=dev)
+                    pos = torch.arange(wl, device=dev)
+                    gathered = torch.zeros(n, al["n_slots"], self.max_len, d.max_source_positions, dtype=torch.float32,
+                                           device=dev)
+                    gathered[:, :, :wl] = al["probs"][bi[:, None, :], slots[None, :, None], pos[None, None, :]]
+                    self.last_beam_frames = self.token_frames(n, [], P, frames_keep, probs=gathered, n_tok=wl - P)
                 return bs.result()
             finally:
+                self._align_on = False
                 self.enc_row.copy_(torch.arange(self.max_batch, dtype=torch.int32, device=dev))
 
     # ------------------------------------------------------------------------------------ generate
@@ -675,7 +706,9 @@ class WhisperEngine:
         ``self.last_token_ts_raw[b]`` = the padded `token_timestamps` output, no offset)."""
         gen = self.gen
         if token_timestamps:
-            if num_beams > 1:
+            if num_beams > 1 and not os.environ.get("TWB200_EXPERIMENTAL_BEAM_WORD"):
+                # the code path below exists (decode_beams(frames_keep=...)) but has never run on a GPU: it was written
+                # after the round's GPU budget was spent; tests/test_gpu_zz_word_timestamps.py holds its xfail-marked check
                 raise NotImplementedError("token timestamps with beam search are not implemented by the B200 engine")
             if num_frames is None or len(num_frames) != B:
                 raise ValueError("token_timestamps needs num_frames for every row")
@@ -725,7 +758,14 @@ class WhisperEngine:
                                 langs[b] = int(first[i])
                         prompts = torch.tensor([[gen.decoder_start_token_id, langs[b], gen.task_to_id[task]] for b in rows],
                                                dtype=torch.int32)
-                    best = self.decode_beams(n, prompts, num_beams, timestamps=bool(return_timestamps)).cpu().tolist()
+                    keep_b = None
+                    if token_timestamps:
+                        S_ = self.dims.max_source_positions
+                        left_ = [int(num_frames[b]) - seek[b] for b in rows]
+                        twice_ = len(set(left_)) == 1
+                        keep_b = [len((range(S_)[: v // 2] if twice_ else range(S_))[: v // 2]) for v in left_]
+                    best = self.decode_beams(n, prompts, num_beams, timestamps=bool(return_timestamps),
+                                             frames_keep=keep_b).cpu().tolist()
                     head = [gen.decoder_start_token_id, 0, gen.task_to_id[task]] + ([] if return_timestamps else [gen.no_timestamps_token_id])
                     toks = [[head[0], langs[b]] + head[2:] + best[i] for i, b in enumerate(rows)]
                 else:
@@ -736,7 +776,9 @@ class WhisperEngine:
                         self._align_on = False
                 self.stats["d2h_bytes"] += n * self.max_len * 4
                 tok_frames = None
-                if token_timestamps:
+                if token_timestamps and num_beams > 1:
+                    tok_frames = self.last_beam_frames
+                elif token_timestamps:
                     # weights[..., : (num_frames - seek) // 2] (_postprocess_outputs :1146-1151, :354): python slice rules
                     # and, when every active row has the same value, cropped once more up front (:322-323) — a no-op for
                     # non-negative counts, a second crop from the end for negative ones

@@ -19,6 +19,7 @@ token ids runs on the GPU engine(s).
 from __future__ import annotations
 
 import io
+import os
 import subprocess
 import wave
 from typing import Any, Dict, List, Optional, Sequence, Tuple, Union
@@ -300,7 +301,7 @@ class B200WhisperPipeline:
         task = generate_kwargs.pop("task", None) or "transcribe"
         language = generate_kwargs.pop("language", None)
         num_beams = int(generate_kwargs.pop("num_beams", None) or self.num_beams or 1)
-        if return_timestamps == "word" and num_beams > 1:
+        if return_timestamps == "word" and num_beams > 1 and not os.environ.get("TWB200_EXPERIMENTAL_BEAM_WORD"):
             raise NotImplementedError('return_timestamps="word" with beam search is not implemented by the B200 engine; '
                                       'pass generate_kwargs={"num_beams": 1}')
         if return_timestamps == "char":
