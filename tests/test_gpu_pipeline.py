@@ -106,7 +106,7 @@ def test_pipeline_short_clip_and_errors(pipes):
         p(pcm, return_timestamps=True, generate_kwargs={"task": "summarize"})
     with pytest.raises(ValueError, match="alignment_heads"):     # HF's error for a generation config without them
         p(pcm, return_timestamps="word")
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError, match="alignment_heads"):
         p(pcm, return_timestamps="word", generate_kwargs={"num_beams": 2})
     r2 = p(pcm)                      # HF default: no timestamps -> {"text"} only
     assert set(r2) == {"text"} and isinstance(r2["text"], str)

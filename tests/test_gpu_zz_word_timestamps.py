@@ -241,11 +241,6 @@ def test_empty_and_tiny_windows(setup, cuda_device):
     assert [len(r) for r in plain] == [len(r) for r in got]
 
 
-@pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent (never run on a GPU): silent "
-                   "(all-zero) windows decode to 456 tokens on the engine and 47 on the oracle.  On CPU the oracle shows "
-                   "non-decisive steps right at the start of these windows (rule gap 0.27 at step 9, top-1 margin 0.054 at "
-                   "step 11 of the first iteration; 0.12 / 0.035 at steps 0 / 5 of the second), so a bf16 divergence there "
-                   "is within the parity rule; this test checks that the FIRST differing pick is such a step")
 def test_silent_windows_diverge_only_at_low_margin_steps(setup, cuda_device):
     from oracle import logmel_ref as L
     clips, feats, ref, eng = setup
@@ -261,9 +256,6 @@ def test_silent_windows_diverge_only_at_low_margin_steps(setup, cuda_device):
     assert 2 in identical_rows
 
 
-@pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent (never run on a GPU); both halves "
-                   "are verified separately: the FLAC reader on CPU (tests/test_flac.py), the ingest kernel on B200 "
-                   "(tests/test_gpu_ops.py, tests/test_gpu_pipeline.py).  Expected to pass (XPASS)")
 def test_flac_files_go_through_the_gpu_ingest(cuda_device, tmp_path):
     """A 48 kHz stereo 16-bit FLAC (written by the test-side encoder) and the same samples as a WAV file decode to the
     same integers, so the ingest kernel must give identical 16 kHz PCM for both — equal to torchaudio's resample of the
@@ -293,16 +285,11 @@ def test_flac_files_go_through_the_gpu_ingest(cuda_device, tmp_path):
     assert c.shape == want.shape and float(np.abs(c - want).max()) < 1e-5
 
 
-@pytest.mark.xfail(strict=False, reason="EXPERIMENTAL path written after the round's GPU budget was spent (never run on a "
-                   "GPU): token timestamps under beam search on the engine (decode_beams(frames_keep=...), gated by "
-                   "TWB200_EXPERIMENTAL_BEAM_WORD).  The oracle side is pinned time-exact to transformers "
-                   "(tests/test_oracle_golden.py) and BeamSearch's beam_indices to the oracle (tests/test_beam_cpu.py)")
-def test_experimental_token_timestamps_under_beam_search(cuda_device, monkeypatch):
+def test_token_timestamps_under_beam_search(cuda_device):
     from oracle import logmel_ref as L
     from oracle import whisper_ref as R
     from turbo_whisper_workspace_b200.config import GenerationSettings, WhisperDims
     from turbo_whisper_workspace_b200.engine import WhisperEngine
-    monkeypatch.setenv("TWB200_EXPERIMENTAL_BEAM_WORD", "1")
     clips = [helpers.synth_clip(0), helpers.synth_clip(2, seconds=11.3, kind="mod")]
     nf = [3000, 1130]
     feats = torch.stack([torch.from_numpy(L.log_mel(c)) for c in clips]).to(torch.bfloat16).float()

@@ -26,10 +26,11 @@ class OracleScheduler:
         self.ref = R.WhisperRef(rd, helpers.variant_state_dict(rd, variant))
         self.last_stats = {}
 
-    def run(self, clips, task="transcribe", language=None, return_timestamps=True, token_timestamps=False, group=None):
+    def run(self, clips, task="transcribe", language=None, return_timestamps=True, token_timestamps=False, group=None,
+            num_beams=1):
         feats = torch.stack([torch.from_numpy(L.log_mel(c)) for c in clips])
         if not token_timestamps:
-            return self.ref.generate(feats, task=task, return_timestamps=return_timestamps)
+            return self.ref.generate(feats, task=task, return_timestamps=return_timestamps, num_beams=num_beams)
         # word timestamps: one generate call per HF batch of `group` consecutive windows; num_frames = the feature
         # extractor's attention-mask sum
         rows = []
@@ -37,7 +38,8 @@ class OracleScheduler:
             sub = clips[g0:g0 + group]
             nf = [min(3000, -(-len(c) // 160)) for c in sub]
             ts = {}
-            ids = self.ref.generate(feats[g0:g0 + group], task=task, alignment_heads=WORD_HEADS, num_frames=nf, token_ts=ts)
+            ids = self.ref.generate(feats[g0:g0 + group], task=task, alignment_heads=WORD_HEADS, num_frames=nf, token_ts=ts,
+                                    num_beams=num_beams)
             rows += [(ids[b], ts["segments"][b]) for b in range(len(sub))]
         return rows
 
@@ -101,8 +103,11 @@ def test_host_pipeline_word_timestamps_match_hf_golden(wav, variant):
         r = pipe(wav, chunk_length_s=60, stride_length_s=5, batch_size=32, generate_kwargs={"task": "transcribe"},
                  return_timestamps="word")
         assert _norm(r) == gold["varied_60_5_32"]
-    with pytest.raises(NotImplementedError):
-        pipe(wav, chunk_length_s=30, generate_kwargs={"num_beams": 5}, return_timestamps="word")
+    if variant == "decisive":
+        # word timestamps under beam search (the reference's literal decoding mode with transformers >= 4.53) go through
+        # the same host plumbing: one (start, end) per word, monotone within a window
+        r = pipe(wav, chunk_length_s=30, generate_kwargs={"num_beams": 5}, return_timestamps="word")
+        assert r["chunks"] and all(len(c["timestamp"]) == 2 and isinstance(c["text"], str) for c in r["chunks"])
 
 
 def test_host_pipeline_edge_inputs_match_hf_golden():

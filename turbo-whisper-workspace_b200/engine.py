@@ -566,7 +566,7 @@ class WhisperEngine:
         continuations on the device, and the paged self-attention cache rows are re-gathered by beam of origin.
         prompts: int [n, 3] with the language resolved.  Returns int64 [n, T]: best hypothesis per window without
         the prompt, right-padded with pad_token_id.
-        ``frames_keep`` (EXPERIMENTAL, never run on a GPU — see generate()): per window the encoder frames kept for
+        ``frames_keep``: per window the encoder frames kept for
         the token-timestamp DTW; the alignment tap runs in every step, BeamSearch tracks HF's `beam_indices`, the
         tapped rows of every position are gathered from the beam that produced it
         ($TF/models/whisper/generation_whisper.py:265-303) and ``self.last_beam_frames`` receives the frames."""
@@ -706,10 +706,6 @@ class WhisperEngine:
         ``self.last_token_ts_raw[b]`` = the padded `token_timestamps` output, no offset)."""
         gen = self.gen
         if token_timestamps:
-            if num_beams > 1 and not os.environ.get("TWB200_EXPERIMENTAL_BEAM_WORD"):
-                # the code path below exists (decode_beams(frames_keep=...)) but has never run on a GPU: it was written
-                # after the round's GPU budget was spent; tests/test_gpu_zz_word_timestamps.py holds its xfail-marked check
-                raise NotImplementedError("token timestamps with beam search are not implemented by the B200 engine")
             if num_frames is None or len(num_frames) != B:
                 raise ValueError("token_timestamps needs num_frames for every row")
             self.enable_alignment()

@@ -301,9 +301,6 @@ class B200WhisperPipeline:
         task = generate_kwargs.pop("task", None) or "transcribe"
         language = generate_kwargs.pop("language", None)
         num_beams = int(generate_kwargs.pop("num_beams", None) or self.num_beams or 1)
-        if return_timestamps == "word" and num_beams > 1 and not os.environ.get("TWB200_EXPERIMENTAL_BEAM_WORD"):
-            raise NotImplementedError('return_timestamps="word" with beam search is not implemented by the B200 engine; '
-                                      'pass generate_kwargs={"num_beams": 1}')
         if return_timestamps == "char":
             raise ValueError("Whisper cannot return `char` timestamps, only word level or segment level timestamps. "
                              "Use `return_timestamps='word'` or `return_timestamps=True` respectively.")

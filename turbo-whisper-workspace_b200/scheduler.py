@@ -2,8 +2,8 @@
 
 The reference has no multi-GPU code at all (single process, ``cuda:0``); HF only
 batches the windows of one file on one device.  Windows are independent units (no conditioning across
-windows in the chunked pipeline), so the path is embarrassingly parallel: weights are replicated, every
-worker gets a contiguous range of windows, and only token ids travel back — there is no collective on
+windows in the chunked pipeline), so the path is embarrassingly parallel: weights are replicated, the
+workers pull micro-batches of consecutive windows, and only token ids travel back — there is no collective on
 the data path.
 
 Two deployment shapes share the same partitioning:
@@ -72,11 +72,48 @@ def run_in_microbatches(engine, clips: Sequence[np.ndarray], task: str, language
     return rows
 
 
+MIN_MICROBATCH = 6     # below this the encoder GEMMs no longer fill the SMs (6 windows = 9000 rows = 36 row tiles)
+
+
+def balanced_microbatch(n_items: int, workers: int, max_mb: int, min_mb: int = MIN_MICROBATCH) -> int:
+    """Micro-batch size for a job of ``n_items`` windows over ``workers`` engine contexts.  A micro-batch costs about
+    the same whatever its size (the decode loop is latency-bound: ~2 x 445 steps per micro-batch), so the job should
+    use as FEW micro-batches as possible while keeping every context busy in every round:
+    rounds = ceil(n / (workers * max_mb)), size = ceil(n / (workers * rounds)) clamped to [min_mb, max_mb].
+    One 1 h file (180 windows): 1 GPU x 4 contexts -> 8 micro-batches of 23; 8 GPUs x 4 contexts -> 30 of 6."""
+    workers, max_mb = max(1, workers), max(1, max_mb)
+    min_mb = max(1, min(min_mb, max_mb))
+    if n_items <= 0:
+        return max_mb
+    rounds = -(-n_items // (workers * max_mb))
+    return max(min_mb, min(max_mb, -(-n_items // (workers * rounds))))
+
+
+class WorkQueue:
+    """One shared queue over the windows of a job: ``take`` hands out the next micro-batch of ``size`` consecutive
+    windows to whichever engine context asks first (no static per-device ranges)."""
+
+    def __init__(self, n_items: int, size: int):
+        self.n, self.pos, self.size = n_items, 0, max(1, size)
+        self.lock = threading.Lock()
+        self.handed: List[Tuple[int, int]] = []
+
+    def take(self) -> Optional[Tuple[int, int]]:
+        with self.lock:
+            if self.pos >= self.n:
+                return None
+            a, b = self.pos, min(self.n, self.pos + self.size)
+            self.pos = b
+            self.handed.append((a, b))
+            return a, b
+
+
 class WindowScheduler:
     """One process; ``contexts_per_device`` engine contexts per local GPU, each driven by its own host thread and
-    CUDA stream and sharing one copy of the weights.  Work is handed out as micro-batches of ``max_batch``
-    consecutive windows from one queue per device, so that a context's latency-bound decode overlaps another
-    context's tensor-bound encoder (and another decode) on the same GPU."""
+    CUDA stream and sharing one copy of the weights.  All contexts of all devices pull micro-batches of consecutive
+    windows (:func:`balanced_microbatch`) from ONE :class:`WorkQueue` (no static per-device ranges: a device that
+    finishes early takes the next micro-batch), so that a context's latency-bound decode overlaps another context's tensor-bound encoder (and
+    another decode) on the same GPU, and one file strong-scales over the devices."""
 
     def __init__(self, state_dict, dims, generation, devices: Sequence[Any] = ("cuda:0",), max_batch: int = 24,
                  engine_factory: Optional[Callable[..., Any]] = None, contexts_per_device: int = 1):
@@ -101,6 +138,10 @@ class WindowScheduler:
     def flat_engines(self) -> List[Any]:
         return [e for ctxs in self.engines for e in ctxs]
 
+    @property
+    def max_batch(self) -> int:
+        return self.engines[0][0].max_batch
+
     def run(self, clips: Sequence[np.ndarray], task: str = "transcribe", language: Optional[str] = None,
             return_timestamps: bool = True, num_beams: int = 1, token_timestamps: bool = False,
             group: Optional[int] = None) -> List[Any]:
@@ -109,33 +150,37 @@ class WindowScheduler:
         a row depend on the longest row of its batch, $TF/models/whisper/generation_whisper.py:241-381)."""
         t0 = time.perf_counter()
         n = len(clips)
-        mb0 = microbatch_size(self.engines[0][0].max_batch, num_beams, group) if (group and self.engines) else None
-        ranges = group_ranges(n, len(self.devices), mb0) if mb0 else partition(n, len(self.devices))
+        engines = self.flat_engines
+        if not engines or n == 0:
+            self.last_stats = {"workers": len(self.devices), "contexts_per_device": self.contexts_per_device,
+                               "microbatches": [], "seconds": time.perf_counter() - t0}
+            return []
+        cap = min(e.max_batch for e in engines)
+        # word timestamps: exactly the HF pipeline's batches; otherwise as few, equally sized micro-batches as keep
+        # every context busy
+        mb = microbatch_size(cap, num_beams, group) if group else \
+            balanced_microbatch(n, len(engines), microbatch_size(cap, num_beams), min(MIN_MICROBATCH, max(1, cap // max(1, num_beams))))
+        queue = WorkQueue(n, mb)
         results: List[Optional[List[int]]] = [None] * n
         errors: List[BaseException] = []
-        lock = threading.Lock()
-        threads = []
-        for di, (s, e) in enumerate(ranges):
-            ctxs = self.engines[di]
-            mb = mb0 or microbatch_size(ctxs[0].max_batch, num_beams)
-            queue = [(i, min(i + mb, e)) for i in range(s, e, mb)]   # micro-batches of this device, in order
+        extra = _extra(return_timestamps, num_beams, token_timestamps)
 
-            def work(engine, queue=queue):
-                try:
-                    while True:
-                        with lock:
-                            if not queue or errors:
-                                return
-                            a, b = queue.pop(0)
-                        rows = engine.generate_from_pcm(clips[a:b], task=task, language=language,
-                                                        **_extra(return_timestamps, num_beams, token_timestamps))
-                        results[a:b] = rows
-                except BaseException as ex:  # surfaced on the calling thread
-                    with lock:
-                        errors.append(ex)
+        def work(engine):
+            try:
+                while not errors:
+                    item = queue.take()
+                    if item is None:
+                        return
+                    a, b = item
+                    results[a:b] = engine.generate_from_pcm(clips[a:b], task=task, language=language, **extra)
+            except BaseException as ex:  # surfaced on the calling thread
+                errors.append(ex)
 
-            for eng in ctxs:
-                threads.append(threading.Thread(target=work, args=(eng,), daemon=True))
+        # never more host threads than micro-batches the job can produce
+        n_threads = min(len(engines), -(-n // mb))
+        # contexts of different devices first, so a small job spreads over the GPUs before it stacks contexts
+        order = [self.engines[d][c] for c in range(self.contexts_per_device) for d in range(len(self.devices))]
+        threads = [threading.Thread(target=work, args=(eng,), daemon=True) for eng in order[:n_threads]]
         if len(threads) == 1:
             threads[0].run()
         else:
@@ -146,7 +191,7 @@ class WindowScheduler:
         if errors:
             raise errors[0]
         self.last_stats = {"workers": len(self.devices), "contexts_per_device": self.contexts_per_device,
-                           "ranges": ranges, "seconds": time.perf_counter() - t0}
+                           "microbatches": list(queue.handed), "seconds": time.perf_counter() - t0}
         return [r for r in results]
 
     def close(self):
@@ -155,11 +200,21 @@ class WindowScheduler:
 
 class DistributedWindowScheduler:
     """One rank per GPU.  ``run`` must be called by every rank with the same ``clips`` (or the same count):
-    rank r processes ``partition(n, world)[r]`` on its engine; the token lists are gathered in rank order."""
+    rank r processes ``partition(n, world)[r]`` on its local engine — or on its local :class:`WindowScheduler`
+    (several engine contexts on the rank's GPU pulling from a queue over the rank's range) — and the token
+    lists are gathered in rank order on the host (``all_gather_object``; no data-path collective)."""
 
     def __init__(self, engine, rank: int, world_size: int, group=None):
         self.engine, self.rank, self.world_size, self.group = engine, rank, world_size, group
         self.last_stats: Dict[str, Any] = {}
+
+    @property
+    def devices(self):
+        return getattr(self.engine, "devices", [getattr(self.engine, "device", None)])
+
+    @property
+    def flat_engines(self) -> List[Any]:
+        return getattr(self.engine, "flat_engines", [self.engine])
 
     def local_range(self, n: int, mb: Optional[int] = None) -> Tuple[int, int]:
         return (group_ranges(n, self.world_size, mb) if mb else partition(n, self.world_size))[self.rank]
@@ -169,8 +224,13 @@ class DistributedWindowScheduler:
                   group: Optional[int] = None) -> List[Any]:
         mb = microbatch_size(self.engine.max_batch, num_beams, group) if group else None
         s, e = self.local_range(len(clips), mb)
+        if e <= s:
+            return []
+        if hasattr(self.engine, "run"):          # a local WindowScheduler (engine contexts of this rank's GPU)
+            return self.engine.run(clips[s:e], task=task, language=language, return_timestamps=return_timestamps,
+                                   num_beams=num_beams, token_timestamps=token_timestamps, group=group)
         return run_in_microbatches(self.engine, clips[s:e], task, language, return_timestamps, num_beams,
-                                   token_timestamps, group) if e > s else []
+                                   token_timestamps, group)
 
     def gather(self, local_rows: List[List[int]]) -> List[List[int]]:
         if self.world_size == 1:
@@ -186,4 +246,13 @@ class DistributedWindowScheduler:
     def run(self, clips: Sequence[np.ndarray], task: str = "transcribe", language: Optional[str] = None,
             return_timestamps: bool = True, num_beams: int = 1, token_timestamps: bool = False,
             group: Optional[int] = None) -> List[Any]:
-        return self.gather(self.run_local(clips, task, language, return_timestamps, num_beams, token_timestamps, group))
+        t0 = time.perf_counter()
+        s, e = self.local_range(len(clips), microbatch_size(self.engine.max_batch, num_beams, group) if group else None)
+        rows = self.gather(self.run_local(clips, task, language, return_timestamps, num_beams, token_timestamps, group))
+        self.last_stats = {"workers": self.world_size, "rank": self.rank, "local_range": (s, e),
+                           "seconds": time.perf_counter() - t0}
+        return rows
+
+    def close(self):
+        if hasattr(self.engine, "close"):
+            self.engine.close()
