@@ -11,9 +11,16 @@ workload: BASELINE.json configs[1] — 24 x 30 s synthetic windows per GPU per s
 value   : device-timed (CUDA events) with the PCM already resident in HBM; log-mel -> encoder -> decode -> seek loop.
 e2e     : the same work through the reference-facing callable (B200WhisperPipeline.__call__, the HF ASR pipeline
           signature) with HOST PCM: H2D of the audio, D2H of the token ids and host-side stitching inside the
-          timed region.
-The `--impl reference` arm times the reference's own CPU implementation of the path (the transformers Whisper
-classes the reference's pipeline call runs, fp32, greedy) on the box's host cores on a bounded sample.
+          timed region.  The rows of the e2e call are checked against a single-context run of the same windows.
+extras  : (own arm, unless --no-extras) the other BASELINE.json configs as extra keys of the same line:
+          `encoder` (whole encoder at batch 24 vs the tensor-pipe peak), `decode_step` (µs per greedy step alone vs the
+          HBM floor), `config3` (ONE 1 h file through the pipeline callable, sharded over the N ranks by the chunk
+          scheduler — strong scaling), `config4` (large-v3, 32 decoder layers, batch 16), `config5` (log-mel +
+          encoder-only sweep, batch 1..256).
+The `--impl reference` arm times the reference's own CPU implementation of the path: every step is ONE real call of the
+reference's `AudioProcessingPipeline.process_audio(path, task="transcribe")` (the unmodified `vocalis` package installed
+under baseline/_ref, its transformers ASR pipeline object on the CPU in fp32, greedy) on ONE 30 s window of the
+workload — nothing is extrapolated: `ms_per_step` is the wall time of that call.
 """
 from __future__ import annotations
 
@@ -29,13 +36,21 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-import numpy as np  # noqa: E402
-import torch  # noqa: E402
-
 WINDOWS_PER_GPU = 24
 WINDOW_S = 30.0
 ENC_FLOPS_PER_WINDOW = 2.2738e12
-GEMM_SHAPES = None
+METRIC = "RTFx (audio s / wall s), large-v3-turbo bf16"
+
+
+def workload_config(world: int) -> dict:
+    """The `config` object — identical for both arms (the reference arm runs a bounded sample of it, see its
+    `cpu_baseline.sample`)."""
+    return {"workload": "whisper-large-v3-turbo bf16, 24 x 30 s windows per GPU per step (BASELINE.json configs[1]); "
+                        "random-init weights (HF init, seed 0), 0.1*N(0,1) audio; greedy, timestamps, HF short-form "
+                        "seek loop",
+            "windows_per_gpu": WINDOWS_PER_GPU,
+            "parallelism": f"window-sharded x{world}, no data-path collective",
+            "l2": "working set (1.6 GB weights + >2 GB activations per step) exceeds the 126 MB L2"}
 
 
 def peaks():
@@ -45,6 +60,16 @@ def peaks():
         return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
                 "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of the two roofline kernels from THIS round's `ncu --set full` capture
+    (profiles/ncu_traffic.json, written by tools/ncu_traffic.py from the .ncu-rep); None when absent."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return json.load(open(p))
+    except (OSError, ValueError):
+        return {}
 
 
 class ClockSampler:
@@ -71,6 +96,7 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        import numpy as np
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -97,9 +123,10 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------
-# reference arm (CPU): the transformers classes the reference's pipeline call executes
+# reference arm (CPU): the reference's own process_audio call
 # ----------------------------------------------------------------------------------------------------
 def build_hf_turbo(seed: int = 0):
+    import torch
     from transformers import GenerationConfig, WhisperConfig, WhisperForConditionalGeneration
     from transformers.models.whisper.tokenization_whisper import LANGUAGES
     from oracle import whisper_ref as R
@@ -118,73 +145,158 @@ def build_hf_turbo(seed: int = 0):
     return model
 
 
-def cpu_reference_sample(model, fe, clip):
-    """Bounded sample of the reference's CPU path for ONE 30 s window: feature extraction, one encoder
-    forward and a short greedy decode through WhisperGenerationMixin.generate; extrapolated to the forwards
-    the full reference call performs for this workload (random-init weights never emit eos: language-id pass
-    + 2 seek iterations = 3 encoder forwards and 1 + 2*445 decoder forwards)."""
-    t0 = time.perf_counter()
-    feats = torch.from_numpy(fe(clip, sampling_rate=16000, return_tensors="np")["input_features"])
-    t_mel = time.perf_counter() - t0
-    with torch.no_grad():
-        t0 = time.perf_counter()
-        model.model.encoder(feats)
-        t_enc = time.perf_counter() - t0
+def build_reference_callable():
+    """-> (call(path) -> result dict, kind, description).
 
-        def gen(n):
-            t = time.perf_counter()
-            model.generate(input_features=feats, return_timestamps=True, task="transcribe", num_beams=1,
-                           do_sample=False, max_new_tokens=n)
-            return time.perf_counter() - t
-        t_a, t_b = gen(4), gen(20)
-    t_dec = max((t_b - t_a) / 16.0, 1e-6)
-    total = t_mel + 3 * t_enc + 891 * t_dec
-    return {"t_mel": t_mel, "t_enc": t_enc, "t_dec_step": t_dec, "t_window_extrapolated": total,
-            "measured_s": t_mel + t_enc + t_a + t_b}
+    The reference's entry point for this path is `vocalis.core.audio_pipeline.AudioProcessingPipeline.process_audio`
+    (ref:vocalis/core/audio_pipeline.py:567-688 -> transcribe :323-369).  It is imported UNMODIFIED from
+    baseline/_ref (installed with `pip install --no-deps --target baseline/_ref <copy of /root/reference>`, DESIGN.md §6;
+    /root/reference itself is used when present and baseline/_ref is not).  What has to be supplied around it offline
+    (SURVEY.md §8c recipe): empty stub modules for its optional imports (librosa, soundfile, sherpa_onnx, pydub), a WAV
+    reader in place of the `ffmpeg` binary HF's `ffmpeg_read` shells out to, diarization / LLM post-steps off
+    ("diarization off" is BASELINE.json configs[0]), and the `transcription_model` object itself — the reference would
+    download openai weights; here it is the same `transformers.pipeline("automatic-speech-recognition", ...)`
+    construction over the random-init large-v3-turbo model on the CPU in fp32, `num_beams = 1` (greedy, the north
+    star's mode).  Without the package (neither path exists) the same pipeline object is called with the reference's
+    literal keyword arguments (:351-358) and the arm says kind = "port"."""
+    import io
+    import types
+    import wave
+    import importlib.machinery
+    import numpy as np
+    import torch
+    os.environ.setdefault("HF_HUB_OFFLINE", "1")
+    from transformers import WhisperFeatureExtractor, pipeline
+    import transformers.pipelines.automatic_speech_recognition as asr
+    import helpers
+
+    def wav_read(payload, sampling_rate):
+        with wave.open(io.BytesIO(payload)) as w:
+            assert w.getframerate() == sampling_rate and w.getnchannels() == 1 and w.getsampwidth() == 2
+            return np.frombuffer(w.readframes(w.getnframes()), np.int16).astype(np.float32) / 32768.0
+    asr.ffmpeg_read = wav_read
+    model = build_hf_turbo(0)
+    pipe = pipeline("automatic-speech-recognition", model=model, tokenizer=helpers.build_tokenizer(),
+                    feature_extractor=WhisperFeatureExtractor(feature_size=128), device="cpu", dtype=torch.float32)
+    pipe.generation_config.num_beams = 1
+    src = None
+    for cand in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if os.path.isdir(os.path.join(cand, "vocalis", "core")):
+            src = cand
+            break
+    if src is None:
+        def call(path):
+            return pipe(path, chunk_length_s=60, batch_size=32, stride_length_s=5, generate_kwargs={"task": "transcribe"},
+                        return_timestamps=True)
+        return call, pipe, "port", ("transformers ASR pipeline object called with the reference's literal transcribe() "
+                                    "keyword arguments (vocalis package not present)")
+    for m in ("librosa", "soundfile", "sherpa_onnx", "pydub"):
+        if m not in sys.modules:
+            stub = types.ModuleType(m)
+            stub.__spec__ = importlib.machinery.ModuleSpec(m, None)
+            sys.modules[m] = stub
+    if not hasattr(sys.modules["pydub"], "AudioSegment"):
+        sys.modules["pydub"].AudioSegment = type("AudioSegment", (), {})
+    if src not in sys.path:
+        sys.path.insert(0, src)
+    import vocalis.core.audio_pipeline as ap
+    ap.LLM_AVAILABLE = False
+    p = ap.AudioProcessingPipeline()
+    p.transcription_model = pipe
+    p.diarize = lambda *a, **k: []
+
+    def call(path):
+        return p.process_audio(path, task="transcribe")
+    return call, pipe, "reference", (f"vocalis.core.audio_pipeline.AudioProcessingPipeline.process_audio from {src} "
+                                     "(unmodified), transcription_model = transformers ASR pipeline, CPU fp32, greedy")
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return 0
-    from transformers import WhisperFeatureExtractor
+    import tempfile
+    import numpy as np
+    import torch
     import helpers
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    model = build_hf_turbo(0)
-    fe = WhisperFeatureExtractor(feature_size=128)
-    clip = helpers.synth_clip(0)
-    samples = []
-    for i in range(args.warmup + args.steps):
-        s = cpu_reference_sample(model, fe, clip)
-        if i >= args.warmup:
-            samples.append(s)
-    t = float(np.mean([s["t_window_extrapolated"] for s in samples]))
+    call, pipe, kind, what = build_reference_callable()
+    tmp = tempfile.mkdtemp(prefix="twb200_ref_")
+
+    def wav_for(i):
+        path = os.path.join(tmp, f"w{i}.wav")
+        helpers.write_wav16(path, helpers.synth_clip(i))
+        return path
+    # warm-up: untimed SHORT calls of the same pipeline object (lazy imports, thread pool, allocator); a full call
+    # costs ~20 s of CPU and warms nothing more
+    for i in range(args.warmup):
+        pipe(wav_for(0), chunk_length_s=60, stride_length_s=5, batch_size=32, return_timestamps=True,
+             generate_kwargs={"task": "transcribe", "max_new_tokens": 4})
+    times, chunks, t_begin = [], None, time.perf_counter()
+    for i in range(args.steps):
+        path = wav_for(i % WINDOWS_PER_GPU)
+        t0 = time.perf_counter()
+        res = call(path)
+        times.append(time.perf_counter() - t0)
+        if "error" in res:
+            raise SystemExit(f"bench.py: the reference call failed: {res['error']}")
+        chunks = len(res.get("segments", res.get("chunks", [])))
+        if time.perf_counter() - t_begin > args.reference_budget_s:
+            break
+    t = float(np.mean(times))
     rtfx = WINDOW_S / t
-    sample = ("per step: 1 window of config[1] on the host CPU — HF feature extractor + 1 encoder forward + greedy "
-              "generate(max_new_tokens=4 and 20), extrapolated to the 3 encoder + 891 decoder forwards the full "
-              f"reference call runs per 30 s window; t_enc={samples[-1]['t_enc']:.2f}s t_dec_step="
-              f"{samples[-1]['t_dec_step'] * 1e3:.1f}ms")
-    line = {"impl": "reference", "metric": "RTFx (audio s / wall s), large-v3-turbo bf16",
-            "value": rtfx, "unit": "x realtime", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": t * 1e3 * WINDOWS_PER_GPU, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "whisper-large-v3-turbo bf16, 24 x 30 s windows per GPU per step (BASELINE.json "
-                                   "configs[1]); random-init weights (HF init, seed 0), 0.1*N(0,1) audio; greedy, "
-                                   "timestamps, HF short-form seek loop",
-                       "windows_per_gpu": WINDOWS_PER_GPU,
-                       "reference_arm": "the reference's own CPU implementation of the path (transformers Whisper "
-                                        "classes, fp32, greedy), rank 0 only, one bounded window sample per step"},
-            "cpu_baseline": {"value": rtfx, "unit": "x realtime", "cores": torch.get_num_threads(), "kind": "port",
+    sample = (f"{len(times)} timed call(s), each ONE full reference call on ONE 30 s window of the workload (windows "
+              f"0..{len(times) - 1} of the 24); {what}; per call 3 encoder + 891 decoder forwards (language id + 2 seek "
+              f"iterations to max_length; random-init weights never emit eos); wall {min(times):.1f}-{max(times):.1f} s "
+              f"per call; nothing extrapolated")
+    line = {"impl": "reference", "metric": METRIC, "value": rtfx, "unit": "x realtime", "n_gpus": args.gpus,
+            "steps": len(times), "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(world),
+            "cpu_baseline": {"value": rtfx, "unit": "x realtime", "cores": torch.get_num_threads(), "kind": kind,
                              "sample": sample},
             "e2e": {"value": rtfx, "unit": "x realtime", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "steps_requested": args.steps, "chunks_last_call": chunks,
             "host": {"cpu_count": cores, "torch_threads": torch.get_num_threads(), "torch": torch.__version__}}
     emit(line)
     return 0
 
 
+def cpu_baseline_subprocess(budget_s: float):
+    """Own arm, N = 1: the reference arm's measurement (one real call) in a child process with the GPU hidden."""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    try:
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1",
+                              "--warmup", "1"], env=env, capture_output=True, text=True, timeout=budget_s)
+        for ln in reversed(out.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)["cpu_baseline"]
+        return {"value": None, "unit": "x realtime", "cores": os.cpu_count(), "kind": "reference",
+                "sample": "reference child process printed no result: " + out.stderr[-300:]}
+    except subprocess.TimeoutExpired:
+        return {"value": None, "unit": "x realtime", "cores": os.cpu_count(), "kind": "reference",
+                "sample": f"reference child process exceeded {budget_s:.0f} s"}
+
+
 # ----------------------------------------------------------------------------------------------------
 # own arm
 # ----------------------------------------------------------------------------------------------------
+def cuda_timed(fn, iters, warm=1):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
 def gemm_roofline_probe(eng, B, iters=5):
     """Average launch duration of the dominant encoder kernel (K5 tcgen05 GEMM) on the encoder's own four
     shapes, CUDA events on the launching stream; algorithmic FLOPs = 2*M*N*K per launch."""
@@ -200,17 +312,11 @@ def gemm_roofline_probe(eng, B, iters=5):
         (lambda: ops.gemm(xn, w[p + "fc1_w"], rows=M, bias=w[p + "fc1_b"], act=1, out=hid), 2.0 * M * F * D),
         (lambda: ops.gemm(hid, w[p + "fc2_w"], rows=M, bias=w[p + "fc2_b"], resid=x, resid_ld=D, out=x), 2.0 * M * D * F),
     ]
-    for fn, _ in launches:
-        fn()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(iters):
+
+    def all_four():
         for fn, _ in launches:
             fn()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / (iters * len(launches))
+    ms = cuda_timed(all_four, iters) / len(launches)
     flops = sum(f for _, f in launches) / len(launches)
     return ms, flops
 
@@ -220,6 +326,7 @@ def cross_attn_roofline_probe(eng, B, iters=20):
     the engine's own head-major K/V, CUDA events on the launching stream.  Algorithmic bytes per launch =
     B * 2 (K,V) * 1500 * 1280 * 2 B (7.68 MB per sequence-layer)."""
     import ctypes as C
+    import torch
     from turbo_whisper_workspace_b200 import _lib
     lib = _lib.load()
     d = eng.dims
@@ -228,30 +335,101 @@ def cross_attn_roofline_probe(eng, B, iters=20):
     p = lambda t: C.c_void_p(t.data_ptr())
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     L = d.dec_layers
+    it = [0]
 
-    def launch(i):
+    def launch():
+        i = it[0] % L          # rotate layers: 4 x 184 MB > L2
+        it[0] += 1
         kptr = C.c_void_p(eng.ckv.data_ptr() + ((i * 2 + 0) * H) * blk * 2)
         vptr = C.c_void_p(eng.ckv.data_ptr() + ((i * 2 + 1) * H) * blk * 2)
         _lib.check(lib.tw_dec_cross_attn(p(eng.dq), p(eng.datt), kptr, vptr, 64, S * 64, blk, None, S, B, H,
                                          eng.cross_splits, p(eng.cross_part), p(eng.cross_cnt), st), "cross_attn")
-    for i in range(L):
-        launch(i)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for it in range(iters):
-        launch(it % L)          # rotate layers: 4 x 184 MB > L2
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / iters, B * 2.0 * S * D * 2
+    return cuda_timed(launch, iters, warm=L), B * 2.0 * S * D * 2
+
+
+def decode_step_probe(eng, B, steps=256):
+    """µs per greedy decode step of ONE context alone (CUDA-graph replays back to back, CUDA events) and the
+    algorithmic HBM bytes a step has to move: decoder weights once + LM head + cross K/V of the B rows
+    (+ the self-attention cache, averaged over the positions visited)."""
+    import torch
+    d, gen = eng.dims, eng.gen
+    D, F, L, S = d.d_model, d.ffn, d.dec_layers, d.max_source_positions
+    prompts = torch.tensor([[gen.decoder_start_token_id, 50259, gen.task_to_id["transcribe"]]] * B, dtype=torch.int32)
+    with torch.cuda.device(eng.device):
+        eng.decode(B, prompts, n_steps=1)
+        graph = eng._graph_for(B)
+        torch.cuda.synchronize()
+        steps = min(steps, eng.max_len - 4)
+        ms = cuda_timed(graph.replay, steps, warm=0)
+    weights = L * (4 * D * D + 4 * D * D + 2 * D * F) * 2
+    lm_head = d.vocab * D * 2
+    cross = B * L * 2 * S * D * 2
+    self_kv = B * L * 2 * (steps / 2.0) * D * 2
+    return ms * 1e3, float(weights + lm_head + cross + self_kv)
+
+
+def synth_state_dict_on_device(dims, device, seed=0):
+    """HF-layout random-init weights generated ON the device (N(0, 0.02) like WhisperPreTrainedModel._init_weights,
+    zero biases, unit LayerNorm): the 1.5 B parameters of large-v3 take a minute on host cores."""
+    import torch
+    import helpers
+    g = torch.Generator(device=device).manual_seed(seed)
+    D, F, V = dims.d_model, dims.ffn, dims.vocab
+    sd = {}
+
+    def lin(name, o, i, bias=True):
+        sd[name + ".weight"] = torch.randn(o, i, generator=g, device=device) * 0.02
+        if bias:
+            sd[name + ".bias"] = torch.zeros(o, device=device)
+
+    def ln(name):
+        sd[name + ".weight"] = torch.ones(D, device=device)
+        sd[name + ".bias"] = torch.zeros(D, device=device)
+
+    def attn(p):
+        lin(p + "q_proj", D, D)
+        lin(p + "k_proj", D, D, bias=False)
+        lin(p + "v_proj", D, D)
+        lin(p + "out_proj", D, D)
+    e = "model.encoder."
+    sd[e + "conv1.weight"] = torch.randn(D, dims.n_mels, 3, generator=g, device=device) * 0.02
+    sd[e + "conv1.bias"] = torch.zeros(D, device=device)
+    sd[e + "conv2.weight"] = torch.randn(D, D, 3, generator=g, device=device) * 0.02
+    sd[e + "conv2.bias"] = torch.zeros(D, device=device)
+    sd[e + "embed_positions.weight"] = helpers.sinusoids(dims.max_source_positions, D).to(device)
+    for i in range(dims.enc_layers):
+        p = f"{e}layers.{i}."
+        attn(p + "self_attn.")
+        ln(p + "self_attn_layer_norm")
+        lin(p + "fc1", F, D)
+        lin(p + "fc2", D, F)
+        ln(p + "final_layer_norm")
+    ln(e + "layer_norm")
+    dd = "model.decoder."
+    sd[dd + "embed_tokens.weight"] = torch.randn(V, D, generator=g, device=device) * 0.02
+    sd[dd + "embed_positions.weight"] = torch.randn(dims.max_target_positions, D, generator=g, device=device) * 0.02
+    for i in range(dims.dec_layers):
+        p = f"{dd}layers.{i}."
+        attn(p + "self_attn.")
+        ln(p + "self_attn_layer_norm")
+        attn(p + "encoder_attn.")
+        ln(p + "encoder_attn_layer_norm")
+        lin(p + "fc1", F, D)
+        lin(p + "fc2", D, F)
+        ln(p + "final_layer_norm")
+    ln(dd + "layer_norm")
+    return sd
 
 
 def run_own(args, rank, world, local_rank):
-    import threading
+    import numpy as np
+    import torch
     import torch.distributed as dist
     import helpers
     from turbo_whisper_workspace_b200.config import WhisperDims
+    from turbo_whisper_workspace_b200.engine import WhisperEngine
     from turbo_whisper_workspace_b200.pipeline import B200WhisperPipeline
+    from turbo_whisper_workspace_b200.scheduler import DistributedWindowScheduler
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the B200 engine has no CPU path (use --impl reference)")
@@ -277,6 +455,12 @@ def run_own(args, rank, world, local_rank):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(*vals):
+        t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t]
 
     def stats_sum(key):
         return sum(e.stats.get(key, 0) for e in engines)
@@ -341,32 +525,44 @@ def run_own(args, rank, world, local_rank):
     clocks = sampler.stop()
     h2d = (stats_sum("h2d_bytes") - h0) // max(K, 1)
     d2h = (stats_sum("d2h_bytes") - dd0) // max(K, 1)
+    e2e_rows = list(pipe.last_token_rows)
 
-    # ---- rooflines of the two dominant kernels, measured live
+    # ---- output check: the e2e rows (4 contexts, host path) == ONE context decoding the same 24 windows
+    single = engines[0].generate_from_pcm(clips) if engines[0].stream is None else None
+    if single is None:
+        with torch.cuda.stream(engines[0].stream):
+            single = engines[0].generate_from_pcm(clips)
+    rows_ok = len(e2e_rows) == K * B and all(e2e_rows[i] == single[i % B] for i in range(len(e2e_rows)))
+    resident_ok = rows is not None and rows == single
+
+    # ---- rooflines of the dominant kernels, measured live
     pk = peaks()
     eng0 = engines[0]
-    ca_ms, ca_bytes = cross_attn_roofline_probe(eng0, B)
-    gemm_ms, gemm_flops = gemm_roofline_probe(eng0, B)
+    stream_ctx = torch.cuda.stream(eng0.stream) if eng0.stream is not None else torch.cuda.stream(torch.cuda.current_stream())
+    with stream_ctx:
+        eng0.load_pcm(clips)
+        eng0.features(B)
+        enc_ms = cuda_timed(lambda: eng0.encode(B), iters=3, warm=1)
+        ca_ms, ca_bytes = cross_attn_roofline_probe(eng0, B)
+        gemm_ms, gemm_flops = gemm_roofline_probe(eng0, B)
+        step_us, step_bytes = decode_step_probe(eng0, B)
 
-    t = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    t_dev, t_e2e = float(t[0]), float(t[1])
+    t_dev, t_e2e = max_over_ranks(t_dev, t_e2e)
     audio_s = WINDOW_S * B * world * K
+    traffic = ncu_traffic()
+    line = None
     if rank == 0:
         ca_gbs = ca_bytes / (ca_ms * 1e-3) / 1e9
         gemm_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12
+        enc_flops = B * (ENC_FLOPS_PER_WINDOW + dims.dec_layers * 4 * 1500 * 1280 ** 2)
+        enc_tf = enc_flops / (enc_ms * 1e-3) / 1e12
         line = {
-            "metric": "RTFx (audio s / wall s), large-v3-turbo bf16", "value": audio_s / t_dev, "unit": "x realtime",
+            "metric": METRIC, "value": audio_s / t_dev, "unit": "x realtime",
             "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": t_dev / K * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "whisper-large-v3-turbo bf16, 24 x 30 s windows per GPU per step (BASELINE.json "
-                                   "configs[1]); random-init weights (HF init, seed 0), 0.1*N(0,1) audio; greedy, "
-                                   "timestamps, HF short-form seek loop",
-                       "windows_per_gpu": B, "parallelism": f"window-sharded x{world}, no data-path collective",
-                       "contexts_per_gpu": len(engines),
-                       "l2": "working set (1.6 GB weights + >2 GB activations per step) exceeds the 126 MB L2",
-                       "decoder_steps_per_step": dec_steps // K, "encoder_windows_per_step": enc_windows // K},
+            "config": workload_config(world),
+            "detail": {"contexts_per_gpu": len(engines), "decoder_steps_per_step": dec_steps // K,
+                       "encoder_windows_per_step": enc_windows // K},
             "e2e": {"value": audio_s / t_e2e, "unit": "x realtime", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": t_e2e / K * 1e3,
                     "api": "B200WhisperPipeline.__call__(np.ndarray[steps*720 s], chunk_length_s=30, stride_length_s=0, "
@@ -376,33 +572,135 @@ def run_own(args, rank, world, local_rank):
             "roofline": {"bound": "hbm", "kernel": "decode_attn_kernel (cross-attention over the encoder K/V; largest "
                                                    "single kernel of a step by time)",
                          "achieved": ca_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ca_gbs / pk["hbm_gbs"],
-                         "traffic": 189.84e6 if B == 24 else None,   # dram read+write per launch, ncu --set full (profiles/r1e_summary.md)
+                         "traffic": traffic.get("decode_attn_kernel"), "traffic_source": traffic.get("source"),
                          "peak_source": pk["source"], "bytes_per_launch": ca_bytes, "ms_per_launch": ca_ms},
-            "roofline_encoder_gemm": {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05; encoder qkv/out/fc1/fc2 "
+            "roofline_encoder_gemm": {"bound": "tensor", "kernel": "gemm_bf16_2cta_kernel (tcgen05; encoder qkv/out/fc1/fc2 "
                                       "shapes, fused bias/GELU/residual)", "achieved": gemm_tf,
                                       "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": gemm_tf / pk["bf16_tflops"],
-                                      "traffic": 332.7e6 if B == 24 else None,   # qkv-shape launch, ncu (profiles/r1e_summary.md)
+                                      "traffic": traffic.get("gemm_bf16_2cta_kernel"),
+                                      "traffic_source": traffic.get("source"),
                                       "peak_source": pk["source"] + " burst",
                                       "flops_per_launch": gemm_flops, "ms_per_launch": gemm_ms},
+            "encoder": {"bound": "tensor", "what": "whole encoder pass at batch 24 (conv stem, 32 layers incl. attention "
+                        "and LayerNorm, final LN, cross-K/V GEMM), one context alone", "ms": enc_ms,
+                        "achieved": enc_tf, "unit": "TFLOP/s", "frac_burst": enc_tf / pk["bf16_tflops"],
+                        "frac_sustained": enc_tf / pk["bf16_tflops_sustained"], "flops": enc_flops},
+            "decode_step": {"bound": "hbm", "what": "one greedy step at 24 rows, one context alone (graph replays)",
+                            "us": step_us, "bytes": step_bytes, "floor_us": step_bytes / pk["hbm_gbs"] / 1e3,
+                            "frac": step_bytes / pk["hbm_gbs"] / 1e3 / step_us,
+                            "launches_per_step": eng0.launches_per_step,
+                            "in_bench_us": max(0.0, t_dev / K * 1e6 - (enc_windows / K / B) * enc_ms * 1e3) / max(1, dec_steps // K)},
             "output_check": {"chunks": len(result["chunks"]) if isinstance(result, dict) else None,
-                             "tokens_first_row": len(rows[0]) if rows else None},
+                             "rows": len(e2e_rows), "tokens_first_row": len(single[0]) if single else None,
+                             "e2e_rows_equal_single_context": bool(rows_ok),
+                             "resident_rows_equal_single_context": bool(resident_ok)},
         }
+
+    # ---- extras: the other BASELINE.json configs
+    if not args.no_extras:
+        extras = run_extras(args, rank, world, dev, pipe, dims, tok, barrier, max_over_ranks, pk)
+        if line is not None:
+            line.update(extras)
+    if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            from transformers import WhisperFeatureExtractor
-            cores = os.cpu_count() or 1
-            torch.set_num_threads(cores)
-            s = cpu_reference_sample(build_hf_turbo(0), WhisperFeatureExtractor(feature_size=128), helpers.synth_clip(0))
-            line["cpu_baseline"] = {
-                "value": WINDOW_S / s["t_window_extrapolated"], "unit": "x realtime", "cores": torch.get_num_threads(),
-                "kind": "port",
-                "sample": (f"1 x 30 s window on the host CPU: HF feature extractor + 1 encoder forward + greedy "
-                           f"generate(max_new_tokens=4, 20) measured in {s['measured_s']:.1f} s, extrapolated to the "
-                           f"3 encoder + 891 decoder forwards of the full reference call (t_enc={s['t_enc']:.2f}s, "
-                           f"t_dec_step={s['t_dec_step'] * 1e3:.1f}ms)")}
+            line["cpu_baseline"] = cpu_baseline_subprocess(args.reference_budget_s)
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+    if rank == 0 and not (rows_ok and resident_ok):
+        sys.stderr.write("bench.py: OUTPUT CHECK FAILED — multi-context rows differ from the single-context rows\n")
+        return 1
     return 0
+
+
+def run_extras(args, rank, world, dev, pipe, dims, tok, barrier, max_over_ranks, pk):
+    import numpy as np
+    import torch
+    import helpers
+    from turbo_whisper_workspace_b200.config import WhisperDims
+    from turbo_whisper_workspace_b200.engine import WhisperEngine
+    from turbo_whisper_workspace_b200.pipeline import B200WhisperPipeline
+    from turbo_whisper_workspace_b200.scheduler import DistributedWindowScheduler
+    out = {}
+    # ---- config 3: ONE 1 h file through the pipeline callable, windows sharded over the ranks by the chunk scheduler
+    hour = np.concatenate([helpers.synth_clip(1000 + i) for i in range(120)])          # 3600 s, same on every rank
+    dpipe = pipe if world == 1 else B200WhisperPipeline(
+        None, dims, tok, scheduler=DistributedWindowScheduler(pipe.scheduler, rank, world))
+    c3 = {"what": "one 1 h synthetic file through B200WhisperPipeline.__call__ (host PCM in, dict with chunk-level "
+                  "timestamps out); the windows of the ONE job are sharded over the ranks' engine contexts by the "
+                  "chunk scheduler (strong scaling), token ids gathered on the host", "n_gpus": world}
+    for name, cl, st, bs in (("30_5", 30, 5, 24), ("60_5_literal", 60, 5, 512)):
+        ckw = dict(chunk_length_s=cl, stride_length_s=st, batch_size=bs, generate_kwargs={"task": "transcribe"},
+                   return_timestamps=True)
+        dpipe(hour[:16000 * 400], **ckw)                  # warm-up (graphs of the micro-batch size, call path)
+        dpipe(hour, **ckw)
+        barrier()
+        t0 = time.perf_counter()
+        r = dpipe(hour, **ckw)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        (dt,) = max_over_ranks(dt)
+        rec = {"windows": dpipe.last_stats.get("windows"), "seconds": dt, "rtfx": 3600.0 / dt,
+               "chunks": len(r["chunks"]), "last_timestamp": list(r["chunks"][-1]["timestamp"]) if r["chunks"] else None,
+               "microbatches": [b - a for a, b in pipe.scheduler.last_stats.get("microbatches", [])][:8]}
+        if world > 1:
+            barrier()
+            if rank == 0:       # the same job on rank 0 alone: the gathered result must be identical
+                rec["equal_to_one_gpu"] = bool(pipe(hour, **ckw) == r)
+            barrier()
+        c3[name] = rec
+    out["config3"] = c3
+    del hour
+
+    # ---- config 4: large-v3 (32 decoder layers), batch 16 per GPU, decoder-heavy greedy decode
+    torch.cuda.empty_cache()
+    d4 = WhisperDims.large_v3()
+    e4 = WhisperEngine(d4, synth_state_dict_on_device(d4, dev, 0), device=dev, max_batch=16)
+    c4clips = [helpers.synth_clip(2000 + rank * 16 + i) for i in range(16)]
+    e4.generate_from_pcm(c4clips)
+    barrier()
+    s0, t0 = e4.stats["dec_steps"], time.perf_counter()
+    rows4 = e4.generate_from_pcm(c4clips)
+    torch.cuda.synchronize()
+    dt4 = time.perf_counter() - t0
+    steps4 = e4.stats["dec_steps"] - s0
+    step_us4, step_bytes4 = decode_step_probe(e4, 16)
+    (dt4,) = max_over_ranks(dt4)
+    out["config4"] = {"what": "whisper-large-v3 dims (32 decoder layers), bf16, 16 windows per GPU in one batch, greedy "
+                              "with timestamps, random-init (decodes to max_length: decoder-heavy); one engine context",
+                      "n_gpus": world, "seconds": dt4, "rtfx": 16 * WINDOW_S * world / dt4, "decoder_steps": steps4,
+                      "tokens_first_rows": [len(r) for r in rows4[:4]],
+                      "decode_step": {"us": step_us4, "bytes": step_bytes4, "floor_us": step_bytes4 / pk["hbm_gbs"] / 1e3,
+                                      "frac": step_bytes4 / pk["hbm_gbs"] / 1e3 / step_us4,
+                                      "launches_per_step": e4.launches_per_step}}
+    del e4
+    torch.cuda.empty_cache()
+
+    # ---- config 5: log-mel + encoder-only sweep (rank 0; the other ranks wait at the barrier)
+    if rank == 0:
+        batches = [1, 2, 4, 8, 16, 24, 32, 64, 128, 256]
+        e5 = WhisperEngine(dims, None, device=dev, max_batch=24, max_enc_batch=max(batches),
+                           shared_weights=pipe.scheduler.flat_engines[0].w)
+        base = [helpers.synth_clip(3000 + i) for i in range(8)]
+        sweep = []
+        for Bs in batches:
+            e5.load_pcm([base[i % 8] for i in range(Bs)])
+            torch.cuda.synchronize()
+            mel_ms = cuda_timed(lambda: e5.features(Bs), iters=10 if Bs <= 32 else 4, warm=2)
+            enc_ms = cuda_timed(lambda: e5.encode(Bs), iters=3 if Bs <= 32 else 1, warm=1)
+            mel_bytes = Bs * (480000 * 4 + 128 * 3000 * 2)
+            enc_flops = Bs * (ENC_FLOPS_PER_WINDOW + dims.dec_layers * 4 * 1500 * 1280 ** 2)
+            sweep.append({"batch": Bs, "logmel_ms": round(mel_ms, 4), "logmel_GBps": round(mel_bytes / mel_ms / 1e6, 1),
+                          "logmel_frac_hbm": round(mel_bytes / mel_ms / 1e6 / pk["hbm_gbs"], 3),
+                          "encoder_ms": round(enc_ms, 3), "encoder_TFLOPs": round(enc_flops / enc_ms / 1e9, 1),
+                          "encoder_frac_burst": round(enc_flops / enc_ms / 1e9 / pk["bf16_tflops"], 3)})
+        out["config5"] = {"what": "log-mel front end (fp32 PCM in, bf16 time-major features out: 2.688 MB / window) and "
+                                  "encoder-only pass (2.2738 TFLOP + cross-K/V GEMM per window), one context, CUDA events",
+                          "sweep": sweep}
+        del e5
+        torch.cuda.empty_cache()
+    barrier()
+    return out
 
 
 _RESULT_FD = None
@@ -432,12 +730,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the config3 / config4 / config5 extra keys")
     ap.add_argument("--contexts", type=int, default=4, help="engine contexts (streams) per GPU sharing one weight copy")
+    ap.add_argument("--reference-budget-s", type=float, default=480.0,
+                    help="reference arm: stop after the call that crosses this wall-clock budget (steps reports the calls made)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
+        os.environ["CUDA_VISIBLE_DEVICES"] = ""       # the reference arm is the CPU path; set before torch is imported
         return run_reference(args, rank, world)
     if args.warmup < 3:
         args.warmup = 3

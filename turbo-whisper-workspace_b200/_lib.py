@@ -6,7 +6,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtwb200.so")
+# TWB200_LIB: another build of the same library (kernel A/B variants made by tools/build_variants.sh); the default is the
+# in-tree library __graft_entry__.build() makes
+LIB_PATH = os.environ.get("TWB200_LIB") or os.path.join(_HERE, "libtwb200.so")
 
 c_void_p, c_int32, c_int64, c_float, c_size_t = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
 

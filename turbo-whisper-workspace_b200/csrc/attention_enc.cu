@@ -69,6 +69,12 @@ TW_DEVINL uint32_t ex2_bf16x2(uint32_t x) {
     asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(y) : "r"(x));
     return y;
 }
+// three-input maximum (FMNMX3, sm_100): halves the instruction count of the row-maximum pass
+TW_DEVINL float max3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
 TW_DEVINL float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -326,6 +332,16 @@ attention_enc_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
             float mx = -INFINITY;
             if (full) {
                 float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // independent chains
+#ifdef ATTN_MAX3
+#pragma unroll
+                for (int i = 0; i < HK; i += 8) {   // 64 keys: 32 three-input maxima instead of 64 two-input ones
+                    m4[0] = max3(m4[0], __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+                    m4[1] = max3(m4[1], __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+                    m4[2] = max3(m4[2], __uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
+                    m4[3] = max3(m4[3], __uint_as_float(v[i + 6]), __uint_as_float(v[i + 7]));
+                }
+                mx = fmaxf(max3(m4[0], m4[1], m4[2]), m4[3]);
+#else
 #pragma unroll
                 for (int i = 0; i < HK; i += 4) {
                     m4[0] = fmaxf(m4[0], __uint_as_float(v[i]));
@@ -334,6 +350,7 @@ attention_enc_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
                     m4[3] = fmaxf(m4[3], __uint_as_float(v[i + 3]));
                 }
                 mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+#endif
             } else {
 #pragma unroll
                 for (int i = 0; i < HK; ++i)
@@ -480,12 +497,11 @@ extern "C" int tw_attention_enc(const void* qkv_bf16, void* out_bf16, int32_t ba
         return 1;
     Params p;
     p.T = seq; p.H = heads; p.D = D; p.out_ld = out_ld; p.out = (__nv_bfloat16*)out_bf16; p.dbg = g_attn_dbg;
-    static bool attr_set[64] = {};
-    const int dev = current_device();
-    if (!attr_set[dev]) {
+    static std::atomic<unsigned long long> attr_done{0};
+    if (device_needs_setup(attr_done)) {
         TW_CUDA_CHECK(cudaFuncSetAttribute(attention_enc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(1)));
         TW_CUDA_CHECK(cudaFuncSetAttribute(attention_enc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(2)));
-        attr_set[dev] = true;
+        mark_device_done(attr_done);
     }
     if (g_attn_tiles == 1) {
         dim3 grid((seq + BQ - 1) / BQ, heads, batch);

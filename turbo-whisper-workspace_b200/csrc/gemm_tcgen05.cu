@@ -596,12 +596,11 @@ extern "C" int tw_gemm_bf16(const tw_gemm_args* a, void* stream) {
             gemm_bf16_2cta_kernel<false, false, 0>, gemm_bf16_2cta_kernel<false, false, 1>, gemm_bf16_2cta_kernel<false, true, 0>,
             gemm_bf16_2cta_kernel<false, true, 1>,  gemm_bf16_2cta_kernel<true, false, 0>,  gemm_bf16_2cta_kernel<true, false, 1>,
             gemm_bf16_2cta_kernel<true, true, 0>,   gemm_bf16_2cta_kernel<true, true, 1>};
-        static bool attr2_set[64] = {};
-        const int dev2 = current_device();
-        if (!attr2_set[dev2]) {
+        static std::atomic<unsigned long long> attr2_done{0};
+        if (device_needs_setup(attr2_done)) {
             for (int i = 0; i < 8; ++i)
                 TW_CUDA_CHECK(cudaFuncSetAttribute(kernels2[i], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
-            attr2_set[dev2] = true;
+            mark_device_done(attr2_done);
         }
         const int clusters = p.num_tiles < sms / 2 ? p.num_tiles : sms / 2;
         const kern2_t k2 = kernels2[(p.out_f32 ? 4 : 0) + (p.resid ? 2 : 0) + (p.act ? 1 : 0)];
@@ -615,12 +614,11 @@ extern "C" int tw_gemm_bf16(const tw_gemm_args* a, void* stream) {
         gemm_bf16_kernel<false, false, 0>, gemm_bf16_kernel<false, false, 1>, gemm_bf16_kernel<false, true, 0>,
         gemm_bf16_kernel<false, true, 1>,  gemm_bf16_kernel<true, false, 0>,  gemm_bf16_kernel<true, false, 1>,
         gemm_bf16_kernel<true, true, 0>,   gemm_bf16_kernel<true, true, 1>};
-    static bool attr_set[64] = {};
-    const int dev = current_device();
-    if (!attr_set[dev]) {
+    static std::atomic<unsigned long long> attr_done{0};
+    if (device_needs_setup(attr_done)) {
         for (int i = 0; i < 8; ++i)
             TW_CUDA_CHECK(cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        attr_set[dev] = true;
+        mark_device_done(attr_done);
     }
     const kern_t k = kernels[(p.out_f32 ? 4 : 0) + (p.resid ? 2 : 0) + (p.act ? 1 : 0)];
     k<<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmB, p);

@@ -329,13 +329,12 @@ extern "C" int tw_logmel(const void* tables_dev, const float* pcm, int64_t pcm_s
     cudaStream_t st = (cudaStream_t)stream;
     float* scr = (float*)scratch;
     int* clip_max = (int*)(scr + (size_t)batch * N_MEL * N_FRAMES);
-    static bool attr_set[64] = {};
-    const int dev = current_device();
-    if (!attr_set[dev]) {
+    static std::atomic<unsigned long long> attr_done{0};
+    if (device_needs_setup(attr_done)) {
         TW_CUDA_CHECK(cudaFuncSetAttribute(logmel_power_kernel,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)sizeof(Smem)));
-        attr_set[dev] = true;
+        mark_device_done(attr_done);
     }
     // 0x80000000 is the ordered-int image of the most negative float
     TW_CUDA_CHECK(cudaMemsetAsync(clip_max, 0x80, (size_t)batch * sizeof(int), st));

@@ -3,6 +3,7 @@
 #include "twb200_internal.h"
 #include <stdarg.h>
 #include <stdio.h>
+#include <atomic>
 #include <mutex>
 
 namespace tw {
@@ -67,9 +68,11 @@ int encode_tensor_map(CUtensorMap* map, CUtensorMapDataType dtype, uint32_t rank
     return 0;
 }
 
+// Binds the calling host thread to the device that owns `device_ptr` — on EVERY call, so that one host thread can serve
+// several GPUs through the C ABI (a plain C caller has no torch.cuda.device() guard around it).  The pointer query is
+// ~0.2 us; cudaSetDevice only happens when the current device differs.
 int ensure_device(const void* device_ptr) {
-    static thread_local int bound = -1;
-    if (bound >= 0 || device_ptr == nullptr) return 0;
+    if (device_ptr == nullptr) return 0;
     cudaPointerAttributes attr;
     cudaError_t e = cudaPointerGetAttributes(&attr, device_ptr);
     if (e != cudaSuccess || attr.type != cudaMemoryTypeDevice) {
@@ -77,13 +80,23 @@ int ensure_device(const void* device_ptr) {
         set_error("expected a device pointer (%s)", e != cudaSuccess ? cudaGetErrorString(e) : "host memory");
         return 1;
     }
+    int cur = -1;
+    if (cudaGetDevice(&cur) == cudaSuccess && cur == attr.device) return 0;
     e = cudaSetDevice(attr.device);
     if (e != cudaSuccess) {
         set_error("cudaSetDevice(%d) failed: %s", attr.device, cudaGetErrorString(e));
         return 1;
     }
-    bound = attr.device;
     return 0;
+}
+
+// true exactly until `mark_device_done` was called for the current device (kernel attributes are per device); safe to race:
+// cudaFuncSetAttribute is idempotent, the flag word is atomic
+bool device_needs_setup(std::atomic<unsigned long long>& done_mask) {
+    return !((done_mask.load(std::memory_order_acquire) >> current_device()) & 1ull);
+}
+void mark_device_done(std::atomic<unsigned long long>& done_mask) {
+    done_mask.fetch_or(1ull << current_device(), std::memory_order_release);
 }
 
 int current_device() {
@@ -93,13 +106,12 @@ int current_device() {
 }
 
 int num_sms() {
-    static thread_local int n = 0;   // per thread: threads may serve different devices
+    static std::atomic<int> cache[64];   // per device (zero-initialised): a thread may serve several devices
+    const int dev = current_device();
+    int n = cache[dev].load(std::memory_order_relaxed);
     if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-        cudaDeviceProp p;
-        if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 0;
-        n = p.multiProcessorCount;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+        cache[dev].store(n, std::memory_order_relaxed);
     }
     return n;
 }

@@ -274,6 +274,7 @@ class B200WhisperPipeline:
         from .decode_asr import AsrDecoder
         self.asr_decoder = AsrDecoder(tokenizer, segment_size=dims.max_source_positions)
         self.last_stats: Dict[str, Any] = {}
+        self.last_token_rows: List[Any] = []
 
     @classmethod
     def from_hf_model(cls, model, tokenizer, devices=("cuda:0",), max_batch: int = 24,
@@ -325,6 +326,7 @@ class B200WhisperPipeline:
         if return_timestamps == "word":
             token_times = [np.asarray(t, dtype=np.float32) for _, t in token_rows]
             token_rows = [r for r, _ in token_rows]
+        self.last_token_rows = token_rows      # the engines' rows of this call, window order (bench.py's output check)
         self.last_stats = dict(self.scheduler.last_stats, windows=len(clips), files=len(items),
                                audio_seconds=sum(p["n_samples"] for p in prepared) / sr)
         results, w0 = [], 0
