@@ -275,6 +275,59 @@ int tw_decode_asr(const tw_asr_window* windows, int32_t n_windows, const tw_asr_
                   int64_t out_tokens_cap, int64_t* chunk_offsets, double* chunk_t0, double* chunk_t1,
                   int32_t* chunk_lang, int32_t max_chunks, int32_t* n_chunks_out, int32_t* flags_out);
 
+/* ---- beam search on the device (generate_kwargs={"num_beams": k}) -----------------------------------------
+ * Replaces GenerationMixin._beam_search ($TF/generation/utils.py:3076-3400, helpers :2876-3075) and the Whisper
+ * logits processors applied to log-probabilities ($TF/generation/logits_process.py:1812-2043) for
+ * n_windows x num_beams decode rows (row = window * num_beams + beam), early_stopping = False, do_sample = False.
+ * One call = one search step appended to a decode step whose LM head tapped the raw logits: per-row log-softmax +
+ * processors + best 2K continuations, per-window running / finished bookkeeping, the next token / position of every
+ * decode row, and the paged self-attention cache re-gathered by beam of origin as a block-table permutation (full
+ * pages by pointer, the partial current page copied into the row's own slot of the other page bank).  All state is
+ * device resident, so the step is CUDA-graph capturable; the host only polls ctrl[1] (search over). */
+typedef struct tw_beam_config {
+    int32_t num_beams;        /* K <= 8 */
+    int32_t vocab;
+    int32_t max_length;       /* generation_config.max_length (<= tokens_ld) */
+    int32_t prompt_len;       /* decoder prompt tokens per row */
+    int32_t eos, pad, no_timestamps;
+    int32_t max_initial_ts;   /* max_initial_timestamp_index, -1: none */
+    int32_t timestamps;       /* 0: generate(return_timestamps=False): suppress lists only */
+    int32_t track_indices;    /* 1: keep HF's beam_indices next to the tokens (word timestamps) */
+    float length_penalty;
+} tw_beam_config;
+/* W = tw_beam_record_width(cfg): a hypothesis record is [max_length tokens | max_length beam indices (if tracked)].
+ * Initial state (set by the caller): hist[0][w][k][:prompt_len] = prompt, pad elsewhere; run_score[w][0] = 0, others
+ * -1e9; fin_score = -1e9; fin_flag = fin_len = 0; gram = {0, 1, -1, 0}; improvable = 1; ctrl = 0. */
+typedef struct tw_beam_state {
+    int32_t* hist;        /* [2][n][K][W] running hypotheses, double-buffered by ctrl[0] */
+    int32_t* fin;         /* [2][n][K][W] finished hypotheses (slot 0 = best) */
+    float* run_score;     /* [n][K] */
+    float* fin_score;     /* [n][K] score / generated_length ** length_penalty */
+    int32_t* fin_flag;    /* [n][K] */
+    int32_t* fin_len;     /* [n][K] generated length */
+    int32_t* gram;        /* [n][K][4] timestamp-grammar state of the running rows */
+    int32_t* improvable;  /* [n] */
+    int32_t* hits_all;    /* [n] */
+    int32_t* ctrl;        /* [8]: [0] record parity, [1] search over, [2] scratch, [3] KV page bank, [4] steps taken */
+} tw_beam_state;
+int32_t tw_beam_record_width(const tw_beam_config* cfg);
+/* logits: fp32 [R][vocab] of this step (tw_dec_lmhead's tap); row_state as in the decode kernels (pos = position just
+ * fed; the step sets pos + 1); tokens[r][pos + 1] receives the token row r feeds next.  block_table [R][pages_per_row]
+ * must start as bank-0 identity (row r, page q -> r * pages_per_row + q); the pool holds n_pages >= 2 * bank_pages
+ * pages per (layer, k|v).  cand_val / cand_tok: scratch [R][2K]; copy_src / copy_dst: scratch int32 [R]; copy_len:
+ * scratch int32 [1]; origin_out: int32 [R], the previous row every new row continues. */
+int tw_beam_step(const tw_beam_config* cfg, const tw_beam_state* state, const float* logits, void* row_state,
+                 const uint32_t* suppress_bits, const uint32_t* begin_suppress_bits, float* cand_val,
+                 int32_t* cand_tok, int32_t* tokens, int32_t tokens_ld, int32_t* block_table, int32_t pages_per_row,
+                 int32_t bank_pages, void* kv_pool, int32_t n_pages, int32_t layers, int32_t d_model,
+                 int32_t* copy_src, int32_t* copy_dst, int32_t* copy_len, int32_t* origin_out, int32_t n_windows,
+                 void* stream);
+/* host: the same step on HOST buffers (same scalar code; no device involved) for the CPU test suite.  cur = index the new
+ * token is written to; next_tokens / origin_out: int32 [R]. */
+int tw_beam_step_host(const tw_beam_config* cfg, const tw_beam_state* state, const float* logits, int32_t cur,
+                      const uint32_t* suppress_bits, const uint32_t* begin_suppress_bits, int32_t* next_tokens,
+                      int32_t* origin_out, int32_t n_windows);
+
 #ifdef __cplusplus
 }
 #endif

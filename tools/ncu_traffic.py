@@ -1,56 +1,70 @@
-"""DRAM traffic per launch of the roofline kernels from an `ncu --set full` report of this round.
+"""DRAM traffic per launch of the roofline kernels from this round's `ncu --set full` captures.
 
-    python tools/ncu_traffic.py gpurun_out/r2a_target.ncu-rep [more.ncu-rep ...] > profiles/ncu_traffic.json
+    python tools/ncu_traffic.py RAW_OR_REP [RAW_OR_REP ...] > profiles/ncu_traffic.json
 
-Reads the raw page of every report (`ncu -i REP --page raw --csv`), sums dram__bytes_read.sum + dram__bytes_write.sum per
-kernel launch and averages over the launches of each kernel (base name before '<' / '(').  bench.py reads the result
-for `roofline.traffic` (no literals in bench.py)."""
+Arguments are .ncu-rep reports (read through `ncu -i REP --page raw --csv`) or raw-page CSV exports of them.  Every
+launch is listed (kernel with template arguments, grid, dram__bytes_read.sum + dram__bytes_write.sum, duration under
+ncu), and two aggregates are named for bench.py's `roofline.traffic` (no literals in bench.py):
+  decode_attn_kernel      mean over the CROSS-attention launches (those that stream the encoder K/V: > 50 MB)
+  gemm_bf16_2cta_kernel   mean over the four GEMMs of one encoder layer (qkv, out+res, fc1+GELU, fc2+res = the launches
+                          bench.py's GEMM probe times), i.e. the GEMM launches between the first and the third LayerNorm
+"""
 import csv
 import io
 import json
 import os
 import subprocess
 import sys
-from collections import defaultdict
 
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "bytes": 1.0}
+TIME = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6, "usecond": 1.0, "nsecond": 1e-3, "msecond": 1e3}
 
 
-def raw_rows(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
-    start = out.find('"ID"')
-    rows = list(csv.reader(io.StringIO(out[start:])))
-    header, units = rows[0], rows[1]
-    return header, units, rows[2:]
+def rows_of(path):
+    if path.endswith(".ncu-rep"):
+        text = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    else:
+        text = open(path).read()
+    start = text.find('"ID"')
+    rows = list(csv.reader(io.StringIO(text[start:])))
+    return rows[0], rows[1], rows[2:]
 
 
-def main(reps):
-    acc = defaultdict(list)
-    dur = defaultdict(list)
-    for rep in reps:
-        header, units, rows = raw_rows(rep)
+def num(s):
+    return float(s.replace(",", ""))
+
+
+def main(paths):
+    launches = []
+    for path in paths:
+        header, units, rows = rows_of(path)
         col = {h: i for i, h in enumerate(header)}
-        kn = col.get("Kernel Name")
-        rd, wr, du = col.get("dram__bytes_read.sum"), col.get("dram__bytes_write.sum"), col.get("gpu__time_duration.sum")
-        if kn is None or rd is None or wr is None:
-            continue
+        kn, rd, wr = col["Kernel Name"], col["dram__bytes_read.sum"], col["dram__bytes_write.sum"]
+        du, gs = col.get("gpu__time_duration.sum"), col.get("launch__grid_size")
         for r in rows:
-            name = r[kn].split("<")[0].split("(")[0].strip()
-            name = name.split("::")[-1]
-            try:
-                b = float(r[rd].replace(",", "")) * UNIT.get(units[rd], 1.0) + float(r[wr].replace(",", "")) * UNIT.get(units[wr], 1.0)
-            except ValueError:
-                continue
-            acc[name].append(b)
-            if du is not None:
-                try:
-                    dur[name].append(float(r[du].replace(",", "")) * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(units[du], 1.0))
-                except ValueError:
-                    pass
-    res = {k: sum(v) / len(v) for k, v in acc.items()}
-    res["launches"] = {k: len(v) for k, v in acc.items()}
-    res["us_under_ncu"] = {k: round(sum(v) / len(v), 2) for k, v in dur.items()}
-    res["source"] = "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, mean per launch: " + ", ".join(os.path.basename(r) for r in reps)
+            name = r[kn].split("(")[0].strip()
+            for ns in ("tw::", "gemm::", "attn::", "dec::", "ln::", "logmel::", "void "):
+                name = name.replace(ns, "")
+            launches.append({"kernel": name, "grid": int(num(r[gs])) if gs is not None else None,
+                             "dram_bytes": num(r[rd]) * UNIT.get(units[rd], 1.0) + num(r[wr]) * UNIT.get(units[wr], 1.0),
+                             "us_under_ncu": round(num(r[du]) * TIME.get(units[du], 1.0), 2) if du is not None else None,
+                             "report": os.path.basename(path)})
+    res = {}
+    cross = [l["dram_bytes"] for l in launches if l["kernel"].startswith("decode_attn_kernel") and l["dram_bytes"] > 50e6]
+    if cross:
+        res["decode_attn_kernel"] = sum(cross) / len(cross)
+    ln_seen, layer = 0, []
+    for l in launches:
+        if l["kernel"].startswith("layernorm_kernel"):
+            ln_seen += 1
+        elif l["kernel"].startswith("gemm_bf16") and 1 <= ln_seen <= 2:
+            layer.append(l["dram_bytes"])
+    if len(layer) == 4:
+        res["gemm_bf16_2cta_kernel"] = sum(layer) / 4
+        res["gemm_layer_shapes"] = dict(zip(("qkv", "out+res", "fc1+gelu", "fc2+res"), layer))
+    res["source"] = ("ncu --set full --clock-control none, dram__bytes_read.sum + dram__bytes_write.sum per launch, "
+                     "large-v3-turbo B = 24 (tools/ncu_target.py): " + ", ".join(os.path.basename(p) for p in paths))
+    res["launches"] = launches
     print(json.dumps(res, indent=1))
 
 

@@ -38,6 +38,16 @@ class FlacInfo(C.Structure):
                 ("total_samples", c_int64), ("md5", C.c_uint8 * 16)]
 
 
+class BeamConfig(C.Structure):
+    _fields_ = [(n, c_int32) for n in ("num_beams", "vocab", "max_length", "prompt_len", "eos", "pad", "no_timestamps",
+                                       "max_initial_ts", "timestamps", "track_indices")] + [("length_penalty", c_float)]
+
+
+class BeamState(C.Structure):
+    _fields_ = [(n, c_void_p) for n in ("hist", "fin", "run_score", "fin_score", "fin_flag", "fin_len", "gram",
+                                        "improvable", "hits_all", "ctrl")]
+
+
 class Grammar(C.Structure):
     _fields_ = [(n, c_int32) for n in ("eos", "pad", "no_timestamps", "ts_begin", "vocab", "lang_first", "lang_last",
                                        "max_initial_ts", "begin_index")]
@@ -82,6 +92,12 @@ SIGNATURES = {
     "tw_dtw_token_frames_batch": (C.c_int, [c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_int32]),
     "tw_flac_info_read": (C.c_int, [c_void_p, c_int64, c_void_p]),
     "tw_flac_decode": (C.c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
+    "tw_beam_record_width": (c_int32, [C.POINTER(BeamConfig)]),
+    "tw_beam_step": (C.c_int, [C.POINTER(BeamConfig), C.POINTER(BeamState), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_int32, c_int32, c_int32,
+                               c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
+    "tw_beam_step_host": (C.c_int, [C.POINTER(BeamConfig), C.POINTER(BeamState), c_void_p, c_int32, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_int32]),
     # host-only: (tw_asr_window*, n, tw_asr_config*, out_tokens, cap, offsets, t0, t1, lang, max_chunks, n_chunks*, flags*)
     "tw_decode_asr": (C.c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_int32, c_void_p, c_void_p]),

@@ -246,6 +246,7 @@ class WhisperEngine:
         g.begin_index = 3
         self.grammar = g
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
+        self._beam_ws: Dict[tuple, dict] = {}
         self._ckv_batch = max_batch
         self.use_graphs = not os.environ.get("TWB200_NO_GRAPHS")   # debug knob: eager stepping localises device faults
         self.finish_check_every = 16
@@ -433,8 +434,9 @@ class WhisperEngine:
             a.ln_out_bf16, a.ln_counter = self.dxn.data_ptr(), self.ln_cnt.data_ptr()
         return a
 
-    def _decode_step(self, B: int) -> None:
-        """One greedy step for rows 0..B-1: fixed launch sequence, positions read from self.state."""
+    def _decode_step(self, B: int, finalize: bool = True) -> None:
+        """One greedy step for rows 0..B-1: fixed launch sequence, positions read from self.state.
+        ``finalize=False`` (beam search): the LM head only taps the raw logits; tw_beam_step picks the tokens."""
         lib, d, w, st = _lib.load(), self.dims, self.w, self._stream()
         D, F, L, H = d.d_model, d.ffn, d.dec_layers, d.heads
         p = lambda t: C.c_void_p(t.data_ptr())
@@ -474,9 +476,10 @@ class WhisperEngine:
         check(lib.tw_dec_lmhead(C.byref(self._skinny("tok_emb_frag", self.dxn, None, B, D)), C.byref(self.grammar),
                                 p(self.state), p(self.sup_bits), p(self.bsup_bits), p(self.part_val), p(self.part_idx),
                                 None if self.logits is None else p(self.logits), st), "tw_dec_lmhead")
-        check(lib.tw_dec_finalize(p(self.part_val), p(self.part_idx), self.n_parts, p(self.tokens), self.max_len,
-                                  p(self.forced), None if self.choices is None else p(self.choices), p(self.state),
-                                  C.byref(self.grammar), B, st), "tw_dec_finalize")
+        if finalize:
+            check(lib.tw_dec_finalize(p(self.part_val), p(self.part_idx), self.n_parts, p(self.tokens), self.max_len,
+                                      p(self.forced), None if self.choices is None else p(self.choices), p(self.state),
+                                      C.byref(self.grammar), B, st), "tw_dec_finalize")
 
     @property
     def launches_per_step(self) -> int:
@@ -558,25 +561,84 @@ class WhisperEngine:
             self.stats["launches"] += steps * self.launches_per_step
             return self.tokens[:B]
 
+    # ------------------------------------------------------------------------------------ beam search
+    def _enable_beam_pool(self) -> None:
+        """Beam search re-gathers the paged self-attention cache by block-table permutation; the partial current page
+        of every row is copied into the row's own slot of the OTHER page bank, so the pool needs two banks."""
+        need = 2 * self.max_batch * self.pages_per_row
+        if self.n_pages >= need:
+            return
+        d, dev = self.dims, self.device
+        with torch.cuda.device(dev):
+            self.kv_pool = torch.zeros(d.dec_layers, 2, need, PAGE, d.d_model, dtype=torch.bfloat16, device=dev)
+        self.n_pages = need
+        self._graphs.clear()     # the pool pointer and n_pages are baked into the captured launches
+
+    def _beam_workspace(self, n: int, K: int, P: int, timestamps: bool, track: bool) -> dict:
+        key = (n, K, P, bool(timestamps), bool(track))
+        ws = self._beam_ws.get(key)
+        if ws is not None:
+            return ws
+        gen, dev, lib = self.gen, self.device, _lib.load()
+        cfg = _lib.BeamConfig()
+        cfg.num_beams, cfg.vocab, cfg.max_length, cfg.prompt_len = K, self.dims.vocab, self.max_len, P
+        cfg.eos, cfg.pad, cfg.no_timestamps = gen.eos_token_id, gen.pad_token_id, gen.no_timestamps_token_id
+        mi = gen.max_initial_timestamp_index
+        cfg.max_initial_ts = -1 if mi is None else int(mi)
+        cfg.timestamps, cfg.track_indices, cfg.length_penalty = int(bool(timestamps)), int(bool(track)), 1.0
+        W, R = int(lib.tw_beam_record_width(C.byref(cfg))), n * K
+        i32, f32 = torch.int32, torch.float32
+        with torch.cuda.device(dev):
+            z = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, device=dev)
+            ws = {"cfg": cfg, "W": W, "hist": z(2, n, K, W, dtype=i32), "fin": z(2, n, K, W, dtype=i32),
+                  "run_score": z(n, K, dtype=f32), "fin_score": z(n, K, dtype=f32), "fin_flag": z(n, K, dtype=i32),
+                  "fin_len": z(n, K, dtype=i32), "gram": z(n, K, 4, dtype=i32), "improvable": z(n, dtype=i32),
+                  "hits_all": z(n, dtype=i32), "ctrl": z(8, dtype=i32), "cand_val": z(R, 2 * K, dtype=f32),
+                  "cand_tok": z(R, 2 * K, dtype=i32), "copy_src": z(R, dtype=i32), "copy_dst": z(R, dtype=i32),
+                  "copy_len": z(1, dtype=i32), "origin": z(R, dtype=i32)}
+        st = _lib.BeamState()
+        for name in ("hist", "fin", "run_score", "fin_score", "fin_flag", "fin_len", "gram", "improvable", "hits_all", "ctrl"):
+            setattr(st, name, ws[name].data_ptr())
+        ws["state"] = st
+        self._beam_ws[key] = ws
+        return ws
+
+    def _beam_step(self, R: int, n: int, ws: dict) -> None:
+        """decode step (no finalize; the LM head taps the raw logits) + one tw_beam_step: everything the search needs
+        per position, on the device — captured as ONE CUDA graph by decode_beams."""
+        p = lambda t: C.c_void_p(t.data_ptr())
+        self._decode_step(R, finalize=False)
+        check(_lib.load().tw_beam_step(C.byref(ws["cfg"]), C.byref(ws["state"]), p(self.logits), p(self.state),
+                                       p(self.sup_bits), p(self.bsup_bits), p(ws["cand_val"]), p(ws["cand_tok"]),
+                                       p(self.tokens), self.max_len, p(self.block_table), self.pages_per_row,
+                                       self.max_batch * self.pages_per_row, p(self.kv_pool), self.n_pages,
+                                       self.dims.dec_layers, self.dims.d_model, p(ws["copy_src"]), p(ws["copy_dst"]),
+                                       p(ws["copy_len"]), p(ws["origin"]), n, self._stream()), "tw_beam_step")
+
     def decode_beams(self, n: int, prompts: torch.Tensor, num_beams: int, timestamps: bool = True,
                      frames_keep: Optional[Sequence[int]] = None) -> torch.Tensor:
         """Beam search ($TF/generation/utils.py:3076 `_beam_search`, early_stopping=False) for n windows against the
-        encoder state left by encode(): n * num_beams decode rows share the windows' cross K/V through `enc_row`, the
-        decode kernels produce the raw fp32 logits of every row (tap), :class:`beam.BeamSearch` picks the
-        continuations on the device, and the paged self-attention cache rows are re-gathered by beam of origin.
+        encoder state left by encode(): n * num_beams decode rows share the windows' cross K/V through `enc_row`; per
+        position ONE CUDA-graph replay runs the decode kernels (raw fp32 logits of every row) and `tw_beam_step`
+        (csrc/beam.cu: log-softmax + processors + best 2K per row, the running / finished bookkeeping per window, the
+        next token of every row, the paged self-attention cache re-gathered by beam of origin as a block-table
+        permutation).  The host only polls the "search over" flag every few steps.
         prompts: int [n, 3] with the language resolved.  Returns int64 [n, T]: best hypothesis per window without
         the prompt, right-padded with pad_token_id.
-        ``frames_keep``: per window the encoder frames kept for
-        the token-timestamp DTW; the alignment tap runs in every step, BeamSearch tracks HF's `beam_indices`, the
-        tapped rows of every position are gathered from the beam that produced it
-        ($TF/models/whisper/generation_whisper.py:265-303) and ``self.last_beam_frames`` receives the frames."""
-        from .beam import BeamConfig, BeamSearch
+        ``frames_keep``: per window the encoder frames kept for the token-timestamp DTW; the alignment tap runs in
+        every step, the search keeps HF's `beam_indices`, the tapped rows of every position are gathered from the beam
+        that produced it ($TF/models/whisper/generation_whisper.py:265-303) and ``self.last_beam_frames`` receives
+        the frames."""
         K, R = int(num_beams), n * int(num_beams)
         if R > self.max_batch:
             raise ValueError(f"{n} windows x {K} beams exceed max_batch {self.max_batch}")
+        if K > 8:
+            raise ValueError("num_beams > 8 is not supported")
         dev, gen, d = self.device, self.gen, self.dims
         if self.logits is None:
             self.enable_taps()
+        self._enable_beam_pool()
+        want_frames = frames_keep is not None
         with torch.cuda.device(dev):
             tail = [] if timestamps else [gen.no_timestamps_token_id]
             prompt = torch.cat([prompts.to(torch.long).cpu(), torch.tensor([tail] * n, dtype=torch.long).view(n, len(tail))], dim=1)
@@ -588,58 +650,91 @@ class WhisperEngine:
             frc[:, 1:P] = rows_prompt[:, 1:].to(torch.int32)
             st0 = torch.zeros(R, ROWSTATE_INTS, dtype=torch.int32)
             st0[:, 2] = -1
-            st0[:, 7] = 2      # "flat" mode: the grammar is applied by BeamSearch on the tapped logits, not by the LM head
+            st0[:, 7] = 2      # "flat" mode: the grammar is applied by tw_beam_step on the tapped logits, not by the LM head
             self.tokens[:R].copy_(tok0.to(dev))
             self.forced[:R].copy_(frc.to(dev))
             self.state[:R].copy_(st0.to(dev))
             self.enc_row[:R].copy_((torch.arange(R, dtype=torch.int32) // K).to(dev))
+            self.block_table.copy_(torch.arange(self.max_batch * self.pages_per_row, dtype=torch.int32,
+                                                device=dev).view(self.max_batch, self.pages_per_row))
             self.grammar.begin_index = P
-            _lib.load().tw_set_pdl(0 if self.use_graphs else 1)
-
-            want_frames = frames_keep is not None
+            _lib.load().tw_set_pdl(0)
+            # ---- search state
+            ws = self._beam_workspace(n, K, P, timestamps, want_frames)
+            L = self.max_len
+            ws["hist"].fill_(gen.pad_token_id)
+            ws["fin"].fill_(gen.pad_token_id)
+            if want_frames:
+                ws["hist"][..., L:] = -1
+                ws["fin"][..., L:] = -1
+            ws["hist"][0, :, :, :P] = prompt.to(torch.int32).to(dev)[:, None, :]
+            ws["run_score"].fill_(-1.0e9)
+            ws["run_score"][:, 0] = 0
+            ws["fin_score"].fill_(-1.0e9)
+            for name in ("fin_flag", "fin_len", "hits_all", "ctrl"):
+                ws[name].zero_()
+            ws["gram"].copy_(torch.tensor([0, 1, -1, 0], dtype=torch.int32, device=dev).expand(n, K, 4))
+            ws["improvable"].fill_(1)
             if want_frames:
                 self.enable_alignment()
             self._align_on = want_frames
             try:
-                graph = self._graph_for(R) if self.use_graphs else None
-            except BaseException:
-                self._align_on = False
-                raise
+                # the prompt but its last token: plain forced steps (their logits are not needed)
+                plain = self._graph_for(R) if (self.use_graphs and P > 1) else None
+                for _ in range(P - 1):
+                    if plain is not None:
+                        plain.replay()
+                    else:
+                        self._decode_step(R)
+                key = ("beam", R, K, self._ckv_batch, P, bool(timestamps), want_frames)
+                graph = self._graphs.get(key) if self.use_graphs else None
+                if self.use_graphs and graph is None:
+                    # warm-up outside capture, then restore everything the step mutated
+                    keep = {k: ws[k].clone() for k in ("hist", "fin", "run_score", "fin_score", "fin_flag", "fin_len", "gram",
+                                                        "improvable", "hits_all", "ctrl")}
+                    sb, tb, bt = self.state.clone(), self.tokens.clone(), self.block_table.clone()
+                    self._beam_step(R, n, ws)
+                    torch.cuda.current_stream(dev).synchronize()
 
-            def step():
-                if graph is not None:
-                    graph.replay()
-                else:
-                    self._decode_step(R)
-
-            try:
-                for _ in range(P):          # feed the prompt; the last of these steps yields the first real logits
-                    step()
-                cfg = BeamConfig(num_beams=K, vocab=d.vocab, max_length=self.max_len, eos_id=gen.eos_token_id,
-                                 pad_id=gen.pad_token_id, no_timestamps_id=gen.no_timestamps_token_id,
-                                 suppress=gen.suppress_tokens, begin_suppress=gen.begin_suppress_tokens,
-                                 max_initial_timestamp_index=gen.max_initial_timestamp_index, timestamps=timestamps)
-                bs = BeamSearch(cfg, prompt.to(dev), track_indices=want_frames)
-                L = d.dec_layers
-                ppr = self.pages_per_row
-                pool = self.kv_pool.view(L, 2, self.max_batch, ppr * PAGE, d.d_model)   # block_table is the identity layout
-                steps = P
-                while True:
-                    origin = bs.step(self.logits[:R])
-                    if bs.done:
-                        break
-                    cached = bs.cur - 1                                   # positions 0 .. cached-1 hold the histories
-                    pool[:, :, :R, :cached] = pool[:, :, :R, :cached].index_select(2, origin)
-                    self.tokens[:R, :bs.cur].copy_(bs.rows().to(torch.int32))
-                    step()
+                    def restore():
+                        for k, v in keep.items():
+                            ws[k].copy_(v)
+                        self.state.copy_(sb)
+                        self.tokens.copy_(tb)
+                        self.block_table.copy_(bt)
+                    restore()
+                    graph = torch.cuda.CUDAGraph()
+                    with _CAPTURE_LOCK:
+                        with torch.cuda.graph(graph, stream=self._capture_stream, capture_error_mode="thread_local"):
+                            self._beam_step(R, n, ws)
+                    restore()
+                    self._graphs[key] = graph
+                steps, max_steps, poll = 0, L - P, 8
+                while steps < max_steps:
+                    if graph is not None:
+                        graph.replay()
+                    else:
+                        self._beam_step(R, n, ws)
                     steps += 1
-                self.stats["dec_steps"] += steps
-                self.stats["launches"] += steps * self.launches_per_step
+                    if steps % poll == 0 or steps == max_steps:
+                        self.stats["d2h_bytes"] += 32
+                        if int(ws["ctrl"][1]):       # search over: later replays left the state untouched
+                            break
+                ctrl = ws["ctrl"].cpu()
+                if not int(ctrl[1]):
+                    raise RuntimeError("beam search did not terminate within max_length")
+                taken, par = int(ctrl[4]), int(ctrl[0])
+                self.stats["dec_steps"] += P - 1 + steps
+                self.stats["launches"] += (P - 1) * self.launches_per_step + steps * (self.launches_per_step - 1 + 3)
+                fin_len = ws["fin_len"][:, 0].cpu()
+                fin_score = ws["fin_score"][:, 0].cpu()
                 # the search's own accounting of the returned hypotheses (sum of processed log-probabilities, length)
-                self.last_beam = {"sum_logprob": (bs.beam_scores[:, 0] * bs.gen_len[:, 0].float() ** bs.cfg.length_penalty).cpu(),
-                                  "length": bs.gen_len[:, 0].cpu()}
+                self.last_beam = {"sum_logprob": fin_score * fin_len.float() ** float(ws["cfg"].length_penalty),
+                                  "length": fin_len.to(torch.long), "steps": taken}
+                m = int(fin_len.max())
+                best = ws["fin"][par, :, 0, P:P + m].to(torch.long)
                 if want_frames:
-                    bi = bs.beam_indices()                                   # [n, longest generated]
+                    bi = ws["fin"][par, :, 0, L:L + m].to(torch.long)        # HF's beam_indices, -1 beyond a hypothesis
                     if P > 1:
                         bi = torch.cat([bi[:, :1].expand(-1, P - 1), bi], dim=-1)
                     bi = bi.masked_fill(bi == -1, 0)                         # [n, wl]
@@ -650,10 +745,12 @@ class WhisperEngine:
                                            device=dev)
                     gathered[:, :, :wl] = al["probs"][bi[:, None, :], slots[None, :, None], pos[None, None, :]]
                     self.last_beam_frames = self.token_frames(n, [], P, frames_keep, probs=gathered, n_tok=wl - P)
-                return bs.result()
+                return best
             finally:
                 self._align_on = False
                 self.enc_row.copy_(torch.arange(self.max_batch, dtype=torch.int32, device=dev))
+                self.block_table.copy_(torch.arange(self.max_batch * self.pages_per_row, dtype=torch.int32,
+                                                    device=dev).view(self.max_batch, self.pages_per_row))
 
     # ------------------------------------------------------------------------------------ generate
     def generate_from_pcm(self, clips: Sequence[np.ndarray], task: str = "transcribe",
