@@ -6,6 +6,7 @@ mkdir -p gpurun_out
 step() { echo "== $1" >&2; }
 step "beam tests"; timeout 600 python -m pytest tests/test_gpu_engine.py tests/test_gpu_pipeline.py tests/test_gpu_zz_word_timestamps.py -m gpu -x -q -s -k "beam or pipeline" > gpurun_out/${T}_beam_tests.log 2>&1; tail -5 gpurun_out/${T}_beam_tests.log
 step "beam throughput"; timeout 300 python tools/bench_beams.py > gpurun_out/${T}_beams.jsonl 2> gpurun_out/${T}_beams.err; cat gpurun_out/${T}_beams.jsonl; tail -3 gpurun_out/${T}_beams.err
+step "microbatch probe"; timeout 400 python tools/probe_microbatch.py > gpurun_out/${T}_microbatch.jsonl 2>gpurun_out/${T}_microbatch.err; cat gpurun_out/${T}_microbatch.jsonl
 step "ncu attention source"
 cat > /tmp/attn_only.py <<'P'
 import sys, os

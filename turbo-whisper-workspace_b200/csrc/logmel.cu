@@ -1,22 +1,25 @@
-// K1 — fused log-mel front end.
+// K1 — fused log-mel front end, ONE launch.
 //
 // Replaces WhisperFeatureExtractor._torch_extract_fbank_features
 // ($TF/models/whisper/feature_extraction_whisper.py:135-164): reflect-padded 400-point STFT at
 // hop 160 with a periodic Hann window, power spectrum, 128-bin slaney mel filterbank, log10 clamp
 // at 1e-10, per-clip `max - 8` floor and (x + 4) / 4.
 //
-// Two launches:
-//   logmel_power_kernel : PCM -> log10(mel) into an fp32 scratch [B,128,3000] + per-clip max
-//                         (ordered-int atomicMax).  One CTA owns FR consecutive frames of one
-//                         clip: samples are staged once in shared memory (each sample is reused by
-//                         2.5 frames), the 400-point real FFT runs as a 200-point complex Stockham
-//                         FFT (radix 8,5,5) entirely in shared memory, then the sparse (<=9 taps)
-//                         mel projection.
-//   logmel_norm_kernel  : clamp to max-8, (x+4)/4; writes fp32 [B,128,3000] (reference layout)
-//                         and/or the bf16 time-major padded layout [B, rows, 128] the conv stem's
-//                         TMA im2col view consumes (row 1+t = frame t).
+// logmel_kernel: a CTA owns FR = 32 consecutive frames of one clip.  The 5360 samples they touch are staged once in
+// shared memory (coalesced; reflect padding and the zero tail are index arithmetic), then every WARP works alone on
+// its 4 frames, one frame at a time, in a private shared-memory workspace — the 400-point real FFT as a 200-point
+// complex Stockham FFT (radix 8, 5, 5), the real post-process + power, the sparse (<= 12 taps) mel projection, log10 —
+// with __syncwarp between the phases and NO block-wide barrier in the loop (the previous version ran the phases
+// CTA-wide behind six __syncthreads per 16 frames and was latency-bound at 0.07 of HBM).  Lane l owns mel bins
+// 4l..4l+3, so a frame's 128 bf16 values leave as one coalesced 256-byte row of the time-major layout the conv stem's
+// TMA view reads (and, for the reference layout, as float4 runs of 4 frames).
+// The per-clip floor needs the maximum over the WHOLE clip.  (x + 4) / 4 and the bf16 rounding are monotone, so
+//   (max(l, m - 8) + 4) / 4 == max((l + 4) / 4, ((m - 8) + 4) / 4)      bit for bit,
+// i.e. the kernel can store the un-floored value right away, publish its tile's max / min (ordered-int atomicMax, a
+// per-tile min), and the LAST CTA of a clip to finish (per-clip arrival counter) raises the few values that lie below
+// the floor — only in tiles whose min is below it, read back from L2.  Counters re-arm themselves: one kernel per call.
 //
-// The phases are written as __host__ __device__ functions over (tid, nthreads) so that the exact
+// The arithmetic phases are __host__ __device__ functions over (tid, nthreads) so that the exact
 // index arithmetic is also exercised on the CPU by tests/csrc/logmel_host_test.cu.
 #include "common.cuh"
 #include "twb200_internal.h"
@@ -32,11 +35,14 @@ constexpr int N_MEL = 128;
 constexpr int N_FRAMES = 3000;
 constexpr int N_SAMPLES = 480000;
 constexpr int NC = 200;  // complex FFT length
-constexpr int FR = 16;   // frames per CTA
+constexpr int FR = 32;   // frames per CTA
 constexpr int NT = 256;  // threads per CTA
-constexpr int SX = FR * HOP + (N_FFT - HOP);  // 2800 staged samples
+constexpr int NWARP = NT / 32;
+constexpr int FPW = FR / NWARP;               // consecutive frames per warp
+constexpr int SX = FR * HOP + (N_FFT - HOP);  // 5360 staged samples
 constexpr int POW_LD = 203;                   // padded row length of the power buffer
 constexpr int MEL_MAX_TAPS = 12;
+constexpr int N_TILES = (N_FRAMES + FR - 1) / FR;   // 94 CTAs per clip
 
 struct Tables {
     float2 tw200[NC];       // exp(-2 pi i m / 200)
@@ -49,11 +55,15 @@ struct Tables {
 
 struct Smem {
     float x[SX];
-    float2 a[FR][NC];
-    float2 b[FR][NC];
+    float2 a[NWARP][NC];      // per-warp FFT ping
+    float2 b[NWARP][NC];      // per-warp FFT pong, then the power spectrum (POW_LD floats)
     float2 tw200[NC];
     float2 tw400[N_BINS];
-    float red[NT / 32];
+    float window[N_FFT];
+    float mel_w[N_MEL][MEL_MAX_TAPS];
+    int mel_start[N_MEL];
+    int mel_cnt[N_MEL];
+    float red[2][NWARP];
 };
 
 #define HD __host__ __device__ __forceinline__
@@ -114,12 +124,11 @@ HD void phase_load(int tid, int nt, const float* pcm, int n_valid, int f0, float
         sx[i] = (g < n_valid) ? pcm[g] : 0.0f;
     }
 }
-// phase 1: window + pack to complex + radix-8 stage (Ns = 1, no twiddles).  25 items / frame.
-HD void phase_fft_r8(int tid, int nt, const float* sx, const float* window, float2 (*out)[NC]) {
+// The FFT phases below work on ONE frame (a warp's current frame): xf = its 400 staged samples.
+// phase 1: window + pack to complex + radix-8 stage (Ns = 1, no twiddles).  25 items.
+HD void phase_fft_r8(int tid, int nt, const float* xf, const float* window, float2* out) {
     constexpr int T = NC / 8;  // 25
-    for (int w = tid; w < FR * T; w += nt) {
-        const int fr = w / T, j = w - fr * T;
-        const float* xf = sx + fr * HOP;
+    for (int j = tid; j < T; j += nt) {
         float2 v[8];
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
@@ -128,135 +137,192 @@ HD void phase_fft_r8(int tid, int nt, const float* sx, const float* window, floa
         }
         dft8(v);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) out[fr][j * 8 + u] = v[u];
+        for (int u = 0; u < 8; ++u) out[j * 8 + u] = v[u];
     }
 }
-// phases 2/3: radix-5 Stockham stage with sub-transform length Ns (8, then 40).  40 items / frame.
-HD void phase_fft_r5(int tid, int nt, int Ns, const float2* tw200, const float2 (*in)[NC],
-                     float2 (*out)[NC]) {
+// phases 2/3: radix-5 Stockham stage with sub-transform length Ns (8, then 40).  40 items.
+HD void phase_fft_r5(int tid, int nt, int Ns, const float2* tw200, const float2* in, float2* out) {
     constexpr int T = NC / 5;  // 40
     const int twstep = NC / (Ns * 5);
-    for (int w = tid; w < FR * T; w += nt) {
-        const int fr = w / T, j = w - fr * T;
+    for (int j = tid; j < T; j += nt) {
         const int k = j % Ns;
         float2 v[5];
-        v[0] = in[fr][j];
+        v[0] = in[j];
 #pragma unroll
-        for (int t = 1; t < 5; ++t) v[t] = cmul(in[fr][j + t * T], tw200[t * k * twstep]);
+        for (int t = 1; t < 5; ++t) v[t] = cmul(in[j + t * T], tw200[t * k * twstep]);
         dft5(v);
         const int j0 = (j / Ns) * Ns * 5 + k;
 #pragma unroll
-        for (int u = 0; u < 5; ++u) out[fr][j0 + u * Ns] = v[u];
+        for (int u = 0; u < 5; ++u) out[j0 + u * Ns] = v[u];
     }
 }
 // phase 4: real-FFT post-process + power.  X[k] = E[k] + W400^k O[k], k = 0..200.
-HD void phase_power(int tid, int nt, const float2* tw400, const float2 (*Z)[NC], float* pw) {
-    for (int w = tid; w < FR * N_BINS; w += nt) {
-        const int fr = w / N_BINS, k = w - fr * N_BINS;
-        const float2 zk = Z[fr][k == NC ? 0 : k];
-        const float2 zr = Z[fr][(k == 0 || k == NC) ? 0 : NC - k];
+HD void phase_power(int tid, int nt, const float2* tw400, const float2* Z, float* pw) {
+    for (int k = tid; k < N_BINS; k += nt) {
+        const float2 zk = Z[k == NC ? 0 : k];
+        const float2 zr = Z[(k == 0 || k == NC) ? 0 : NC - k];
         const float2 zc = make_float2(zr.x, -zr.y);
         const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
         const float2 d = make_float2(0.5f * (zk.x - zc.x), 0.5f * (zk.y - zc.y));
         const float2 o = cmul_mi(d);
         const float2 x = cadd(e, cmul(tw400[k], o));
-        pw[fr * POW_LD + k] = x.x * x.x + x.y * x.y;
+        pw[k] = x.x * x.x + x.y * x.y;
     }
 }
-// phase 5: sparse mel projection + log10 clamp.  Item = (mel, frame) with frame fastest so that
-// the global store of one warp covers 2 mel rows x 16 consecutive frames (64 B segments).
-HD float phase_mel(int tid, int nt, const int* mel_start, const int* mel_cnt,
-                   const float (*mel_w)[MEL_MAX_TAPS], const float* pw, float* out_clip, int f0) {
-    float vmax = -1e30f;
-    for (int w = tid; w < FR * N_MEL; w += nt) {
-        const int m = w / FR, fr = w - m * FR;
-        const int f = f0 + fr;
-        if (f >= N_FRAMES) continue;
-        const int s = mel_start[m], c = mel_cnt[m];
-        float acc = 0.0f;
-        for (int i = 0; i < c; ++i) acc = fmaf(mel_w[m][i], pw[fr * POW_LD + s + i], acc);
-        const float v = log10f(fmaxf(acc, 1e-10f));
-        out_clip[(size_t)m * N_FRAMES + f] = v;
-        vmax = fmaxf(vmax, v);
-    }
-    return vmax;
+// phase 5: one mel bin of one frame: sparse projection + log10 clamp
+HD float mel_log10(int m, const int* mel_start, const int* mel_cnt, const float (*mel_w)[MEL_MAX_TAPS], const float* pw) {
+    const int s = mel_start[m], c = mel_cnt[m];
+    float acc = 0.0f;
+    for (int i = 0; i < c; ++i) acc = fmaf(mel_w[m][i], pw[s + i], acc);
+    return log10f(fmaxf(acc, 1e-10f));
 }
+// the value stored before the per-clip floor is known, and the floor in the same scale (see the header: monotone)
+HD float scaled(float log10_value) { return (log10_value + 4.0f) * 0.25f; }
+HD float scaled_floor(float clip_max_log10) { return ((clip_max_log10 - 8.0f) + 4.0f) * 0.25f; }
 
 #ifndef TW_HOST_TEST
-__global__ void __launch_bounds__(NT) logmel_power_kernel(const float* __restrict__ pcm,
-                                                         long long pcm_stride,
-                                                         const int* __restrict__ n_valid,
-                                                         const Tables* __restrict__ tab,
-                                                         float* __restrict__ scratch,
-                                                         int* __restrict__ clip_max) {
+// monotone map float -> unsigned whose ZERO is below every float: zero-filled scratch is a valid "no maximum yet"
+TW_DEVINL unsigned int float_to_umono(float f) { return (unsigned int)float_to_ordered(f) ^ 0x80000000u; }
+TW_DEVINL float umono_to_float(unsigned int u) { return ordered_to_float((int)(u ^ 0x80000000u)); }
+
+struct Scratch {            // per clip; zero-filled once by the owner, re-armed by the kernel
+    unsigned int clip_max;  // float_to_umono(max log10 value of the clip)
+    unsigned int arrived;   // CTAs of this clip that have stored their tile
+    float tile_min[N_TILES];
+    float tile_max[N_TILES];
+};
+
+__global__ void __launch_bounds__(NT) logmel_kernel(const float* __restrict__ pcm, long long pcm_stride,
+                                                   const int* __restrict__ n_valid, const Tables* __restrict__ tab,
+                                                   Scratch* __restrict__ scratch, float* __restrict__ out_f32,
+                                                   __nv_bfloat16* __restrict__ out_t, long long out_t_bstride,
+                                                   int row_off) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem& s = *reinterpret_cast<Smem*>(smem_raw);
-    const int b = blockIdx.y;
-    const int f0 = blockIdx.x * FR;
-    const int tid = threadIdx.x;
+    __shared__ int s_last;
+    const int b = blockIdx.y, tile = blockIdx.x;
+    const int f0 = tile * FR;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nv = n_valid ? min(n_valid[b], N_SAMPLES) : N_SAMPLES;
 
     for (int i = tid; i < NC; i += NT) s.tw200[i] = tab->tw200[i];
     for (int i = tid; i < N_BINS; i += NT) s.tw400[i] = tab->tw400[i];
+    for (int i = tid; i < N_FFT; i += NT) s.window[i] = tab->window[i];
+    for (int i = tid; i < N_MEL * MEL_MAX_TAPS; i += NT) (&s.mel_w[0][0])[i] = (&tab->mel_w[0][0])[i];
+    for (int i = tid; i < N_MEL; i += NT) { s.mel_start[i] = tab->mel_start[i]; s.mel_cnt[i] = tab->mel_cnt[i]; }
     phase_load(tid, NT, pcm + (size_t)b * pcm_stride, nv, f0, s.x);
     __syncthreads();
-    phase_fft_r8(tid, NT, s.x, tab->window, s.a);
-    __syncthreads();
-    phase_fft_r5(tid, NT, 8, s.tw200, s.a, s.b);
-    __syncthreads();
-    phase_fft_r5(tid, NT, 40, s.tw200, s.b, s.a);
-    __syncthreads();
-    float* pw = reinterpret_cast<float*>(&s.b[0][0]);  // FR*POW_LD floats <= FR*NC*2
-    phase_power(tid, NT, s.tw400, s.a, pw);
-    __syncthreads();
-    float vmax = phase_mel(tid, NT, tab->mel_start, tab->mel_cnt, tab->mel_w, pw,
-                           scratch + (size_t)b * N_MEL * N_FRAMES, f0);
-    vmax = warp_max(vmax);
-    if ((tid & 31) == 0) s.red[tid >> 5] = vmax;
-    __syncthreads();
-    if (tid == 0) {
-        float m = s.red[0];
-#pragma unroll
-        for (int i = 1; i < NT / 32; ++i) m = fmaxf(m, s.red[i]);
-        atomicMax(clip_max + b, float_to_ordered(m));
-    }
-}
 
-// normalise: y = (max(x, clipmax - 8) + 4) / 4.  Tile = 32 frames x 128 mels; the fp32 output
-// keeps the reference [128,3000] layout, the bf16 output is transposed through shared memory
-// into [rows,128] (row = row_off + frame), 256 B per frame, fully coalesced on both sides.
-constexpr int NTILE_F = 32;
-__global__ void __launch_bounds__(256) logmel_norm_kernel(const float* __restrict__ scratch,
-                                                         const int* __restrict__ clip_max,
-                                                         float* __restrict__ out_f32,
-                                                         __nv_bfloat16* __restrict__ out_t,
-                                                         long long out_t_bstride, int row_off) {
-    __shared__ float tile[N_MEL][NTILE_F + 1];
-    const int b = blockIdx.y;
-    const int f0 = blockIdx.x * NTILE_F;
-    const float floor_v = ordered_to_float(clip_max[b]) - 8.0f;
-    const float* src = scratch + (size_t)b * N_MEL * N_FRAMES;
-    const int tid = threadIdx.x;
-    for (int w = tid; w < N_MEL * NTILE_F; w += 256) {
-        const int m = w / NTILE_F, fr = w % NTILE_F;
-        const int f = f0 + fr;
-        float v = 0.0f;
-        if (f < N_FRAMES) {
-            v = (fmaxf(src[(size_t)m * N_FRAMES + f], floor_v) + 4.0f) * 0.25f;
-            if (out_f32) out_f32[((size_t)b * N_MEL + m) * N_FRAMES + f] = v;
+    // every warp: its FPW frames, one at a time, in its own workspace
+    float2* wa = s.a[warp];
+    float2* wb = s.b[warp];
+    float* pw = reinterpret_cast<float*>(wb);
+    float vmax = -INFINITY, vmin = INFINITY;
+    float keep[FPW][4];                       // reference-layout output: 4 mel rows x FPW consecutive frames per lane
+    float* of = out_f32 ? out_f32 + ((size_t)b * N_MEL + 4 * lane) * N_FRAMES : nullptr;
+    __nv_bfloat16* ot = out_t ? out_t + (size_t)b * out_t_bstride : nullptr;
+#pragma unroll
+    for (int i = 0; i < FPW; ++i) {
+        const int fl = warp * FPW + i;        // frame within the tile
+        const int f = f0 + fl;
+        if (f < N_FRAMES) {                   // warp-uniform
+            phase_fft_r8(lane, 32, s.x + fl * HOP, s.window, wa);
+            __syncwarp();
+            phase_fft_r5(lane, 32, 8, s.tw200, wa, wb);
+            __syncwarp();
+            phase_fft_r5(lane, 32, 40, s.tw200, wb, wa);
+            __syncwarp();
+            phase_power(lane, 32, s.tw400, wa, pw);
+            __syncwarp();
+            float y[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float l = mel_log10(4 * lane + q, s.mel_start, s.mel_cnt, s.mel_w, pw);
+                vmax = fmaxf(vmax, l);
+                vmin = fminf(vmin, l);
+                y[q] = scaled(l);
+                keep[i][q] = y[q];
+            }
+            if (ot) {
+                uint2 pk;
+                pk.x = pack_bf16x2(y[0], y[1]);
+                pk.y = pack_bf16x2(y[2], y[3]);
+                reinterpret_cast<uint2*>(ot + (size_t)(row_off + f) * N_MEL)[lane] = pk;
+            }
+            __syncwarp();                     // pw (= wb) and wa are reused by the next frame
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) keep[i][q] = 0.f;
         }
-        tile[m][fr] = v;
     }
-    if (!out_t) return;
+    if (of) {
+        const int fw = f0 + warp * FPW;       // first frame of this warp: a multiple of 4, so float4 stores are aligned
+        if (fw + FPW <= N_FRAMES) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<float4*>(of + (size_t)q * N_FRAMES + fw) = make_float4(keep[0][q], keep[1][q], keep[2][q], keep[3][q]);
+        } else {
+            for (int i = 0; i < FPW; ++i)
+                if (fw + i < N_FRAMES)
+                    for (int q = 0; q < 4; ++q) of[(size_t)q * N_FRAMES + fw + i] = keep[i][q];
+        }
+    }
+    // tile statistics -> clip maximum (atomic), per-tile min / max for the floor pass
+    vmax = warp_max(vmax);
+    vmin = -warp_max(-vmin);
+    if (lane == 0) { s.red[0][warp] = vmax; s.red[1][warp] = vmin; }
+    __threadfence();                          // this CTA's output is visible before it counts as arrived
     __syncthreads();
-    for (int w = tid; w < NTILE_F * (N_MEL / 2); w += 256) {
-        const int fr = w / (N_MEL / 2), m2 = w % (N_MEL / 2);
-        const int f = f0 + fr;
-        if (f >= N_FRAMES) continue;
-        uint32_t p = pack_bf16x2(tile[2 * m2][fr], tile[2 * m2 + 1][fr]);
-        reinterpret_cast<uint32_t*>(out_t + (size_t)b * out_t_bstride +
-                                    (size_t)(row_off + f) * N_MEL)[m2] = p;
+    Scratch& sc = scratch[b];
+    if (tid == 0) {
+        float mx = s.red[0][0], mn = s.red[1][0];
+#pragma unroll
+        for (int i = 1; i < NWARP; ++i) { mx = fmaxf(mx, s.red[0][i]); mn = fminf(mn, s.red[1][i]); }
+        sc.tile_min[tile] = mn;
+        sc.tile_max[tile] = mx;
+        atomicMax(&sc.clip_max, float_to_umono(mx));
+        __threadfence();
+        const unsigned int prev = atomicAdd(&sc.arrived, 1u);
+        s_last = (prev == gridDim.x - 1);
     }
+    __syncthreads();
+    if (!s_last) return;
+    // ---- last CTA of the clip: raise everything below the floor (only tiles that have such values)
+    __threadfence();
+    const float clip_max = umono_to_float(__ldcg(&sc.clip_max));
+    const float floor_l = clip_max - 8.0f, floor_y = scaled_floor(clip_max);
+    const uint32_t floor_bf = pack_bf16x2(floor_y, floor_y);
+    const float floor_bf_f = __uint_as_float(floor_bf << 16);
+    for (int t = 0; t < (int)gridDim.x; ++t) {
+        if (!(__ldcg(&sc.tile_min[t]) < floor_l)) continue;      // block-uniform
+        const int tf0 = t * FR, nfr = min(FR, N_FRAMES - tf0);
+        if (ot) {   // nfr rows of 128 bf16, contiguous: 16 uint4 per row
+            uint4* base = reinterpret_cast<uint4*>(ot + (size_t)(row_off + tf0) * N_MEL);
+            for (int i = tid; i < nfr * 16; i += NT) {
+                uint4 v = __ldcg(base + i);
+                uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+                bool changed = false;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float lo = __uint_as_float(w[k] << 16), hi = __uint_as_float(w[k] & 0xffff0000u);
+                    if (lo < floor_bf_f) { lo = floor_bf_f; changed = true; }
+                    if (hi < floor_bf_f) { hi = floor_bf_f; changed = true; }
+                    w[k] = (__float_as_uint(lo) >> 16) | (__float_as_uint(hi) & 0xffff0000u);
+                }
+                if (changed) base[i] = v;
+            }
+        }
+        if (out_f32) {
+            float* fb = out_f32 + (size_t)b * N_MEL * N_FRAMES + tf0;
+            for (int i = tid; i < N_MEL * nfr; i += NT) {
+                const int m = i / nfr, fr = i - m * nfr;
+                float* p = fb + (size_t)m * N_FRAMES + fr;
+                if (__ldcg(p) < floor_y) *p = floor_y;
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) { sc.clip_max = 0u; sc.arrived = 0u; }      // re-arm for the next call on this stream
 }
 #endif  // TW_HOST_TEST
 
@@ -297,9 +363,7 @@ using namespace tw;
 using namespace tw::logmel;
 
 extern "C" size_t tw_logmel_tables_bytes(void) { return sizeof(Tables); }
-extern "C" size_t tw_logmel_scratch_bytes(int batch) {
-    return (size_t)batch * N_MEL * N_FRAMES * sizeof(float) + (size_t)batch * sizeof(int);
-}
+extern "C" size_t tw_logmel_scratch_bytes(int batch) { return (size_t)batch * sizeof(Scratch); }
 
 extern "C" int tw_logmel_init(void* tables_dev, const float* mel_filters_host_201x128) {
     TW_REQUIRE(tables_dev && mel_filters_host_201x128, "tw_logmel_init: null argument");
@@ -325,25 +389,18 @@ extern "C" int tw_logmel(const void* tables_dev, const float* pcm, int64_t pcm_s
     TW_REQUIRE(batch >= 0 && batch <= 65535, "tw_logmel: batch %d out of range", batch);
     TW_REQUIRE(pcm_stride >= N_SAMPLES, "tw_logmel: pcm_stride %lld < %d", (long long)pcm_stride,
                N_SAMPLES);
+    TW_REQUIRE(!out_bf16_t || (((uintptr_t)out_bf16_t & 15) == 0 && out_t_bstride % 8 == 0),
+               "tw_logmel: the time-major output must be 16-byte aligned");
+    TW_REQUIRE(!out_f32 || ((uintptr_t)out_f32 & 15) == 0, "tw_logmel: out_f32 must be 16-byte aligned");
     if (batch == 0) return 0;
-    cudaStream_t st = (cudaStream_t)stream;
-    float* scr = (float*)scratch;
-    int* clip_max = (int*)(scr + (size_t)batch * N_MEL * N_FRAMES);
     static std::atomic<unsigned long long> attr_done{0};
     if (device_needs_setup(attr_done)) {
-        TW_CUDA_CHECK(cudaFuncSetAttribute(logmel_power_kernel,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)sizeof(Smem)));
+        TW_CUDA_CHECK(cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
         mark_device_done(attr_done);
     }
-    // 0x80000000 is the ordered-int image of the most negative float
-    TW_CUDA_CHECK(cudaMemsetAsync(clip_max, 0x80, (size_t)batch * sizeof(int), st));
-    dim3 g1((N_FRAMES + FR - 1) / FR, batch);
-    logmel_power_kernel<<<g1, NT, sizeof(Smem), st>>>(pcm, (long long)pcm_stride, n_valid,
-                                                      (const Tables*)tables_dev, scr, clip_max);
-    dim3 g2((N_FRAMES + NTILE_F - 1) / NTILE_F, batch);
-    logmel_norm_kernel<<<g2, 256, 0, st>>>(scr, clip_max, out_f32, (__nv_bfloat16*)out_bf16_t,
-                                           (long long)out_t_bstride, out_t_row_off);
+    logmel_kernel<<<dim3(N_TILES, batch), NT, sizeof(Smem), (cudaStream_t)stream>>>(
+        pcm, (long long)pcm_stride, n_valid, (const Tables*)tables_dev, (Scratch*)scratch, out_f32,
+        (__nv_bfloat16*)out_bf16_t, (long long)out_t_bstride, out_t_row_off);
     TW_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -375,7 +375,7 @@ class WhisperEngine:
     def features(self, B: int, out_f32: Optional[torch.Tensor] = None):
         """K1: PCM (self.pcm[:B]) -> time-major bf16 features in self.mel_t (and optionally fp32 [B,128,3000])."""
         self.logmel(self.pcm[:B], self.n_valid[:B], out_f32=out_f32, out_t=self.mel_t, out_t_row_off=1)
-        self.stats["launches"] += 2
+        self.stats["launches"] += 1
 
     # ------------------------------------------------------------------------------------ encoder
     def encode(self, B: int, mel: Optional[torch.Tensor] = None, taps: Optional[dict] = None) -> torch.Tensor:

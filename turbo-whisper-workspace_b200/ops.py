@@ -59,7 +59,8 @@ class LogMel:
         self.device = torch.device(device)
         self.max_batch = max_batch
         self.tables = torch.empty(lib.tw_logmel_tables_bytes(), dtype=torch.uint8, device=self.device)
-        self.scratch = torch.empty(lib.tw_logmel_scratch_bytes(max_batch), dtype=torch.uint8, device=self.device)
+        # zero-filled ONCE: the kernel keeps its per-clip maximum / arrival counters here and re-arms them itself
+        self.scratch = torch.zeros(lib.tw_logmel_scratch_bytes(max_batch), dtype=torch.uint8, device=self.device)
         fb = slaney_mel_filters()
         with torch.cuda.device(self.device):
             check(lib.tw_logmel_init(_ptr(self.tables), fb.ctypes.data_as(C.c_void_p)), "tw_logmel_init")

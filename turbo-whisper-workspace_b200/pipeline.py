@@ -306,7 +306,10 @@ class B200WhisperPipeline:
             raise ValueError("Whisper cannot return `char` timestamps, only word level or segment level timestamps. "
                              "Use `return_timestamps='word'` or `return_timestamps=True` respectively.")
         sr = self.sampling_rate
+        import time
+        t0 = time.perf_counter()
         prepared = [self._prepare(x, chunk_length_s, stride_length_s) for x in items]
+        t1 = time.perf_counter()
         clips = [c for p in prepared for c in p["clips"]]
         # return_timestamps falsy (the HF default): generate runs with <|notimestamps|> in the prompt and without the
         # timestamp grammar, and the windows are merged on their overlapping text only
@@ -326,15 +329,18 @@ class B200WhisperPipeline:
         if return_timestamps == "word":
             token_times = [np.asarray(t, dtype=np.float32) for _, t in token_rows]
             token_rows = [r for r, _ in token_rows]
+        t2 = time.perf_counter()
         self.last_token_rows = token_rows      # the engines' rows of this call, window order (bench.py's output check)
-        self.last_stats = dict(self.scheduler.last_stats, windows=len(clips), files=len(items),
-                               audio_seconds=sum(p["n_samples"] for p in prepared) / sr)
         results, w0 = [], 0
         for p in prepared:
             n = len(p["windows"])
             results.append(self._finish(p, token_rows[w0:w0 + n], None if token_times is None else token_times[w0:w0 + n],
                                         bs, return_timestamps, return_language))
             w0 += n
+        # host phases of the call: ingest + windowing | engines (H2D, kernels, D2H of token ids) | stitching + text
+        self.last_stats = dict(self.scheduler.last_stats, windows=len(clips), files=len(items),
+                               audio_seconds=sum(p["n_samples"] for p in prepared) / sr,
+                               host_seconds={"prepare": t1 - t0, "engines": t2 - t1, "finish": time.perf_counter() - t2})
         return results if many else results[0]
 
     def _prepare(self, inputs, chunk_length_s, stride_length_s) -> Dict[str, Any]:

@@ -72,7 +72,10 @@ def run_in_microbatches(engine, clips: Sequence[np.ndarray], task: str, language
     return rows
 
 
-MIN_MICROBATCH = 6     # below this the encoder GEMMs no longer fill the SMs (6 windows = 9000 rows = 36 row tiles)
+# Floor of the micro-batch size.  Measured on one B200 (profiles/r2c_microbatch.jsonl: a rank's share of a 1 h file on 8
+# GPUs = 23 windows): 4 x 6 windows 0.563 s, 3 x 8 0.529 s, 2 x 12 0.520 s, 1 x 23 0.538 s — the decode loop costs ~890
+# latency-bound steps per micro-batch whatever its size, so fewer, larger micro-batches win until contexts go idle.
+MIN_MICROBATCH = 12
 
 
 def balanced_microbatch(n_items: int, workers: int, max_mb: int, min_mb: int = MIN_MICROBATCH) -> int:
@@ -80,7 +83,7 @@ def balanced_microbatch(n_items: int, workers: int, max_mb: int, min_mb: int = M
     the same whatever its size (the decode loop is latency-bound: ~2 x 445 steps per micro-batch), so the job should
     use as FEW micro-batches as possible while keeping every context busy in every round:
     rounds = ceil(n / (workers * max_mb)), size = ceil(n / (workers * rounds)) clamped to [min_mb, max_mb].
-    One 1 h file (180 windows): 1 GPU x 4 contexts -> 8 micro-batches of 23; 8 GPUs x 4 contexts -> 30 of 6."""
+    One 1 h file (180 windows): 1 GPU x 4 contexts -> 8 micro-batches of 23; 8 GPUs x 4 contexts -> 15 of 12."""
     workers, max_mb = max(1, workers), max(1, max_mb)
     min_mb = max(1, min(min_mb, max_mb))
     if n_items <= 0:
