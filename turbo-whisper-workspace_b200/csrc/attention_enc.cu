@@ -47,7 +47,16 @@ constexpr int TILE_BYTES = 128 * DH * 2;   // 16 KB: Q, K, V tiles and each half
 // P never touches shared memory: tcgen05.mma reads it from tensor memory.
 constexpr int XCH_BYTES = 2 * 2 * 2 * 128 * 4;   // row-max / row-sum exchange between the two threads of a row: [parity][tile][half][row]
 constexpr int smem_bytes(int nt) { return (nt + 4) * TILE_BYTES + XCH_BYTES + 1024 + 256; }
-constexpr int num_threads(int nt) { return 64 + nt * GROUP_THREADS; }   // warp 0 TMA, warp 1 MMA, 8 softmax warps per tile
+// -DATTN_MERGED_ISSUE=1: ONE warp issues both the TMA loads and the MMAs (both are single-lane jobs driven by the same
+// event loop), a CTA is then 9 warps.  Measured (profiles/r2e_attn_variants.jsonl): 0.464 ms vs 0.466 ms for the default
+// two-warp layout — no gain, because ptxas derives the register cap of __launch_bounds__(288, 2) as for 10 warps (96
+// registers either way; the ~90 bytes of loop spills stay), and stating the cap directly (__maxnreg__(112), which cannot
+// be combined with __launch_bounds__) loses the second CTA per SM: 0.636 ms.  Kept as a build option.
+#ifndef ATTN_MERGED_ISSUE
+#define ATTN_MERGED_ISSUE 0
+#endif
+constexpr int ISSUE_WARPS = ATTN_MERGED_ISSUE ? 1 : 2;
+constexpr int num_threads(int nt) { return 32 * ISSUE_WARPS + nt * GROUP_THREADS; }   // issue warp(s), 8 softmax warps per tile
 constexpr float LOG2E = 1.4426950408889634f;
 // One pair of exponentials in POLY_EVERY takes the FMA-pipe polynomial path (1000 = none).  Measured on one box:
 // none 0.526 ms, every 4th 0.476 ms, every 3rd 0.470 ms, every 2nd 0.484 ms per layer.  It is OFF by default: the
@@ -177,7 +186,8 @@ attention_enc_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
         }
         fence_barrier_init();
     }
-    if (warp == 1) {
+    constexpr int MMA_WARP = ISSUE_WARPS - 1;   // the warp that issues the MMAs (and owns the TMEM allocation)
+    if (warp == MMA_WARP) {
         tmem_alloc(tmem_ptr_smem, TMEM_COLS);
         tmem_relinquish();
     }
@@ -186,7 +196,7 @@ attention_enc_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    if (warp == 0) {
+    if (!ATTN_MERGED_ISSUE && warp == 0) {
         if (lane == 0) {
             mbar_arrive_expect_tx(q_full, NT * TILE_BYTES);
 #pragma unroll
@@ -202,7 +212,7 @@ attention_enc_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
                 tma_load_3d(&tmQKV, &v_full[s], sV + s * TILE_BYTES, 2 * p.D + h * DH, j * BKV, b);
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == MMA_WARP) {
         // The whole warp runs this loop converged and one elected lane issues: every operand of tcgen05.mma is
         // then warp-uniform (uniform registers), so an issue costs ~3 instructions.  (With a single divergent
         // thread and descriptor arrays in local memory each issue cost ~110 cycles - more than the 32-64
@@ -240,6 +250,33 @@ attention_enc_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
             if (elect_one_sync()) tcgen05_commit(bar);
             __syncwarp();
         };
+        // merged layout: this warp is also the TMA producer.  Q and the first two K / V stages go out at once; later
+        // stages are (re)filled from the event loop below as soon as their consumers release them.
+        int jk = 0, jv = 0;   // next K / V tile to load
+        auto load_k = [&](int j) {
+            if (elect_one_sync()) {
+                mbar_arrive_expect_tx(&k_full[j & 1], TILE_BYTES);
+                tma_load_3d(&tmQKV, &k_full[j & 1], sK + (j & 1) * TILE_BYTES, p.D + h * DH, j * BKV, b);
+            }
+            __syncwarp();
+        };
+        auto load_v = [&](int j) {
+            if (elect_one_sync()) {
+                mbar_arrive_expect_tx(&v_full[j & 1], TILE_BYTES);
+                tma_load_3d(&tmQKV, &v_full[j & 1], sV + (j & 1) * TILE_BYTES, 2 * p.D + h * DH, j * BKV, b);
+            }
+            __syncwarp();
+        };
+        if (ATTN_MERGED_ISSUE) {
+            if (elect_one_sync()) {
+                mbar_arrive_expect_tx(q_full, NT * TILE_BYTES);
+#pragma unroll
+                for (int g = 0; g < NT; ++g) tma_load_3d(&tmQKV, q_full, sQ + g * TILE_BYTES, h * DH, q0 + g * BQ, b);
+            }
+            __syncwarp();
+            for (; jk < 2 && jk < nkv; ++jk) load_k(jk);
+            for (; jv < 2 && jv < nkv; ++jv) load_v(jv);
+        }
         if (lane == 0) TRACE(0);
         mbar_wait(q_full, 0);
         mbar_wait(&k_full[0], 0);
@@ -260,6 +297,12 @@ attention_enc_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
             for (int g = 0; g < NT; ++g) any = any || jp[g] < nkv;
             return any; };
         while (pending()) {
+            if (ATTN_MERGED_ISSUE) {
+                // a stage is free again once the MMAs that read its previous tile have completed (k_empty / v_empty are
+                // armed by tcgen05.commit); tile j reuses the stage of tile j - 2
+                if (jk < nkv && __any_sync(0xffffffffu, mbar_test_wait(&k_empty[jk & 1], ((jk >> 1) & 1) ^ 1))) { load_k(jk); ++jk; }
+                if (jv < nkv && __any_sync(0xffffffffu, mbar_test_wait(&v_empty[jv & 1], ((jv >> 1) & 1) ^ 1))) { load_v(jv); ++jv; }
+            }
 #pragma unroll
             for (int g = 0; g < NT; ++g) {
                 // (K_j / V_j are part of the non-blocking condition: a tile that runs two kv tiles ahead of the other
@@ -296,9 +339,10 @@ attention_enc_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
         // idle during its TMEM load / row-max / store phases and the FMA pipe idle during its exp phase; with four
         // warps in different phases both stay busy.  Warps w and w+4 of a tile share a TMEM lane quarter (w % 4) and
         // split the columns; they agree on the row maximum through shared memory (named barrier per warp pair).
-        const int grp = (warp - 2) >> 3;    // 0: tile A, 1: tile B
-        const int quarter = warp & 3;       // TMEM lane quarter this warp may access
-        const int hf = ((warp - 2) >> 2) & 1;   // which 64 keys of the tile (and which 32 output columns) this thread owns
+        const int ws = warp - ISSUE_WARPS;  // softmax warp index
+        const int grp = ws >> 3;            // 0: tile A, 1: tile B
+        const int quarter = warp & 3;       // TMEM lane quarter this warp may access (hardware: warp id % 4)
+        const int hf = (ws >> 2) & 1;       // which 64 keys of the tile (and which 32 output columns) this thread owns
         const int r = quarter * 32 + lane;  // query row within the tile == TMEM lane
         const int pair_bar = 1 + grp * 4 + quarter;   // named barrier of the two warps that share these rows
         const uint32_t t_lane = (uint32_t)(quarter * 32) << 16;
@@ -461,7 +505,7 @@ attention_enc_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
     }
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == MMA_WARP) {
         tcgen05_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
     }

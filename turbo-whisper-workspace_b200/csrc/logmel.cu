@@ -43,6 +43,7 @@ constexpr int SX = FR * HOP + (N_FFT - HOP);  // 5360 staged samples
 constexpr int POW_LD = 203;                   // padded row length of the power buffer
 constexpr int MEL_MAX_TAPS = 12;
 constexpr int N_TILES = (N_FRAMES + FR - 1) / FR;   // 94 CTAs per clip
+constexpr int NCP = NC + NC / 16 + 1;               // padded FFT workspace length (213), see padi()
 
 struct Tables {
     float2 tw200[NC];       // exp(-2 pi i m / 200)
@@ -55,14 +56,13 @@ struct Tables {
 
 struct Smem {
     float x[SX];
-    float2 a[NWARP][NC];      // per-warp FFT ping
-    float2 b[NWARP][NC];      // per-warp FFT pong, then the power spectrum (POW_LD floats)
+    float2 a[NWARP][NCP];     // per-warp FFT ping (padded, see padi)
+    float2 b[NWARP][NCP];     // per-warp FFT pong, then the power spectrum (N_BINS floats)
     float2 tw200[NC];
     float2 tw400[N_BINS];
     float window[N_FFT];
-    float mel_w[N_MEL][MEL_MAX_TAPS];
-    int mel_start[N_MEL];
-    int mel_cnt[N_MEL];
+    float4 mel_w4[MEL_MAX_TAPS][32];   // [tap][lane] = the tap's weight for mel bins 4*lane .. 4*lane+3 (one LDS.128, no conflicts)
+    int4 mel_start4[32];               // [lane] = first FFT bin of those four filters
     float red[2][NWARP];
 };
 
@@ -124,6 +124,9 @@ HD void phase_load(int tid, int nt, const float* pcm, int n_valid, int f0, float
         sx[i] = (g < n_valid) ? pcm[g] : 0.0f;
     }
 }
+// FFT workspaces are padded by one complex slot per 16 (the radix-8 stage writes with a stride of 8 complex values =
+// 64 bytes: without padding 13 of its 25 lanes hit the same two banks)
+HD int padi(int i) { return i + (i >> 4); }
 // The FFT phases below work on ONE frame (a warp's current frame): xf = its 400 staged samples.
 // phase 1: window + pack to complex + radix-8 stage (Ns = 1, no twiddles).  25 items.
 HD void phase_fft_r8(int tid, int nt, const float* xf, const float* window, float2* out) {
@@ -137,7 +140,7 @@ HD void phase_fft_r8(int tid, int nt, const float* xf, const float* window, floa
         }
         dft8(v);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) out[j * 8 + u] = v[u];
+        for (int u = 0; u < 8; ++u) out[padi(j * 8 + u)] = v[u];
     }
 }
 // phases 2/3: radix-5 Stockham stage with sub-transform length Ns (8, then 40).  40 items.
@@ -147,20 +150,20 @@ HD void phase_fft_r5(int tid, int nt, int Ns, const float2* tw200, const float2*
     for (int j = tid; j < T; j += nt) {
         const int k = j % Ns;
         float2 v[5];
-        v[0] = in[j];
+        v[0] = in[padi(j)];
 #pragma unroll
-        for (int t = 1; t < 5; ++t) v[t] = cmul(in[j + t * T], tw200[t * k * twstep]);
+        for (int t = 1; t < 5; ++t) v[t] = cmul(in[padi(j + t * T)], tw200[t * k * twstep]);
         dft5(v);
         const int j0 = (j / Ns) * Ns * 5 + k;
 #pragma unroll
-        for (int u = 0; u < 5; ++u) out[j0 + u * Ns] = v[u];
+        for (int u = 0; u < 5; ++u) out[padi(j0 + u * Ns)] = v[u];
     }
 }
 // phase 4: real-FFT post-process + power.  X[k] = E[k] + W400^k O[k], k = 0..200.
 HD void phase_power(int tid, int nt, const float2* tw400, const float2* Z, float* pw) {
     for (int k = tid; k < N_BINS; k += nt) {
-        const float2 zk = Z[k == NC ? 0 : k];
-        const float2 zr = Z[(k == 0 || k == NC) ? 0 : NC - k];
+        const float2 zk = Z[padi(k == NC ? 0 : k)];
+        const float2 zr = Z[padi((k == 0 || k == NC) ? 0 : NC - k)];
         const float2 zc = make_float2(zr.x, -zr.y);
         const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
         const float2 d = make_float2(0.5f * (zk.x - zc.x), 0.5f * (zk.y - zc.y));
@@ -208,8 +211,13 @@ __global__ void __launch_bounds__(NT) logmel_kernel(const float* __restrict__ pc
     for (int i = tid; i < NC; i += NT) s.tw200[i] = tab->tw200[i];
     for (int i = tid; i < N_BINS; i += NT) s.tw400[i] = tab->tw400[i];
     for (int i = tid; i < N_FFT; i += NT) s.window[i] = tab->window[i];
-    for (int i = tid; i < N_MEL * MEL_MAX_TAPS; i += NT) (&s.mel_w[0][0])[i] = (&tab->mel_w[0][0])[i];
-    for (int i = tid; i < N_MEL; i += NT) { s.mel_start[i] = tab->mel_start[i]; s.mel_cnt[i] = tab->mel_cnt[i]; }
+    for (int i = tid; i < MEL_MAX_TAPS * 32; i += NT) {
+        const int tap = i >> 5, l = i & 31;
+        s.mel_w4[tap][l] = make_float4(tab->mel_w[4 * l][tap], tab->mel_w[4 * l + 1][tap], tab->mel_w[4 * l + 2][tap],
+                                       tab->mel_w[4 * l + 3][tap]);
+    }
+    if (tid < 32) s.mel_start4[tid] = make_int4(tab->mel_start[4 * tid], tab->mel_start[4 * tid + 1], tab->mel_start[4 * tid + 2],
+                                                tab->mel_start[4 * tid + 3]);
     phase_load(tid, NT, pcm + (size_t)b * pcm_stride, nv, f0, s.x);
     __syncthreads();
 
@@ -234,10 +242,23 @@ __global__ void __launch_bounds__(NT) logmel_kernel(const float* __restrict__ pc
             __syncwarp();
             phase_power(lane, 32, s.tw400, wa, pw);
             __syncwarp();
+            // sparse mel projection of this lane's four bins: taps beyond a filter's length carry weight 0 (same fmaf order
+            // as mel_log10, so the sums are identical to the host emulation's)
+            const int4 st4 = s.mel_start4[lane];
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int tp = 0; tp < MEL_MAX_TAPS; ++tp) {
+                const float4 w = s.mel_w4[tp][lane];
+                acc[0] = fmaf(w.x, pw[min(st4.x + tp, N_BINS - 1)], acc[0]);
+                acc[1] = fmaf(w.y, pw[min(st4.y + tp, N_BINS - 1)], acc[1]);
+                acc[2] = fmaf(w.z, pw[min(st4.z + tp, N_BINS - 1)], acc[2]);
+                acc[3] = fmaf(w.w, pw[min(st4.w + tp, N_BINS - 1)], acc[3]);
+            }
             float y[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const float l = mel_log10(4 * lane + q, s.mel_start, s.mel_cnt, s.mel_w, pw);
+                // log10 through the hardware log2 (abs. error < 2e-7 here, the stated tolerance is 1e-4)
+                const float l = __log2f(fmaxf(acc[q], 1e-10f)) * 0.30102999566398120f;
                 vmax = fmaxf(vmax, l);
                 vmin = fminf(vmin, l);
                 y[q] = scaled(l);

@@ -57,24 +57,29 @@ def pipeline(task: Optional[str] = None, model: Any = None, *args, **kwargs):
     build = _OPTIONS.get("builder")
     if build is not None:                                   # tests / custom schedulers
         return build(hf_model, tokenizer)
-    return B200WhisperPipeline.from_hf_model(hf_model, tokenizer, devices=_OPTIONS["devices"],
+    pipe = B200WhisperPipeline.from_hf_model(hf_model, tokenizer, devices=_OPTIONS["devices"],
                                              max_batch=_OPTIONS["max_batch"],
                                              contexts_per_device=_OPTIONS["contexts_per_device"])
+    pipe.num_beams = _OPTIONS.get("num_beams", 1)
+    return pipe
 
 
 def install(devices: Optional[Sequence[Any]] = None, max_batch: int = 24, contexts_per_device: int = 4,
             loader: Optional[Callable[..., Tuple[Any, Any]]] = None,
-            builder: Optional[Callable[[Any, Any], Any]] = None) -> None:
+            builder: Optional[Callable[[Any, Any], Any]] = None, num_beams: int = 1) -> None:
     """Patch ``transformers.pipeline``.  ``devices``: CUDA devices of the engine (default: all visible ones);
     ``loader(model, tokenizer) -> (WhisperForConditionalGeneration, tokenizer)`` and ``builder(model, tokenizer) ->
-    callable`` override checkpoint loading and engine construction."""
+    callable`` override checkpoint loading and engine construction.  ``num_beams``: default beam count of the returned
+    pipeline's calls — 1 = greedy (the north star's mode); 5 reproduces what the reference's literal call decodes with
+    under transformers >= 4.53, whose ASR pipeline defaults to ``num_beams=5`` and the reference passes only
+    ``generate_kwargs={"task": task}`` (ref:vocalis/core/audio_pipeline.py:348)."""
     global _ORIGINAL
     import transformers
     if devices is None:
         import torch
         devices = [f"cuda:{i}" for i in range(max(1, torch.cuda.device_count()))]
     _OPTIONS.update(devices=list(devices), max_batch=int(max_batch), contexts_per_device=int(contexts_per_device),
-                    loader=loader, builder=builder)
+                    loader=loader, builder=builder, num_beams=max(1, int(num_beams)))
     if _ORIGINAL is None:
         _ORIGINAL = transformers.pipeline
         transformers.pipeline = pipeline
