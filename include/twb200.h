@@ -150,6 +150,19 @@ typedef struct tw_skinny_args {
     const float* ln_beta;
     void* ln_out_bf16;
     uint32_t* ln_counter;
+    /* LayerNorm FOLDED into the next projection:  W LN(x) + b = rstd (W' x - mean c) + d  with W' = W diag(gamma),
+     * c = row sums of the bf16 W', d = W beta + b.
+     * Producer (residual epilogue): with ln_part_out given, every CTA also stores bf16(updated x) into x_bf16_out
+     * [batch, n] and (mean, M2) of its 16 values per row into the scratch ln_part_out[n / 16][32] (float2); the last CTA
+     * to finish (ln_counter) reduces them in a fixed order to ln_stats_out[32] = (mean, rstd) per row — a tail of a few
+     * hundred loads instead of a LayerNorm over batch x n values.
+     * Consumer (tw_dec_linear epilogues 0 / 3, tw_dec_qkv): with ln_stats_in given, `w` holds W', `bias` holds d, `x` is
+     * the producer's x_bf16_out, ln_c = c [n]; rstd / mean are applied in the epilogue. */
+    void* ln_part_out;
+    void* x_bf16_out;
+    void* ln_stats_out;
+    const void* ln_stats_in;
+    const float* ln_c;
 } tw_skinny_args;
 
 typedef struct tw_grammar {

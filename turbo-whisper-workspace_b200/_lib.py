@@ -30,7 +30,8 @@ class GemmArgs(C.Structure):
 class SkinnyArgs(C.Structure):
     _fields_ = [("w", c_void_p), ("x", c_void_p), ("ldx", c_int32), ("bias", c_void_p), ("batch", c_int32),
                 ("n", c_int32), ("k", c_int32), ("ln_gamma", c_void_p), ("ln_beta", c_void_p), ("ln_out_bf16", c_void_p),
-                ("ln_counter", c_void_p)]
+                ("ln_counter", c_void_p), ("ln_part_out", c_void_p), ("x_bf16_out", c_void_p), ("ln_stats_out", c_void_p),
+                ("ln_stats_in", c_void_p), ("ln_c", c_void_p)]
 
 
 class FlacInfo(C.Structure):

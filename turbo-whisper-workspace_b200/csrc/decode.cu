@@ -123,6 +123,18 @@ struct SkinnyParams {
     unsigned int* ln_counter;    // zero-initialised, self re-arming
     const float* bias;       // [N] or null
     int B, N, K;
+    // LayerNorm folded into the consumer (round 2; removes the serial last-CTA LayerNorm tail of the producer):
+    //   W (LN(x)) + b  =  rstd * (W' x - mean * c) + d,   W' = W diag(gamma), c = W' 1, d = W beta + b
+    // Producer (EPI_RESID with ln_part_out): besides the fp32 update it stores bf16(x_new) into xb_out (the next
+    // projection's operand) and (mean, M2) of its 16 values per row into ln_part_out[cta][row]; the LAST CTA to finish
+    // combines the N / 16 partials of every row (two fixed-order warp reductions: deterministic) into (mean, rstd) —
+    // a tail of a few hundred loads instead of a full LayerNorm over B x N values.  Consumer (LNF instantiations,
+    // weights = W', bias = d): reads the B (mean, rstd) pairs and applies rstd / mean / c in its epilogue.
+    float2* ln_part_out;         // [N/16][MAXB] scratch or null
+    __nv_bfloat16* xb_out;       // [B, N]
+    float2* ln_stats_out;        // [MAXB] (mean, rstd) per row, written by the producer's last CTA
+    const float2* ln_stats_in;   // [MAXB] (consumer)
+    const float* ln_c;           // [N]: row sums of the bf16 W'
     // EPI_BF16 / EPI_GELU_BF16
     __nv_bfloat16* out_bf16;
     int ldo;
@@ -220,11 +232,12 @@ TW_DEVINL void warp_layernorm_row(const float* __restrict__ x, const float* __re
         }
 }
 
-template <int NB, int EPI, int WARPS>
+template <int NB, int EPI, int WARPS, bool LNF = false>
 __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 2 : 1) skinny_gemm_kernel(const SkinnyParams p) {
     constexpr int NT = WARPS * 32;
     __shared__ float red[WARPS][NB * 8][17];
     __shared__ int s_last;
+    __shared__ float s_mu[LNF ? MAXB : 1], s_rs[LNF ? MAXB : 1];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, tg = lane & 3;
@@ -253,6 +266,11 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 2 : 1) skinny_gemm_
     for (int u = 0; u < UN; ++u)
         if (u < steps) { alo[u] = ldg_stream(wa + u * FRAG_STEP); ahi[u] = ldg_stream(wb + u * FRAG_STEP); }
     pdl_wait();
+    if (LNF && threadIdx.x < p.B) {     // (mean, rstd) of every row, left by the producer's last CTA
+        const float2 st2 = __ldcg(p.ln_stats_in + threadIdx.x);
+        s_mu[threadIdx.x] = st2.x;
+        s_rs[threadIdx.x] = st2.y;
+    }
     for (int s0 = 0; s0 < steps; s0 += UN) {
         uint4 xb[UN][NB];
 #pragma unroll
@@ -286,10 +304,35 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 2 : 1) skinny_gemm_
     for (int o = threadIdx.x; o < NB * 8 * 16; o += NT) {
         const int bb = o >> 4, rr = o & 15;
         const int n = n0 + rr;
-        if (bb >= p.B || n >= p.N) continue;
+        const bool live = bb < p.B && n < p.N;
+        if (EPI == EPI_RESID && p.ln_part_out) {
+            // producer of a folded LayerNorm: fp32 update, bf16 copy for the next projection, and (mean, M2) of the 16
+            // values of row bb this CTA owns (one half-warp = one row; N % 16 == 0 here).  Whole warps run this branch.
+            float x = 0.f;
+            if (live) {
+                float v = 0.f;
+#pragma unroll
+                for (int w = 0; w < WARPS; ++w) v += red[w][bb][rr];
+                if (p.bias) v += p.bias[n];
+                x = p.resid[(size_t)bb * p.N + n] + v;
+                p.resid[(size_t)bb * p.N + n] = x;
+                p.xb_out[(size_t)bb * p.N + n] = __float2bfloat16(x);
+            }
+            float sm = x;
+#pragma unroll
+            for (int d = 1; d < 16; d <<= 1) sm += __shfl_xor_sync(0xffffffffu, sm, d);
+            const float mc = sm * (1.0f / 16.0f);
+            float dq = (x - mc) * (x - mc);
+#pragma unroll
+            for (int d = 1; d < 16; d <<= 1) dq += __shfl_xor_sync(0xffffffffu, dq, d);
+            if (live && rr == 0) p.ln_part_out[(size_t)blockIdx.x * MAXB + bb] = make_float2(mc, dq);
+            continue;
+        }
+        if (!live) continue;
         float v = 0.f;
 #pragma unroll
         for (int w = 0; w < WARPS; ++w) v += red[w][bb][rr];
+        if (LNF) v = s_rs[bb] * (v - s_mu[bb] * p.ln_c[n]);
         if (p.bias) v += p.bias[n];
         if (EPI == EPI_BF16) {
             p.out_bf16[(size_t)bb * p.ldo + n] = __float2bfloat16(v);
@@ -307,6 +350,48 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 2 : 1) skinny_gemm_
                 __nv_bfloat16* dst = p.kv_pool + ((size_t)(which - 1) * p.n_pages + page) * PAGE * p.D +
                                      (size_t)(pos % PAGE) * p.D + c;
                 *dst = __float2bfloat16(v);
+            }
+        }
+    }
+    if (EPI == EPI_RESID && p.ln_stats_out) {
+        // last CTA: (mean, rstd) of every row from the N / 16 per-CTA partials.  All partials count 16 values, so
+        // mean = avg(m_c) and M2 = sum(M2_c + 16 (m_c - mean)^2): two fixed-order warp reductions per row.
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned int prev = atomicAdd(p.ln_counter, 1u);
+            s_last = (prev == gridDim.x - 1);
+            if (s_last) *p.ln_counter = 0;  // re-arm for the next launch
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            const int parts = gridDim.x;
+            constexpr int RPW = (NB * 8 + WARPS - 1) / WARPS;
+            constexpr int PPL = 3;           // partials per lane (N <= 1536)
+            float2 pr[RPW][PPL];
+#pragma unroll
+            for (int i = 0; i < RPW; ++i) {
+                const int r = warp + i * WARPS;
+#pragma unroll
+                for (int t = 0; t < PPL; ++t) {
+                    const int c = lane + 32 * t;
+                    pr[i][t] = (r < p.B && c < parts) ? __ldcg(p.ln_part_out + (size_t)c * MAXB + r) : make_float2(0.f, 0.f);
+                }
+            }
+            const float inv_parts = 1.0f / (float)parts;
+#pragma unroll
+            for (int i = 0; i < RPW; ++i) {
+                const int r = warp + i * WARPS;
+                const float mean = warp_sum((pr[i][0].x + pr[i][1].x) + pr[i][2].x) * inv_parts;
+                float q = 0.f;
+#pragma unroll
+                for (int t = 0; t < PPL; ++t) {
+                    const float d = pr[i][t].x - mean;
+                    if (lane + 32 * t < parts) q += fmaf(16.0f * d, d, pr[i][t].y);
+                }
+                q = warp_sum(q);
+                if (lane == 0 && r < p.B) p.ln_stats_out[r] = make_float2(mean, rsqrtf(q / (float)p.N + 1e-5f));
             }
         }
     }
@@ -834,13 +919,13 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 
 static_assert(sizeof(RowState) == 32, "RowState layout is part of the ABI (8 x int32)");
 
-template <int EPI, int WARPS>
+template <int EPI, int WARPS, bool LNF = false>
 static int launch_nb(const SkinnyParams& p, int grid, cudaStream_t st) {
     switch ((p.B + 7) / 8) {
-        case 1: TW_CUDA_CHECK(launch_pdl(skinny_gemm_kernel<1, EPI, WARPS>, dim3(grid), dim3(WARPS * 32), 0, st, p)); break;
-        case 2: TW_CUDA_CHECK(launch_pdl(skinny_gemm_kernel<2, EPI, WARPS>, dim3(grid), dim3(WARPS * 32), 0, st, p)); break;
-        case 3: TW_CUDA_CHECK(launch_pdl(skinny_gemm_kernel<3, EPI, WARPS>, dim3(grid), dim3(WARPS * 32), 0, st, p)); break;
-        case 4: TW_CUDA_CHECK(launch_pdl(skinny_gemm_kernel<4, EPI, WARPS>, dim3(grid), dim3(WARPS * 32), 0, st, p)); break;
+        case 1: TW_CUDA_CHECK(launch_pdl(skinny_gemm_kernel<1, EPI, WARPS, LNF>, dim3(grid), dim3(WARPS * 32), 0, st, p)); break;
+        case 2: TW_CUDA_CHECK(launch_pdl(skinny_gemm_kernel<2, EPI, WARPS, LNF>, dim3(grid), dim3(WARPS * 32), 0, st, p)); break;
+        case 3: TW_CUDA_CHECK(launch_pdl(skinny_gemm_kernel<3, EPI, WARPS, LNF>, dim3(grid), dim3(WARPS * 32), 0, st, p)); break;
+        case 4: TW_CUDA_CHECK(launch_pdl(skinny_gemm_kernel<4, EPI, WARPS, LNF>, dim3(grid), dim3(WARPS * 32), 0, st, p)); break;
         default: set_error("skinny gemm: batch %d > %d", p.B, MAXB); return 2;
     }
     TW_CUDA_CHECK(cudaGetLastError());
@@ -851,7 +936,11 @@ static int launch_nb(const SkinnyParams& p, int grid, cudaStream_t st) {
 template <int EPI>
 static int launch_skinny(const SkinnyParams& p, cudaStream_t st) {
     const int grid = (p.N + 15) / 16;
-    if (EPI == EPI_RESID && p.K >= 4096 && p.K % 512 == 0) return launch_nb<EPI_RESID, 16>(p, grid, st);
+    if (EPI == EPI_RESID) {
+        if (p.K >= 4096 && p.K % 512 == 0) return launch_nb<EPI_RESID, 16>(p, grid, st);
+        return launch_nb<EPI_RESID, 8>(p, grid, st);
+    }
+    if (p.ln_stats_in) return launch_nb<EPI, 8, true>(p, grid, st);   // consumer of a folded LayerNorm
     return launch_nb<EPI, 8>(p, grid, st);
 }
 
@@ -877,6 +966,7 @@ static int check_skinny(const tw_skinny_args* a, const char* who) {
     TW_REQUIRE(a->k % 256 == 0, "%s: K (%d) must be a multiple of 256", who, a->k);
     TW_REQUIRE(a->ldx % 8 == 0 && ((uintptr_t)a->x & 15) == 0 && ((uintptr_t)a->w & 15) == 0, "%s: alignment", who);
     TW_REQUIRE(a->n > 0, "%s: bad N", who);
+    if (a->ln_stats_in) TW_REQUIRE(a->ln_c, "%s: a folded LayerNorm needs the W' row sums", who);
     return 0;
 }
 
@@ -889,6 +979,10 @@ static void fill_common(SkinnyParams& p, const tw_skinny_args* a) {
     p.B = a->batch;
     p.N = a->n;
     p.K = a->k;
+    if (a->ln_stats_in) {     // consumer of a folded LayerNorm (weights = W diag(gamma), bias = W beta + b)
+        p.ln_stats_in = (const float2*)a->ln_stats_in;
+        p.ln_c = a->ln_c;
+    }
 }
 
 extern "C" int tw_dec_linear(const tw_skinny_args* a, int32_t epilogue, void* out, int32_t ldo, void* stream) {
@@ -900,6 +994,15 @@ extern "C" int tw_dec_linear(const tw_skinny_args* a, int32_t epilogue, void* ou
     if (epilogue == 3) { p.out_bf16 = (__nv_bfloat16*)out; p.ldo = ldo; return launch_skinny<EPI_GELU_BF16>(p, (cudaStream_t)stream); }
     if (epilogue == 2) {
         p.resid = (float*)out;
+        TW_REQUIRE(!a->ln_stats_in, "tw_dec_linear: the residual epilogue cannot consume a folded LayerNorm");
+        if (a->ln_part_out) {
+            TW_REQUIRE(a->x_bf16_out && a->ln_stats_out && a->ln_counter && a->n % 16 == 0 && a->n <= 1536,
+                       "tw_dec_linear: a folded-LayerNorm producer needs x_bf16_out, ln_stats_out, ln_counter, n %% 16 == 0, n <= 1536");
+            p.ln_part_out = (float2*)a->ln_part_out;
+            p.xb_out = (__nv_bfloat16*)a->x_bf16_out;
+            p.ln_stats_out = (float2*)a->ln_stats_out;
+            p.ln_counter = a->ln_counter;
+        }
         if (a->ln_out_bf16) {
             TW_REQUIRE(a->ln_gamma && a->ln_beta && a->ln_counter, "tw_dec_linear: fused LayerNorm needs gamma, beta, counter");
             TW_REQUIRE(a->n <= 1280 && a->n % 128 == 0, "tw_dec_linear: fused LayerNorm supports n <= 1280, n %% 128 == 0");

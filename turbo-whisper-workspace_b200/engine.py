@@ -25,6 +25,9 @@ from ._lib import Grammar, SkinnyArgs, check
 from .config import N_FRAMES, N_SAMPLES, GenerationSettings, WhisperDims
 
 MAX_DECODE_BATCH = 32
+# timing probe only (results are WRONG): skip the LayerNorm fused into the residual projections, to measure what the
+# last-CTA LayerNorm tails cost per decode step (tools/probe_decode_tail.py)
+_PROBE_NO_LN = bool(os.environ.get("TWB200_PROBE_NO_LN"))
 _CAPTURE_LOCK = threading.Lock()   # CUDA-graph capture is serialised across the engine contexts of a process
 PAGE = 64
 ROWSTATE_INTS = 8
@@ -50,6 +53,13 @@ def pack_skinny_weight(w: torch.Tensor) -> torch.Tensor:
     if n_pad != n:
         w = torch.cat([w, torch.zeros(n_pad - n, k, dtype=w.dtype, device=w.device)], 0)
     return (w.view(n_pad // 16, 2, 8, k // 32, 4, 8).permute(0, 3, 1, 2, 4, 5).contiguous().view(n_pad, k))
+
+
+def ln_fold_enabled() -> bool:
+    """The decoder's LayerNorms are folded into the projections that consume them (csrc/decode.cu, LNF) unless
+    TWB200_NO_LN_FOLD is set — the round-1 form (a last-CTA LayerNorm fused into the residual projections) is kept for A/B
+    measurements."""
+    return not os.environ.get("TWB200_NO_LN_FOLD")
 
 
 def pack_weights(sd: Dict[str, torch.Tensor], dims: WhisperDims, device) -> Dict[str, torch.Tensor]:
@@ -129,9 +139,39 @@ def pack_weights(sd: Dict[str, torch.Tensor], dims: WhisperDims, device) -> Dict
     put("ckv_w", _bf16(torch.cat(ckv_w, 0)))
     put("ckv_b", torch.cat(ckv_b, 0))
     ln(dd + "layer_norm", "dec_ln")
+
+    def fold(dst, w_f32, b_f32, ln_src):
+        """LayerNorm folded into the projection that consumes it (csrc/decode.cu, LNF):
+        W LN(x) + b = rstd (W' x - mean c) + d,  W' = W diag(gamma), c = row sums of the bf16 W', d = W beta + b."""
+        g, be = _f32(sd[ln_src + ".weight"]), _f32(sd[ln_src + ".bias"])
+        wp = _bf16(w_f32 * g[None, :])
+        put(dst + "_wf", pack_skinny_weight(wp.to(dev)))
+        put(dst + "_c", wp.to(torch.float64).sum(dim=1).to(torch.float32))
+        put(dst + "_d", (w_f32.to(torch.float64) @ be.to(torch.float64)).to(torch.float32) + b_f32)
+
+    do_fold = ln_fold_enabled()
+    w["ln_fold"] = torch.tensor([1 if do_fold else 0])
     for i in range(dims.dec_layers):
-        for nm in ("qkv_w", "out_w", "cq_w", "cout_w", "fc1_w", "fc2_w"):
-            w[f"dec{i}.{nm}"] = pack_skinny_weight(w[f"dec{i}.{nm}"])
+        s = f"{dd}layers.{i}."
+        d = f"dec{i}."
+        if not do_fold:
+            for nm in ("qkv_w", "out_w", "cq_w", "cout_w", "fc1_w", "fc2_w"):
+                w[d + nm] = pack_skinny_weight(w[d + nm])
+            continue
+        if i > 0:      # layer 0's first LayerNorm is computed by the embedding kernel
+            a_ = s + "self_attn."
+            qw = torch.cat([_f32(sd[a_ + "q_proj.weight"]) * scale, _f32(sd[a_ + "k_proj.weight"]), _f32(sd[a_ + "v_proj.weight"])], 0)
+            vb_ = _f32(sd[a_ + "v_proj.bias"])
+            qb = torch.cat([_f32(sd[a_ + "q_proj.bias"]) * scale, torch.zeros_like(vb_), vb_], 0)
+            fold(d + "qkv", qw, qb, s + "self_attn_layer_norm")
+            del w[d + "qkv_w"]
+        fold(d + "cq", _f32(sd[s + "encoder_attn.q_proj.weight"]) * scale, _f32(sd[s + "encoder_attn.q_proj.bias"]) * scale,
+             s + "encoder_attn_layer_norm")
+        fold(d + "fc1", _f32(sd[s + "fc1.weight"]), _f32(sd[s + "fc1.bias"]), s + "final_layer_norm")
+        del w[d + "cq_w"], w[d + "fc1_w"]
+        for nm in ("qkv_w", "out_w", "cout_w", "fc2_w"):
+            if d + nm in w:
+                w[d + nm] = pack_skinny_weight(w[d + nm])
     w["tok_emb_frag"] = pack_skinny_weight(w["tok_emb"])
     return w
 
@@ -221,6 +261,9 @@ class WhisperEngine:
             self.state = z(Bm, ROWSTATE_INTS, dtype=i32)
             self.dx = z(Bm, D, dtype=f32)
             self.dxn = z(Bm, D, dtype=bf)
+            self.dxb = z(Bm, D, dtype=bf)                        # bf16 copy of the residual rows (operand of the folded-LayerNorm projections)
+            self.ln_part = z(D // 16, MAX_DECODE_BATCH, 2, dtype=f32)   # per-CTA (mean, M2) partials of the producer (scratch)
+            self.ln_stats = z(MAX_DECODE_BATCH, 2, dtype=f32)           # (mean, rstd) per row, left by the producer's last CTA
             self.dq = z(Bm, D, dtype=bf)
             self.datt = z(Bm, D, dtype=bf)
             self.dhid = z(Bm, F, dtype=bf)
@@ -245,6 +288,7 @@ class WhisperEngine:
         g.max_initial_ts = self.gen.max_initial_timestamp_index
         g.begin_index = 3
         self.grammar = g
+        self.ln_fold = bool(int(self.w["ln_fold"][0])) if "ln_fold" in self.w else False
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
         self._beam_ws: Dict[tuple, dict] = {}
         self._ckv_batch = max_batch
@@ -420,18 +464,28 @@ class WhisperEngine:
         return xn
 
     # ------------------------------------------------------------------------------------ decoder
-    def _skinny(self, wname, x, bias, B, k, ln=None):
-        """tw_skinny_args for W = self.w[wname].  For residual projections ``ln="dec0.ln2"`` makes the kernel's
-        last CTA write LayerNorm(updated x) into self.dxn (no separate LayerNorm launch)."""
+    def _skinny(self, wname, x, bias, B, k, ln=None, part_out=False, fold=None):
+        """tw_skinny_args for W = self.w[wname].
+        ``ln="dec_ln"`` (residual projections): the kernel's last CTA writes LayerNorm(updated x) into self.dxn.
+        ``part_out`` (residual projections): the kernel stores bf16(updated x) into self.dxb and per-CTA LayerNorm
+        partials into self.ln_part instead — the NEXT projection has that LayerNorm folded into its weights.
+        ``fold="dec1.cq"``: such a consumer — weights ``_wf`` (= W diag(gamma)), bias ``_d``, row sums ``_c``."""
         a = SkinnyArgs()
+        if fold is not None:
+            wname, bias = fold + "_wf", fold + "_d"
         wt = self.w[wname]
         a.w, a.x, a.ldx = wt.data_ptr(), x.data_ptr(), x.stride(0)
         a.bias = None if bias is None else self.w[bias].data_ptr()
         # fragment-major weights are padded to 16 rows: the true N is the bias length (the LM head has N = vocab)
         a.batch, a.n, a.k = B, (self.dims.vocab if bias is None else self.w[bias].shape[0]), k
-        if ln is not None:
+        if ln is not None and not _PROBE_NO_LN:
             a.ln_gamma, a.ln_beta = self.w[ln + "_w"].data_ptr(), self.w[ln + "_b"].data_ptr()
             a.ln_out_bf16, a.ln_counter = self.dxn.data_ptr(), self.ln_cnt.data_ptr()
+        if part_out:
+            a.ln_part_out, a.x_bf16_out = self.ln_part.data_ptr(), self.dxb.data_ptr()
+            a.ln_stats_out, a.ln_counter = self.ln_stats.data_ptr(), self.ln_cnt.data_ptr()
+        if fold is not None:
+            a.ln_stats_in, a.ln_c = self.ln_stats.data_ptr(), self.w[fold + "_c"].data_ptr()
         return a
 
     def _decode_step(self, B: int, finalize: bool = True) -> None:
@@ -445,34 +499,70 @@ class WhisperEngine:
                                B, D, p(w["dec0.ln1_w"]), p(w["dec0.ln1_b"]), p(self.dxn), st), "tw_dec_embed")
         Bc = self._ckv_batch                 # windows in the encoder batch that produced self.ckv
         blk = Bc * S * 64                    # elements per (layer, k|v, head) block of the head-major K/V
-        for i in range(L):
-            q = f"dec{i}."
-            nxt = f"dec{i + 1}.ln1" if i + 1 < L else "dec_ln"   # LayerNorm that follows this layer's fc2
-            pool = C.c_void_p(self.kv_pool[i].data_ptr())
-            check(lib.tw_dec_qkv(C.byref(self._skinny(q + "qkv_w", self.dxn, q + "qkv_b", B, D)), p(self.dq), pool,
-                                 p(self.block_table), self.pages_per_row, self.n_pages, p(self.state), st), "tw_dec_qkv")
-            check(lib.tw_dec_self_attn(p(self.dq), p(self.datt), pool, p(self.block_table), self.pages_per_row,
-                                       self.n_pages, p(self.state), B, H, st), "tw_dec_self_attn")
-            check(lib.tw_dec_linear(C.byref(self._skinny(q + "out_w", self.datt, q + "out_b", B, D, ln=q + "ln2")), 2,
-                                    p(self.dx), D, st), "self out_proj")
-            check(lib.tw_dec_linear(C.byref(self._skinny(q + "cq_w", self.dxn, q + "cq_b", B, D)), 0, p(self.dq), D, st),
-                  "cross q_proj")
-            kptr = C.c_void_p(self.ckv.data_ptr() + ((i * 2 + 0) * H) * blk * 2)
-            vptr = C.c_void_p(self.ckv.data_ptr() + ((i * 2 + 1) * H) * blk * 2)
-            if self._align_on and i in self.align["layers"]:
-                al = self.align
-                for slot0, heads_dev in al["layers"][i]:
-                    check(lib.tw_dec_align_tap(p(self.dq), D, kptr, 64, S * 64, blk, p(self.enc_row), p(self.state),
-                                               p(heads_dev), int(heads_dev.numel()), slot0, al["n_slots"], self.max_len,
-                                               S, B, p(al["probs"]), st), "tw_dec_align_tap")
-            check(lib.tw_dec_cross_attn(p(self.dq), p(self.datt), kptr, vptr, 64, S * 64, blk, p(self.enc_row), S, B, H,
-                                        self.cross_splits, p(self.cross_part), p(self.cross_cnt), st), "tw_dec_cross_attn")
-            check(lib.tw_dec_linear(C.byref(self._skinny(q + "cout_w", self.datt, q + "cout_b", B, D, ln=q + "ln3")), 2,
-                                    p(self.dx), D, st), "cross out_proj")
-            check(lib.tw_dec_linear(C.byref(self._skinny(q + "fc1_w", self.dxn, q + "fc1_b", B, D)), 3, p(self.dhid), F, st),
-                  "fc1")
-            check(lib.tw_dec_linear(C.byref(self._skinny(q + "fc2_w", self.dhid, q + "fc2_b", B, F, ln=nxt)), 2,
-                                    p(self.dx), D, st), "fc2")
+        if not self.ln_fold:
+            # round-1 form: a last-CTA LayerNorm fused into every residual projection (TWB200_NO_LN_FOLD, A/B only)
+            for i in range(L):
+                q = f"dec{i}."
+                nxt = f"dec{i + 1}.ln1" if i + 1 < L else "dec_ln"
+                pool = C.c_void_p(self.kv_pool[i].data_ptr())
+                check(lib.tw_dec_qkv(C.byref(self._skinny(q + "qkv_w", self.dxn, q + "qkv_b", B, D)), p(self.dq), pool,
+                                     p(self.block_table), self.pages_per_row, self.n_pages, p(self.state), st), "tw_dec_qkv")
+                check(lib.tw_dec_self_attn(p(self.dq), p(self.datt), pool, p(self.block_table), self.pages_per_row,
+                                           self.n_pages, p(self.state), B, H, st), "tw_dec_self_attn")
+                check(lib.tw_dec_linear(C.byref(self._skinny(q + "out_w", self.datt, q + "out_b", B, D, ln=q + "ln2")), 2,
+                                        p(self.dx), D, st), "self out_proj")
+                check(lib.tw_dec_linear(C.byref(self._skinny(q + "cq_w", self.dxn, q + "cq_b", B, D)), 0, p(self.dq), D, st),
+                      "cross q_proj")
+                kptr = C.c_void_p(self.ckv.data_ptr() + ((i * 2 + 0) * H) * blk * 2)
+                vptr = C.c_void_p(self.ckv.data_ptr() + ((i * 2 + 1) * H) * blk * 2)
+                if self._align_on and i in self.align["layers"]:
+                    al = self.align
+                    for slot0, heads_dev in al["layers"][i]:
+                        check(lib.tw_dec_align_tap(p(self.dq), D, kptr, 64, S * 64, blk, p(self.enc_row), p(self.state),
+                                                   p(heads_dev), int(heads_dev.numel()), slot0, al["n_slots"], self.max_len,
+                                                   S, B, p(al["probs"]), st), "tw_dec_align_tap")
+                check(lib.tw_dec_cross_attn(p(self.dq), p(self.datt), kptr, vptr, 64, S * 64, blk, p(self.enc_row), S, B, H,
+                                            self.cross_splits, p(self.cross_part), p(self.cross_cnt), st), "tw_dec_cross_attn")
+                check(lib.tw_dec_linear(C.byref(self._skinny(q + "cout_w", self.datt, q + "cout_b", B, D, ln=q + "ln3")), 2,
+                                        p(self.dx), D, st), "cross out_proj")
+                check(lib.tw_dec_linear(C.byref(self._skinny(q + "fc1_w", self.dxn, q + "fc1_b", B, D)), 3, p(self.dhid), F, st),
+                      "fc1")
+                check(lib.tw_dec_linear(C.byref(self._skinny(q + "fc2_w", self.dhid, q + "fc2_b", B, F, ln=nxt)), 2,
+                                        p(self.dx), D, st), "fc2")
+        else:
+            # Every LayerNorm but the first (embedding kernel) and the last (LM head operand) is folded into the projection
+            # that consumes it: the residual projections publish bf16(x) + per-CTA partials, no serial LayerNorm tail.
+            for i in range(L):
+                q = f"dec{i}."
+                last = i + 1 == L
+                pool = C.c_void_p(self.kv_pool[i].data_ptr())
+                qkv_args = self._skinny(q + "qkv_w", self.dxn, q + "qkv_b", B, D) if i == 0 else \
+                    self._skinny(None, self.dxb, None, B, D, fold=q + "qkv")
+                check(lib.tw_dec_qkv(C.byref(qkv_args), p(self.dq), pool,
+                                     p(self.block_table), self.pages_per_row, self.n_pages, p(self.state), st), "tw_dec_qkv")
+                check(lib.tw_dec_self_attn(p(self.dq), p(self.datt), pool, p(self.block_table), self.pages_per_row,
+                                           self.n_pages, p(self.state), B, H, st), "tw_dec_self_attn")
+                check(lib.tw_dec_linear(C.byref(self._skinny(q + "out_w", self.datt, q + "out_b", B, D, part_out=True)), 2,
+                                        p(self.dx), D, st), "self out_proj")
+                check(lib.tw_dec_linear(C.byref(self._skinny(None, self.dxb, None, B, D, fold=q + "cq")), 0, p(self.dq), D, st),
+                      "cross q_proj")
+                kptr = C.c_void_p(self.ckv.data_ptr() + ((i * 2 + 0) * H) * blk * 2)
+                vptr = C.c_void_p(self.ckv.data_ptr() + ((i * 2 + 1) * H) * blk * 2)
+                if self._align_on and i in self.align["layers"]:
+                    al = self.align
+                    for slot0, heads_dev in al["layers"][i]:
+                        check(lib.tw_dec_align_tap(p(self.dq), D, kptr, 64, S * 64, blk, p(self.enc_row), p(self.state),
+                                                   p(heads_dev), int(heads_dev.numel()), slot0, al["n_slots"], self.max_len,
+                                                   S, B, p(al["probs"]), st), "tw_dec_align_tap")
+                check(lib.tw_dec_cross_attn(p(self.dq), p(self.datt), kptr, vptr, 64, S * 64, blk, p(self.enc_row), S, B, H,
+                                            self.cross_splits, p(self.cross_part), p(self.cross_cnt), st), "tw_dec_cross_attn")
+                check(lib.tw_dec_linear(C.byref(self._skinny(q + "cout_w", self.datt, q + "cout_b", B, D, part_out=True)), 2,
+                                        p(self.dx), D, st), "cross out_proj")
+                check(lib.tw_dec_linear(C.byref(self._skinny(None, self.dxb, None, B, D, fold=q + "fc1")), 3, p(self.dhid), F, st),
+                      "fc1")
+                fc2 = self._skinny(q + "fc2_w", self.dhid, q + "fc2_b", B, F, ln="dec_ln") if last else \
+                    self._skinny(q + "fc2_w", self.dhid, q + "fc2_b", B, F, part_out=True)
+                check(lib.tw_dec_linear(C.byref(fc2), 2, p(self.dx), D, st), "fc2")
         check(lib.tw_dec_lmhead(C.byref(self._skinny("tok_emb_frag", self.dxn, None, B, D)), C.byref(self.grammar),
                                 p(self.state), p(self.sup_bits), p(self.bsup_bits), p(self.part_val), p(self.part_idx),
                                 None if self.logits is None else p(self.logits), st), "tw_dec_lmhead")
