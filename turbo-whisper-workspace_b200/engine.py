@@ -226,6 +226,7 @@ class WhisperEngine:
         self.dims, self.gen = dims, gen or GenerationSettings()
         self.device = torch.device(device)
         self.max_batch = max_batch
+        cross_splits = int(os.environ.get("TWB200_CROSS_SPLITS", cross_splits))    # tuning knob (tools/probe_decode_tail.py)
         self.cross_splits = cross_splits
         D, F, L, Bm = dims.d_model, dims.ffn, dims.dec_layers, max_batch
         self.max_enc_batch = Be = max(max_batch, int(max_enc_batch or 0))
