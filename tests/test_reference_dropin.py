@@ -121,3 +121,9 @@ def test_zero_touch_install_through_load_transcription_model(ap, tmp_path, monke
     finally:
         twb.uninstall()
     assert transformers.pipeline("x", model="y") == "lib"       # the original factory is back
+    # install(num_beams=5): the drop-in object decodes like the reference's literal call under transformers >= 4.53
+    twb.install(devices=["cuda:0"], loader=loader, builder=builder, num_beams=5)
+    try:
+        assert transformers.pipeline("automatic-speech-recognition", model="openai/whisper-large-v3").num_beams == 5
+    finally:
+        twb.uninstall()

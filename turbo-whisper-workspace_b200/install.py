@@ -56,11 +56,13 @@ def pipeline(task: Optional[str] = None, model: Any = None, *args, **kwargs):
     hf_model, tokenizer = loader(model, kwargs.get("tokenizer"))
     build = _OPTIONS.get("builder")
     if build is not None:                                   # tests / custom schedulers
-        return build(hf_model, tokenizer)
-    pipe = B200WhisperPipeline.from_hf_model(hf_model, tokenizer, devices=_OPTIONS["devices"],
-                                             max_batch=_OPTIONS["max_batch"],
-                                             contexts_per_device=_OPTIONS["contexts_per_device"])
-    pipe.num_beams = _OPTIONS.get("num_beams", 1)
+        pipe = build(hf_model, tokenizer)
+    else:
+        pipe = B200WhisperPipeline.from_hf_model(hf_model, tokenizer, devices=_OPTIONS["devices"],
+                                                 max_batch=_OPTIONS["max_batch"],
+                                                 contexts_per_device=_OPTIONS["contexts_per_device"])
+    if hasattr(pipe, "num_beams"):
+        pipe.num_beams = _OPTIONS.get("num_beams", 1)
     return pipe
 
 
