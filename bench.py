@@ -15,7 +15,7 @@ e2e     : the same work through the reference-facing callable (B200WhisperPipeli
 extras  : (own arm, unless --no-extras) the other BASELINE.json configs as extra keys of the same line:
           `encoder` (whole encoder at batch 24 vs the tensor-pipe peak), `decode_step` (µs per greedy step alone vs the
           HBM floor), `config3` (ONE 1 h file through the pipeline callable, sharded over the N ranks by the chunk
-          scheduler — strong scaling), `config4` (large-v3, 32 decoder layers, batch 16), `config5` (log-mel +
+          scheduler — strong scaling), `config2_beams5` (the 24 windows with num_beams = 5), `config4` (large-v3, 32 decoder layers, batch 16), `config5` (log-mel +
           encoder-only sweep, batch 1..256).
 The `--impl reference` arm times the reference's own CPU implementation of the path: every step is ONE real call of the
 reference's `AudioProcessingPipeline.process_audio(path, task="transcribe")` (the unmodified `vocalis` package installed
@@ -651,6 +651,24 @@ def run_extras(args, rank, world, dev, pipe, dims, tok, barrier, max_over_ranks,
         c3[name] = rec
     out["config3"] = c3
     del hour
+
+    # ---- config 2 with the reference's LITERAL decoding mode (transformers >= 4.53 pipelines default to num_beams = 5 and
+    # the reference passes only generate_kwargs={"task": ...}): 24 windows per GPU through the callable, beam search on the device
+    bclips = np.concatenate([helpers.synth_clip(rank * WINDOWS_PER_GPU + i) for i in range(WINDOWS_PER_GPU)])
+    bkw = dict(chunk_length_s=30, stride_length_s=0, batch_size=WINDOWS_PER_GPU, return_timestamps=True,
+               generate_kwargs={"task": "transcribe", "num_beams": 5})
+    pipe(bclips, **bkw)
+    barrier()
+    t0 = time.perf_counter()
+    rb = pipe(bclips, **bkw)
+    torch.cuda.synchronize()
+    (dtb,) = max_over_ranks(time.perf_counter() - t0)
+    out["config2_beams5"] = {"what": "config 2's 24 windows per GPU with generate_kwargs={'num_beams': 5} (the reference's literal "
+                                     "decoding mode under transformers >= 4.53): windows x beams decode rows, tw_beam_step on the "
+                                     "device, one CUDA graph per position", "n_gpus": world, "seconds": dtb,
+                             "rtfx": WINDOWS_PER_GPU * WINDOW_S * world / dtb, "chunks": len(rb["chunks"]),
+                             "microbatches": [b - a for a, b in pipe.scheduler.last_stats.get("microbatches", [])]}
+    del bclips
 
     # ---- config 4: large-v3 (32 decoder layers), batch 16 per GPU, decoder-heavy greedy decode
     torch.cuda.empty_cache()
