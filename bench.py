@@ -441,7 +441,10 @@ def run_own(args, rank, world, local_rank):
     dims = WhisperDims.large_v3_turbo()
     sd = helpers.random_state_dict(dims, 0, "hf")
     tok = helpers.build_tokenizer()
-    pipe = B200WhisperPipeline(sd, dims, tok, devices=[dev], max_batch=B, contexts_per_device=args.contexts)
+    MB = args.max_batch                     # decode rows per engine context = windows per generate call
+    if MB % B:
+        raise SystemExit("bench.py: --max-batch must be a multiple of 24")
+    pipe = B200WhisperPipeline(sd, dims, tok, devices=[dev], max_batch=MB, contexts_per_device=args.contexts)
     del sd
     engines = pipe.scheduler.flat_engines
     K = args.steps
@@ -465,18 +468,25 @@ def run_own(args, rank, world, local_rank):
     def stats_sum(key):
         return sum(e.stats.get(key, 0) for e in engines)
 
+    from turbo_whisper_workspace_b200.scheduler import balanced_microbatch
+
     def run_resident(n_steps):
-        """n_steps passes over the PCM already resident in each context's HBM buffer; the contexts of the GPU
-        take the steps round-robin on their own streams.  Returns per-context end events."""
+        """n_steps steps (24 windows each) over the PCM already resident in each context's HBM buffer.  The windows are
+        cut into equally sized generate calls exactly as the chunk scheduler cuts a job (`balanced_microbatch`: as few
+        calls as keep every context busy, at most MB windows each); the contexts take the calls round-robin on their
+        own streams.  Returns per-context end events and the rows of the last call."""
         ends, errs = [None] * len(engines), []
+        n_win = n_steps * B
+        mb = balanced_microbatch(n_win, len(engines), MB)
+        calls = [min(mb, n_win - a) for a in range(0, n_win, mb)]
 
         def work(ci):
             try:
                 eng = engines[ci]
                 with torch.cuda.stream(eng.stream) if eng.stream is not None else torch.cuda.stream(torch.cuda.current_stream()):
-                    for s_ in range(ci, n_steps, len(engines)):
-                        eng.features(B)
-                        work.rows = eng.generate(B)
+                    for k in range(ci, len(calls), len(engines)):
+                        eng.features(calls[k])
+                        work.rows = eng.generate(calls[k])
                     ev = torch.cuda.Event(enable_timing=True)
                     ev.record()
                     ends[ci] = ev
@@ -492,18 +502,20 @@ def run_own(args, rank, world, local_rank):
         return ends, getattr(work, "rows", None)
 
     # ---- device-resident leg ("value")
+    res_clips = clips * (MB // B)
     for eng in engines:
         if eng.stream is not None:
             with torch.cuda.stream(eng.stream):
-                eng.load_pcm(clips)
+                eng.load_pcm(res_clips)
         else:
-            eng.load_pcm(clips)
+            eng.load_pcm(res_clips)
     torch.cuda.synchronize()
-    run_resident(max(args.warmup, len(engines)))
+    for _ in range(-(-args.warmup // K)):  # >= W warm-up steps, cut into the SAME call sizes as the timed region
+        run_resident(K)                    # (a CUDA graph is captured per distinct row count: none inside the timing)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    l0, d0, w0 = stats_sum("launches"), stats_sum("dec_steps"), stats_sum("enc_windows")
+    l0, d0, w0, r0_ = stats_sum("launches"), stats_sum("dec_steps"), stats_sum("enc_windows"), stats_sum("dec_row_steps")
     e0 = torch.cuda.Event(enable_timing=True)
     e0.record()
     torch.cuda.synchronize()      # every context stream starts after e0
@@ -513,6 +525,7 @@ def run_own(args, rank, world, local_rank):
     launches = stats_sum("launches") - l0
     dec_steps = stats_sum("dec_steps") - d0
     enc_windows = stats_sum("enc_windows") - w0
+    dec_row_steps = stats_sum("dec_row_steps") - r0_
 
     # ---- end-to-end leg through the reference-facing callable
     pipe(audio[:B * 480000 * min(K, len(engines))], **kw)      # warm-up of the call path
@@ -533,7 +546,7 @@ def run_own(args, rank, world, local_rank):
         with torch.cuda.stream(engines[0].stream):
             single = engines[0].generate_from_pcm(clips)
     rows_ok = len(e2e_rows) == K * B and all(e2e_rows[i] == single[i % B] for i in range(len(e2e_rows)))
-    resident_ok = rows is not None and rows == single
+    resident_ok = rows is not None and all(rows[i] == single[i % B] for i in range(len(rows)))
 
     # ---- rooflines of the dominant kernels, measured live
     pk = peaks()
@@ -561,7 +574,12 @@ def run_own(args, rank, world, local_rank):
             "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": t_dev / K * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": workload_config(world),
-            "detail": {"contexts_per_gpu": len(engines), "decoder_steps_per_step": dec_steps // K,
+            "detail": {"contexts_per_gpu": len(engines), "max_windows_per_generate_call": MB,
+                       "scheduling": "a step is 24 windows (the pipeline call's batch_size); the chunk scheduler packs the "
+                                     "windows of the timed region into equally sized generate calls of up to 96 windows per "
+                                     "engine context — one pass over the decoder weights per decode step for all rows of a "
+                                     "call; results are batch-invariant (output_check)",
+                       "decoder_steps_per_step": dec_steps // K,
                        "encoder_windows_per_step": enc_windows // K},
             "e2e": {"value": audio_s / t_e2e, "unit": "x realtime", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": t_e2e / K * 1e3,
@@ -589,7 +607,10 @@ def run_own(args, rank, world, local_rank):
                             "us": step_us, "bytes": step_bytes, "floor_us": step_bytes / pk["hbm_gbs"] / 1e3,
                             "frac": step_bytes / pk["hbm_gbs"] / 1e3 / step_us,
                             "launches_per_step": eng0.launches_per_step,
-                            "in_bench_us": max(0.0, t_dev / K * 1e6 - (enc_windows / K / B) * enc_ms * 1e3) / max(1, dec_steps // K)},
+                            # decode share of the timed region per 24-row step: (time - encoder passes at the alone rate)
+                            # / (decode row-steps / 24)
+                            "in_bench_us": max(0.0, t_dev * 1e6 - (enc_windows / B) * enc_ms * 1e3) / max(1.0, dec_row_steps / B),
+                            "in_bench_note": "per 24 decode rows; calls decode up to 96 rows per step"},
             "output_check": {"chunks": len(result["chunks"]) if isinstance(result, dict) else None,
                              "rows": len(e2e_rows), "tokens_first_row": len(single[0]) if single else None,
                              "e2e_rows_equal_single_context": bool(rows_ok),
@@ -614,14 +635,27 @@ def run_own(args, rank, world, local_rank):
 
 
 def run_extras(args, rank, world, dev, pipe, dims, tok, barrier, max_over_ranks, pk):
+    out = {}
+    want = {x.strip() for x in args.extras.split(",") if x.strip()}
+    if "config3" in want:
+        out["config3"] = extra_config3(rank, world, pipe, dims, tok, barrier, max_over_ranks)
+    if "config2_beams5" in want:
+        out["config2_beams5"] = extra_beams5(rank, world, pipe, barrier, max_over_ranks)
+    if "config4" in want:
+        out["config4"] = extra_config4(rank, world, dev, barrier, max_over_ranks, pk)
+    if "config5" in want:
+        if rank == 0:       # the other ranks wait at the barrier
+            out["config5"] = extra_config5(dev, pipe, dims, pk)
+        barrier()
+    return out
+
+
+def extra_config3(rank, world, pipe, dims, tok, barrier, max_over_ranks):
     import numpy as np
     import torch
     import helpers
-    from turbo_whisper_workspace_b200.config import WhisperDims
-    from turbo_whisper_workspace_b200.engine import WhisperEngine
     from turbo_whisper_workspace_b200.pipeline import B200WhisperPipeline
     from turbo_whisper_workspace_b200.scheduler import DistributedWindowScheduler
-    out = {}
     # ---- config 3: ONE 1 h file through the pipeline callable, windows sharded over the ranks by the chunk scheduler
     hour = np.concatenate([helpers.synth_clip(1000 + i) for i in range(120)])          # 3600 s, same on every rank
     dpipe = pipe if world == 1 else B200WhisperPipeline(
@@ -649,9 +683,13 @@ def run_extras(args, rank, world, dev, pipe, dims, tok, barrier, max_over_ranks,
                 rec["equal_to_one_gpu"] = bool(pipe(hour, **ckw) == r)
             barrier()
         c3[name] = rec
-    out["config3"] = c3
-    del hour
+    return c3
 
+
+def extra_beams5(rank, world, pipe, barrier, max_over_ranks):
+    import numpy as np
+    import torch
+    import helpers
     # ---- config 2 with the reference's LITERAL decoding mode (transformers >= 4.53 pipelines default to num_beams = 5 and
     # the reference passes only generate_kwargs={"task": ...}): 24 windows per GPU through the callable, beam search on the device
     bclips = np.concatenate([helpers.synth_clip(rank * WINDOWS_PER_GPU + i) for i in range(WINDOWS_PER_GPU)])
@@ -663,13 +701,18 @@ def run_extras(args, rank, world, dev, pipe, dims, tok, barrier, max_over_ranks,
     rb = pipe(bclips, **bkw)
     torch.cuda.synchronize()
     (dtb,) = max_over_ranks(time.perf_counter() - t0)
-    out["config2_beams5"] = {"what": "config 2's 24 windows per GPU with generate_kwargs={'num_beams': 5} (the reference's literal "
+    return {"what": "config 2's 24 windows per GPU with generate_kwargs={'num_beams': 5} (the reference's literal "
                                      "decoding mode under transformers >= 4.53): windows x beams decode rows, tw_beam_step on the "
                                      "device, one CUDA graph per position", "n_gpus": world, "seconds": dtb,
                              "rtfx": WINDOWS_PER_GPU * WINDOW_S * world / dtb, "chunks": len(rb["chunks"]),
                              "microbatches": [b - a for a, b in pipe.scheduler.last_stats.get("microbatches", [])]}
-    del bclips
 
+
+def extra_config4(rank, world, dev, barrier, max_over_ranks, pk):
+    import torch
+    import helpers
+    from turbo_whisper_workspace_b200.config import WhisperDims
+    from turbo_whisper_workspace_b200.engine import WhisperEngine
     # ---- config 4: large-v3 (32 decoder layers), batch 16 per GPU, decoder-heavy greedy decode
     torch.cuda.empty_cache()
     d4 = WhisperDims.large_v3()
@@ -684,7 +727,7 @@ def run_extras(args, rank, world, dev, pipe, dims, tok, barrier, max_over_ranks,
     steps4 = e4.stats["dec_steps"] - s0
     step_us4, step_bytes4 = decode_step_probe(e4, 16)
     (dt4,) = max_over_ranks(dt4)
-    out["config4"] = {"what": "whisper-large-v3 dims (32 decoder layers), bf16, 16 windows per GPU in one batch, greedy "
+    rec = {"what": "whisper-large-v3 dims (32 decoder layers), bf16, 16 windows per GPU in one batch, greedy "
                               "with timestamps, random-init (decodes to max_length: decoder-heavy); one engine context",
                       "n_gpus": world, "seconds": dt4, "rtfx": 16 * WINDOW_S * world / dt4, "decoder_steps": steps4,
                       "tokens_first_rows": [len(r) for r in rows4[:4]],
@@ -693,9 +736,15 @@ def run_extras(args, rank, world, dev, pipe, dims, tok, barrier, max_over_ranks,
                                       "launches_per_step": e4.launches_per_step}}
     del e4
     torch.cuda.empty_cache()
+    return rec
 
-    # ---- config 5: log-mel + encoder-only sweep (rank 0; the other ranks wait at the barrier)
-    if rank == 0:
+
+def extra_config5(dev, pipe, dims, pk):
+    import torch
+    import helpers
+    from turbo_whisper_workspace_b200.engine import WhisperEngine
+    # ---- config 5: log-mel + encoder-only sweep
+    if True:
         batches = [1, 2, 4, 8, 16, 24, 32, 64, 128, 256]
         e5 = WhisperEngine(dims, None, device=dev, max_batch=24, max_enc_batch=max(batches),
                            shared_weights=pipe.scheduler.flat_engines[0].w)
@@ -712,13 +761,12 @@ def run_extras(args, rank, world, dev, pipe, dims, tok, barrier, max_over_ranks,
                           "logmel_frac_hbm": round(mel_bytes / mel_ms / 1e6 / pk["hbm_gbs"], 3),
                           "encoder_ms": round(enc_ms, 3), "encoder_TFLOPs": round(enc_flops / enc_ms / 1e9, 1),
                           "encoder_frac_burst": round(enc_flops / enc_ms / 1e9 / pk["bf16_tflops"], 3)})
-        out["config5"] = {"what": "log-mel front end (fp32 PCM in, bf16 time-major features out: 2.688 MB / window) and "
+        rec = {"what": "log-mel front end (fp32 PCM in, bf16 time-major features out: 2.688 MB / window) and "
                                   "encoder-only pass (2.2738 TFLOP + cross-K/V GEMM per window), one context, CUDA events",
-                          "sweep": sweep}
+               "sweep": sweep}
         del e5
         torch.cuda.empty_cache()
-    barrier()
-    return out
+    return rec
 
 
 _RESULT_FD = None
@@ -749,7 +797,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the config3 / config4 / config5 extra keys")
-    ap.add_argument("--contexts", type=int, default=4, help="engine contexts (streams) per GPU sharing one weight copy")
+    ap.add_argument("--extras", default="config3,config2_beams5,config4,config5",
+                    help="comma-separated subset of the extra keys to measure")
+    ap.add_argument("--contexts", type=int, default=5, help="engine contexts (streams) per GPU sharing one weight copy")
+    ap.add_argument("--max-batch", type=int, default=96,
+                    help="most windows per generate call of an engine context (multiple of 24, <= 96): the decoder weights "
+                         "are streamed once per decode step for all rows of a call")
     ap.add_argument("--reference-budget-s", type=float, default=480.0,
                     help="reference arm: stop after the call that crosses this wall-clock budget (steps reports the calls made)")
     args = ap.parse_args()

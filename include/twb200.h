@@ -199,6 +199,10 @@ int tw_dec_cross_attn(const void* q_bf16, void* out_bf16, const void* k_bf16, co
  * part_val fp32 [batch][parts][3], part_idx int32 [batch][parts][2], parts = tw_dec_lmhead_parts(vocab).
  * logits_out: optional raw fp32 logits [batch, vocab] (parity tests), else NULL. */
 int32_t tw_dec_lmhead_parts(int32_t vocab);
+/* row stride of the LayerNorm scratch buffers (ln_part_out [n / 16][rows], ln_stats [rows]) = the most decode rows a
+ * tw_dec_linear / tw_dec_qkv launch accepts (128); tw_dec_lmhead accepts up to 48 per launch (the engine launches it per
+ * 48-row chunk).  Beyond 32 rows the projections walk the rows in chunks of 24 with ONE pass over their weights. */
+int32_t tw_dec_max_rows(void);
 int tw_dec_lmhead(const tw_skinny_args* args, const tw_grammar* g, const void* row_state,
                   const uint32_t* suppress_bits, const uint32_t* begin_suppress_bits, float* part_val,
                   int32_t* part_idx, float* logits_out, void* stream);

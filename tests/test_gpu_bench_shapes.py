@@ -9,7 +9,11 @@ oracle's fp32 modules run on the GPU with TF32 off, fed the engine's encoder sta
       to the same windows decoded 6 at a time (the NB = 1 instantiation the other full-size tests pin to the oracle);
   (c) large-v3 dims (32 decoder layers, BASELINE.json config 4), B = 16, teacher-forced logits;
   (d) four engine contexts sharing one weight copy (bench.py's mode, `contexts_per_device=4`) give exactly the tokens
-      of a single context, through the scheduler and through the pipeline callable.
+      of a single context, through the scheduler and through the pipeline callable;
+  (e) WIDE generate calls (round 2: bench.py packs up to 96 windows into one call so that the decoder weights are
+      streamed once per decode step): 40 / 72 / 96 rows on tiny dims vs the oracle (row chunks of 24 in every
+      projection, `lmhead_kernel<5|6>`, two LM-head launches), and a full-size 96-row call == the same windows six at
+      a time.
 The file name sorts before the other GPU files so that `pytest -x` reaches it first.
 """
 import numpy as np
@@ -55,22 +59,23 @@ def tiny(cuda_device):
     from oracle import whisper_ref as R
     from turbo_whisper_workspace_b200.config import WhisperDims
     from turbo_whisper_workspace_b200.engine import WhisperEngine
-    clips = _clips(32)
+    clips = _clips(96)
     feats = torch.stack([torch.from_numpy(L.log_mel(c)) for c in clips]).to(torch.bfloat16).float()
     rd = R.WhisperDims(**helpers.TINY)
     sd = helpers.variant_state_dict(rd, "decisive")
     ref = R.WhisperRef(rd, sd)
-    eng = WhisperEngine(WhisperDims(**helpers.TINY), sd, device=cuda_device, max_batch=32)
+    eng = WhisperEngine(WhisperDims(**helpers.TINY), sd, device=cuda_device, max_batch=96)
     eng.enable_taps()
-    # windows are independent units for the oracle as well: rows 0..23 of the 32-row pass serve the B = 24 tests
+    # windows are independent units for the oracle as well: rows 0..B-1 of ONE 96-row oracle pass serve every B below
     it0 = oracle_first_iteration(ref, feats)
     return clips, feats, ref, eng, it0
 
 
-@pytest.mark.parametrize("B", [24, 32])
+@pytest.mark.parametrize("B", [24, 32, 40, 72, 96])
 def test_teacher_forced_logits_tiny_nb3_nb4(tiny, B):
-    """B = 24 -> NB = 3, B = 32 -> NB = 4 of every decode GEMM and of the LM head: raw logits at the oracle's recorded
-    steps and every decisive un-forced pick of the first seek iteration, language ids included."""
+    """B = 24 -> NB = 3, B = 32 -> NB = 4 of every decode GEMM and of the LM head; B = 40 / 72 / 96 -> row chunks of 24 in
+    the projections (one pass over the weights), `lmhead_kernel<5>`, `<6>` + `<3>`, two `<6>` launches: raw logits at the
+    oracle's recorded steps and every decisive un-forced pick of the first seek iteration, language ids included."""
     from oracle import whisper_ref as R
     clips, feats, ref, eng, it0 = tiny
     toks = it0["tokens"][:B]
@@ -106,7 +111,7 @@ def test_teacher_forced_logits_tiny_nb3_nb4(tiny, B):
     assert disagree == 0, f"B={B}: {disagree} of {checked} decisive picks differ from the oracle"
 
 
-@pytest.mark.parametrize("B", [24, 32])
+@pytest.mark.parametrize("B", [24, 32, 96])
 def test_free_running_generate_tiny_nb3_nb4(tiny, B):
     """Free-running seek loop at 24 / 32 rows (row retirement changes NB between iterations): the first iteration of
     every row is identical to the oracle's up to the row's first NON-decisive oracle step (north-star rule); the
@@ -212,17 +217,18 @@ def turbo24(cuda_device):
     torch.backends.cudnn.allow_tf32 = False
     rd = R.WhisperDims()
     sd = helpers.variant_state_dict(rd, "varied", seed=3)
-    eng = WhisperEngine(WhisperDims.large_v3_turbo(), sd, device=cuda_device, max_batch=24)
+    eng = WhisperEngine(WhisperDims.large_v3_turbo(), sd, device=cuda_device, max_batch=96)
     eng.enable_taps()
     ref = R.WhisperRef(rd, {k: v.to(cuda_device) for k, v in sd.items()})
-    return eng, ref, _clips(24, seed0=300)
+    return eng, ref, _clips(96, seed0=300)
 
 
-def test_decoder_logits_turbo_batch24_vs_fp32_reference(turbo24, cuda_device):
+@pytest.mark.parametrize("B", [24, 96])
+def test_decoder_logits_turbo_batch24_vs_fp32_reference(turbo24, cuda_device, B):
     """BASELINE.json config 2 / bench.py: large-v3-turbo dims, 24 rows (skinny_gemm_kernel<3,...>, lmhead_kernel<3>,
-    cross-attention split combine at 24 rows)."""
+    cross-attention split combine at 24 rows) and the 96-row generate call the bench packs its windows into."""
     eng, ref, clips = turbo24
-    _teacher_forced_vs_fp32(eng, ref, clips, 24, cuda_device)
+    _teacher_forced_vs_fp32(eng, ref, clips, B, cuda_device)
 
 
 def test_generate_turbo_batch24_equals_batches_of_six(turbo24):
@@ -230,12 +236,15 @@ def test_generate_turbo_batch24_equals_batches_of_six(turbo24):
     must give exactly the rows of the same windows decoded six at a time (NB = 1, the instantiation
     tests/test_gpu_fullsize.py pins to the fp32 reference)."""
     eng, ref, clips = turbo24
-    all24 = eng.generate_from_pcm(clips)
     six = []
-    for i in range(0, 24, 6):
+    for i in range(0, 96, 6):
         six += eng.generate_from_pcm(clips[i:i + 6])
-    assert all24 == six
-    assert all(len(r) > 0 for r in all24)
+    assert eng.generate_from_pcm(clips[:24]) == six[:24]
+    assert all(len(r) > 0 for r in six)
+    # the bench's wide calls: 96 windows (4 row chunks per projection, 2 LM-head launches), 72 and 40 (lmhead<6>+<3>, <5>)
+    assert eng.generate_from_pcm(clips) == six
+    assert eng.generate_from_pcm(clips[:72]) == six[:72]
+    assert eng.generate_from_pcm(clips[:40]) == six[:40]
 
 
 def test_decoder_logits_large_v3_batch16_vs_fp32_reference(cuda_device):

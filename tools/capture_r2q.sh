@@ -1,0 +1,22 @@
+#!/usr/bin/env bash
+set -u
+T=${1:-r2q}
+mkdir -p gpurun_out
+run() {
+  label=$1; shift
+  timeout 600 python bench.py --steps 12 --warmup 3 --no-extras --no-cpu-baseline "$@" 2>gpurun_out/${T}_err_$label.txt | python -c "
+import json,sys
+l=sys.stdin.readline()
+if not l.strip(): print(json.dumps({'cfg':'$label','error':'no line'})); sys.exit(0)
+d=json.loads(l)
+print(json.dumps({'cfg':'$label','value':round(d['value'],1),'e2e':round(d['e2e']['value'],1),'ms_per_step':round(d['ms_per_step'],1),'steps':d['steps'],'ok':[d['output_check']['e2e_rows_equal_single_context'],d['output_check']['resident_rows_equal_single_context']]}))" | tee -a gpurun_out/${T}_bench_ab.jsonl
+  grep -iE "error|Traceback" -A3 gpurun_out/${T}_err_$label.txt | head -8 | cut -c1-300
+}
+run mb24_c4 --max-batch 24 --contexts 4
+run mb48_c4 --max-batch 48 --contexts 4
+run mb48_c6 --max-batch 48 --contexts 6
+run mb72_c3 --max-batch 72 --contexts 3
+run mb72_c4 --max-batch 72 --contexts 4
+run mb96_c2 --max-batch 96 --contexts 2
+run mb96_c3 --max-batch 96 --contexts 3
+run mb96_c4 --max-batch 96 --contexts 4

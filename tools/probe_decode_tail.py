@@ -9,7 +9,10 @@ import bench, helpers
 from turbo_whisper_workspace_b200.config import WhisperDims
 from turbo_whisper_workspace_b200.engine import WhisperEngine
 dev = torch.device("cuda:0")
-for name, dims, B in (("turbo", WhisperDims.large_v3_turbo(), 24), ("large-v3", WhisperDims.large_v3(), 16)):
+cases = [("turbo", WhisperDims.large_v3_turbo(), 24), ("large-v3", WhisperDims.large_v3(), 16)]
+if os.environ.get("PROBE_B48"):
+    cases = [("turbo", WhisperDims.large_v3_turbo(), 24), ("turbo", WhisperDims.large_v3_turbo(), 48)]
+for name, dims, B in cases:
     eng = WhisperEngine(dims, bench.synth_state_dict_on_device(dims, dev, 0), device=dev, max_batch=B)
     eng.load_pcm([helpers.synth_clip(i) for i in range(B)])
     eng.features(B)

@@ -76,6 +76,7 @@ SIGNATURES = {
     "tw_dec_cross_attn": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int32,
                                     c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "tw_dec_lmhead_parts": (c_int32, [c_int32]),
+    "tw_dec_max_rows": (c_int32, []),
     "tw_dec_lmhead": (C.c_int, [C.POINTER(SkinnyArgs), C.POINTER(Grammar), c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p]),
     "tw_dec_finalize": (C.c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_void_p,

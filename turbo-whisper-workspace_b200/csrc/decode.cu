@@ -25,7 +25,7 @@
 namespace tw {
 namespace dec {
 
-constexpr int MAXB = 32;
+constexpr int MAXB = 128;  // decode rows per launch (ln_part / ln_stats strides; engine.MAX_DECODE_BATCH <= this)
 constexpr int PAGE = 64;  // positions per KV page
 
 // ------------------------------------------------------------------------------------------------
@@ -251,12 +251,6 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 2 : 1) skinny_gemm_
     // fragment-major weights (see frag_ptr): one 16-byte fragment per lane, 512 contiguous bytes per warp load
     const __nv_bfloat16* wa = frag_ptr(p.W, p.K, blockIdx.x, k_begin >> 5, lane);
     const __nv_bfloat16* wb = wa + FRAG_HALF;
-    const __nv_bfloat16* xr[NB];
-#pragma unroll
-    for (int j = 0; j < NB; ++j) xr[j] = p.X + (size_t)min(j * 8 + g, p.B - 1) * p.ldx + k_begin + tg * 8;
-    float acc[NB][4];
-#pragma unroll
-    for (int j = 0; j < NB; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
 
     // the weights do not depend on the previous kernel: the first round of weight fragments is requested
     // before the programmatic-dependency wait, so the stream overlaps the predecessor's tail
@@ -271,12 +265,23 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 2 : 1) skinny_gemm_
         s_mu[threadIdx.x] = st2.x;
         s_rs[threadIdx.x] = st2.y;
     }
+    // Row chunks of NB * 8 decode rows: with more than 32 rows in a launch (several micro-batches decoded together) the
+    // CTA's weight slab is streamed from DRAM ONCE — it stays in registers when K fits one round (K = 1280), later
+    // chunks of a longer K re-read it from L2 — so the weight bytes per decode step do not grow with the rows.
+    for (int rb = 0; rb < p.B; rb += NB * 8) {
+    if (rb > 0) __syncthreads();        // `red` of the previous chunk has been consumed
+    const __nv_bfloat16* xr[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) xr[j] = p.X + (size_t)min(rb + j * 8 + g, p.B - 1) * p.ldx + k_begin + tg * 8;
+    float acc[NB][4];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
     for (int s0 = 0; s0 < steps; s0 += UN) {
         uint4 xb[UN][NB];
 #pragma unroll
         for (int u = 0; u < UN; ++u) {
             if (s0 + u < steps) {
-                if (s0 > 0) { alo[u] = ldg_stream(wa + (s0 + u) * FRAG_STEP); ahi[u] = ldg_stream(wb + (s0 + u) * FRAG_STEP); }
+                if (s0 > 0 || (rb > 0 && steps > UN)) { alo[u] = ldg_stream(wa + (s0 + u) * FRAG_STEP); ahi[u] = ldg_stream(wb + (s0 + u) * FRAG_STEP); }
 #pragma unroll
                 for (int j = 0; j < NB; ++j) xb[u][j] = __ldg(reinterpret_cast<const uint4*>(xr[j] + (s0 + u) * 32));
             }
@@ -302,7 +307,8 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 2 : 1) skinny_gemm_
     __syncthreads();
 
     for (int o = threadIdx.x; o < NB * 8 * 16; o += NT) {
-        const int bb = o >> 4, rr = o & 15;
+        const int bl = o >> 4, rr = o & 15;     // row within the chunk / feature within the slab
+        const int bb = rb + bl;                 // decode row
         const int n = n0 + rr;
         const bool live = bb < p.B && n < p.N;
         if (EPI == EPI_RESID && p.ln_part_out) {
@@ -312,7 +318,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 2 : 1) skinny_gemm_
             if (live) {
                 float v = 0.f;
 #pragma unroll
-                for (int w = 0; w < WARPS; ++w) v += red[w][bb][rr];
+                for (int w = 0; w < WARPS; ++w) v += red[w][bl][rr];
                 if (p.bias) v += p.bias[n];
                 x = p.resid[(size_t)bb * p.N + n] + v;
                 p.resid[(size_t)bb * p.N + n] = x;
@@ -331,7 +337,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 2 : 1) skinny_gemm_
         if (!live) continue;
         float v = 0.f;
 #pragma unroll
-        for (int w = 0; w < WARPS; ++w) v += red[w][bb][rr];
+        for (int w = 0; w < WARPS; ++w) v += red[w][bl][rr];
         if (LNF) v = s_rs[bb] * (v - s_mu[bb] * p.ln_c[n]);
         if (p.bias) v += p.bias[n];
         if (EPI == EPI_BF16) {
@@ -353,6 +359,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 2 : 1) skinny_gemm_
             }
         }
     }
+    }   // row chunks
     if (EPI == EPI_RESID && p.ln_stats_out) {
         // last CTA: (mean, rstd) of every row from the N / 16 per-CTA partials.  All partials count 16 values, so
         // mean = avg(m_c) and M2 = sum(M2_c + 16 (m_c - mean)^2): two fixed-order warp reductions per row.
@@ -369,10 +376,11 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 2 : 1) skinny_gemm_
             const int parts = gridDim.x;
             constexpr int RPW = (NB * 8 + WARPS - 1) / WARPS;
             constexpr int PPL = 3;           // partials per lane (N <= 1536)
+            for (int rw = warp; rw < p.B; rw += WARPS * RPW) {     // one pass per row chunk
             float2 pr[RPW][PPL];
 #pragma unroll
             for (int i = 0; i < RPW; ++i) {
-                const int r = warp + i * WARPS;
+                const int r = rw + i * WARPS;
 #pragma unroll
                 for (int t = 0; t < PPL; ++t) {
                     const int c = lane + 32 * t;
@@ -382,7 +390,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 2 : 1) skinny_gemm_
             const float inv_parts = 1.0f / (float)parts;
 #pragma unroll
             for (int i = 0; i < RPW; ++i) {
-                const int r = warp + i * WARPS;
+                const int r = rw + i * WARPS;
                 const float mean = warp_sum((pr[i][0].x + pr[i][1].x) + pr[i][2].x) * inv_parts;
                 float q = 0.f;
 #pragma unroll
@@ -392,6 +400,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 2 : 1) skinny_gemm_
                 }
                 q = warp_sum(q);
                 if (lane == 0 && r < p.B) p.ln_stats_out[r] = make_float2(mean, rsqrtf(q / (float)p.N + 1e-5f));
+            }
             }
         }
     }
@@ -921,7 +930,9 @@ static_assert(sizeof(RowState) == 32, "RowState layout is part of the ABI (8 x i
 
 template <int EPI, int WARPS, bool LNF = false>
 static int launch_nb(const SkinnyParams& p, int grid, cudaStream_t st) {
-    switch ((p.B + 7) / 8) {
+    // rows per chunk: up to 32 rows one chunk of ceil(B / 8) groups; beyond that chunks of 24 rows (NB = 3: no spills)
+    const int nb = p.B <= 32 ? (p.B + 7) / 8 : 3;
+    switch (nb) {
         case 1: TW_CUDA_CHECK(launch_pdl(skinny_gemm_kernel<1, EPI, WARPS, LNF>, dim3(grid), dim3(WARPS * 32), 0, st, p)); break;
         case 2: TW_CUDA_CHECK(launch_pdl(skinny_gemm_kernel<2, EPI, WARPS, LNF>, dim3(grid), dim3(WARPS * 32), 0, st, p)); break;
         case 3: TW_CUDA_CHECK(launch_pdl(skinny_gemm_kernel<3, EPI, WARPS, LNF>, dim3(grid), dim3(WARPS * 32), 0, st, p)); break;
@@ -1041,6 +1052,7 @@ static GrammarConst to_gc(const tw_grammar* g) {
 
 // number of partial records per batch row = warps of the persistent LM-head grid (one CTA per SM)
 static int lmhead_grid() { int n = num_sms(); return n > 0 ? n : 148; }
+extern "C" int32_t tw_dec_max_rows(void) { return MAXB; }
 extern "C" int32_t tw_dec_lmhead_parts(int32_t vocab) {
     (void)vocab;
     return lmhead_grid() * LMH_WARPS;
@@ -1068,7 +1080,9 @@ extern "C" int tw_dec_lmhead(const tw_skinny_args* a, const tw_grammar* g, const
         case 2: TW_CUDA_CHECK(launch_pdl(lmhead_kernel<2>, dim3(grid), dim3(LMH_WARPS * 32), 0, st, p)); break;
         case 3: TW_CUDA_CHECK(launch_pdl(lmhead_kernel<3>, dim3(grid), dim3(LMH_WARPS * 32), 0, st, p)); break;
         case 4: TW_CUDA_CHECK(launch_pdl(lmhead_kernel<4>, dim3(grid), dim3(LMH_WARPS * 32), 0, st, p)); break;
-        default: set_error("tw_dec_lmhead: batch %d > %d", p.B, MAXB); return 2;
+        case 5: TW_CUDA_CHECK(launch_pdl(lmhead_kernel<5>, dim3(grid), dim3(LMH_WARPS * 32), 0, st, p)); break;
+        case 6: TW_CUDA_CHECK(launch_pdl(lmhead_kernel<6>, dim3(grid), dim3(LMH_WARPS * 32), 0, st, p)); break;
+        default: set_error("tw_dec_lmhead: batch %d > 48", p.B); return 2;
     }
     TW_CUDA_CHECK(cudaGetLastError());
     return 0;

@@ -24,7 +24,8 @@ from . import _lib, ops
 from ._lib import Grammar, SkinnyArgs, check
 from .config import N_FRAMES, N_SAMPLES, GenerationSettings, WhisperDims
 
-MAX_DECODE_BATCH = 32
+MAX_DECODE_BATCH = 96   # decode rows per engine context (projections: up to tw_dec_max_rows(); the LM head runs per 48-row chunk)
+LMHEAD_ROWS = 48
 # timing probe only (results are WRONG): skip the LayerNorm fused into the residual projections, to measure what the
 # last-CTA LayerNorm tails cost per decode step (tools/probe_decode_tail.py)
 _PROBE_NO_LN = bool(os.environ.get("TWB200_PROBE_NO_LN"))
@@ -263,8 +264,9 @@ class WhisperEngine:
             self.dx = z(Bm, D, dtype=f32)
             self.dxn = z(Bm, D, dtype=bf)
             self.dxb = z(Bm, D, dtype=bf)                        # bf16 copy of the residual rows (operand of the folded-LayerNorm projections)
-            self.ln_part = z(D // 16, MAX_DECODE_BATCH, 2, dtype=f32)   # per-CTA (mean, M2) partials of the producer (scratch)
-            self.ln_stats = z(MAX_DECODE_BATCH, 2, dtype=f32)           # (mean, rstd) per row, left by the producer's last CTA
+            ln_rows = int(_lib.load().tw_dec_max_rows())                 # row stride the kernels use for these buffers
+            self.ln_part = z(D // 16, ln_rows, 2, dtype=f32)            # per-CTA (mean, M2) partials of the producer (scratch)
+            self.ln_stats = z(ln_rows, 2, dtype=f32)                    # (mean, rstd) per row, left by the producer's last CTA
             self.dq = z(Bm, D, dtype=bf)
             self.datt = z(Bm, D, dtype=bf)
             self.dhid = z(Bm, F, dtype=bf)
@@ -564,9 +566,12 @@ class WhisperEngine:
                 fc2 = self._skinny(q + "fc2_w", self.dhid, q + "fc2_b", B, F, ln="dec_ln") if last else \
                     self._skinny(q + "fc2_w", self.dhid, q + "fc2_b", B, F, part_out=True)
                 check(lib.tw_dec_linear(C.byref(fc2), 2, p(self.dx), D, st), "fc2")
-        check(lib.tw_dec_lmhead(C.byref(self._skinny("tok_emb_frag", self.dxn, None, B, D)), C.byref(self.grammar),
-                                p(self.state), p(self.sup_bits), p(self.bsup_bits), p(self.part_val), p(self.part_idx),
-                                None if self.logits is None else p(self.logits), st), "tw_dec_lmhead")
+        for r0 in range(0, B, LMHEAD_ROWS):      # the LM head kernel holds its per-row partials in registers: 48 rows per launch
+            rows = min(LMHEAD_ROWS, B - r0)
+            check(lib.tw_dec_lmhead(C.byref(self._skinny("tok_emb_frag", self.dxn[r0:], None, rows, D)), C.byref(self.grammar),
+                                    p(self.state[r0:]), p(self.sup_bits), p(self.bsup_bits), p(self.part_val[r0:]),
+                                    p(self.part_idx[r0:]), None if self.logits is None else p(self.logits[r0:]), st),
+                  "tw_dec_lmhead")
         if finalize:
             check(lib.tw_dec_finalize(p(self.part_val), p(self.part_idx), self.n_parts, p(self.tokens), self.max_len,
                                       p(self.forced), None if self.choices is None else p(self.choices), p(self.state),
@@ -575,7 +580,7 @@ class WhisperEngine:
     @property
     def launches_per_step(self) -> int:
         taps = sum(len(r) for r in self.align["layers"].values()) if self._align_on else 0
-        return 1 + 8 * self.dims.dec_layers + 2 + taps
+        return 1 + 8 * self.dims.dec_layers + 2 + taps      # (+ one more LM-head launch per 48 rows beyond the first 48)
 
     def _graph_for(self, B: int) -> torch.cuda.CUDAGraph:
         # the K/V block stride depends on the encoder batch; begin_index (3 / 4 with <|notimestamps|>) is a kernel argument
@@ -649,7 +654,8 @@ class WhisperEngine:
                         steps = s + 1
                         break
             self.stats["dec_steps"] += steps
-            self.stats["launches"] += steps * self.launches_per_step
+            self.stats["dec_row_steps"] = self.stats.get("dec_row_steps", 0) + steps * B
+            self.stats["launches"] += steps * (self.launches_per_step + (B - 1) // LMHEAD_ROWS)
             return self.tokens[:B]
 
     # ------------------------------------------------------------------------------------ beam search
