@@ -556,9 +556,19 @@ def run_own(args, rank, world, local_rank):
         eng0.load_pcm(clips)
         eng0.features(B)
         enc_ms = cuda_timed(lambda: eng0.encode(B), iters=3, warm=1)
-        ca_ms, ca_bytes = cross_attn_roofline_probe(eng0, B)
+        ca24_ms, ca24_bytes = cross_attn_roofline_probe(eng0, B)
         gemm_ms, gemm_flops = gemm_roofline_probe(eng0, B)
         step_us, step_bytes = decode_step_probe(eng0, B)
+        # the same two probes at the row count of the timed region's generate calls (the launches the bench really makes)
+        R = balanced_microbatch(K * B, len(engines), MB)
+        if R != B:
+            eng0.load_pcm((clips * (-(-R // B)))[:R])
+            eng0.features(R)
+            eng0.encode(R)
+            ca_ms, ca_bytes = cross_attn_roofline_probe(eng0, R, iters=12)
+            stepR_us, stepR_bytes = decode_step_probe(eng0, R, steps=128)
+        else:
+            ca_ms, ca_bytes, stepR_us, stepR_bytes = ca24_ms, ca24_bytes, step_us, step_bytes
 
     t_dev, t_e2e = max_over_ranks(t_dev, t_e2e)
     audio_s = WINDOW_S * B * world * K
@@ -566,6 +576,7 @@ def run_own(args, rank, world, local_rank):
     line = None
     if rank == 0:
         ca_gbs = ca_bytes / (ca_ms * 1e-3) / 1e9
+        ca24_gbs = ca24_bytes / (ca24_ms * 1e-3) / 1e9
         gemm_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12
         enc_flops = B * (ENC_FLOPS_PER_WINDOW + dims.dec_layers * 4 * 1500 * 1280 ** 2)
         enc_tf = enc_flops / (enc_ms * 1e-3) / 1e12
@@ -591,7 +602,12 @@ def run_own(args, rank, world, local_rank):
                                                    "single kernel of a step by time)",
                          "achieved": ca_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ca_gbs / pk["hbm_gbs"],
                          "traffic": traffic.get("decode_attn_kernel"), "traffic_source": traffic.get("source"),
-                         "peak_source": pk["source"], "bytes_per_launch": ca_bytes, "ms_per_launch": ca_ms},
+                         "peak_source": pk["source"], "bytes_per_launch": ca_bytes, "ms_per_launch": ca_ms,
+                         "rows_per_launch": R,
+                         "note": "timed at the row count of the timed region's generate calls; the peak is the measured COPY "
+                                 "bandwidth (read + write), a read-only stream can exceed it slightly",
+                         "at_24_rows": {"achieved": ca24_gbs, "frac": ca24_gbs / pk["hbm_gbs"], "ms_per_launch": ca24_ms,
+                                        "bytes_per_launch": ca24_bytes}},
             "roofline_encoder_gemm": {"bound": "tensor", "kernel": "gemm_bf16_2cta_kernel (tcgen05; encoder qkv/out/fc1/fc2 "
                                       "shapes, fused bias/GELU/residual)", "achieved": gemm_tf,
                                       "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": gemm_tf / pk["bf16_tflops"],
@@ -610,7 +626,10 @@ def run_own(args, rank, world, local_rank):
                             # decode share of the timed region per 24-row step: (time - encoder passes at the alone rate)
                             # / (decode row-steps / 24)
                             "in_bench_us": max(0.0, t_dev * 1e6 - (enc_windows / B) * enc_ms * 1e3) / max(1.0, dec_row_steps / B),
-                            "in_bench_note": "per 24 decode rows; calls decode up to 96 rows per step"},
+                            "in_bench_note": "per 24 decode rows; calls decode up to 96 rows per step",
+                            "at_call_rows": {"rows": R, "us": stepR_us, "us_per_24_rows": stepR_us * B / R,
+                                             "bytes": stepR_bytes, "floor_us": stepR_bytes / pk["hbm_gbs"] / 1e3,
+                                             "frac": stepR_bytes / pk["hbm_gbs"] / 1e3 / stepR_us}},
             "output_check": {"chunks": len(result["chunks"]) if isinstance(result, dict) else None,
                              "rows": len(e2e_rows), "tokens_first_row": len(single[0]) if single else None,
                              "e2e_rows_equal_single_context": bool(rows_ok),

@@ -190,7 +190,12 @@ int tw_dec_self_attn(const void* q_bf16, void* out_bf16, const void* kv_pool_lay
  * k + enc_row[b]*kv_batch_stride + h*kv_head_stride + j*kv_row_stride (elements; V likewise).  The engine stores
  * K/V head-major ([head][row][pos][64], tw_gemm_bf16 out_mode 1) so every CTA streams one contiguous block.
  * `splits` CTAs per (row, head) with a last-CTA combine (part: fp32 [batch][heads][splits][66], counters:
- * zero-initialised uint32 [batch][heads]). */
+ * zero-initialised uint32 [batch][heads]).
+ * tw_set_cross_attn_stream(1) (or TWB200_CROSS_ATTN=stream in the environment) selects the persistent TMA-fed kernel
+ * of csrc/cross_attn.cu for dense head-major K/V (kv_row_stride 64, kv_batch_stride src_len*64, src_len >= 128):
+ * `splits` is then the capacity of `part`, the kernel picks the split count that balances the SMs.  Same results to
+ * fp32 rounding; faster at >= 72 rows, slower at <= 24, so it is off by default. */
+int tw_set_cross_attn_stream(int32_t enabled);
 int tw_dec_cross_attn(const void* q_bf16, void* out_bf16, const void* k_bf16, const void* v_bf16,
                       int64_t kv_row_stride, int64_t kv_batch_stride, int64_t kv_head_stride, const int32_t* enc_row,
                       int32_t src_len, int32_t batch, int32_t heads, int32_t splits, float* part, uint32_t* counters,

@@ -67,6 +67,7 @@ SIGNATURES = {
     "tw_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), c_void_p]),
     "tw_attention_enc": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int64, c_void_p]),
     "tw_set_pdl": (C.c_int, [c_int32]),
+    "tw_set_cross_attn_stream": (C.c_int, [c_int32]),
     "tw_dec_embed": (C.c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p,
                                c_void_p, c_void_p, c_void_p]),
     "tw_dec_linear": (C.c_int, [C.POINTER(SkinnyArgs), c_int32, c_void_p, c_int32, c_void_p]),

@@ -123,6 +123,8 @@ struct SkinnyParams {
     unsigned int* ln_counter;    // zero-initialised, self re-arming
     const float* bias;       // [N] or null
     int B, N, K;
+    int chunk_grid;          // 1: blockIdx.y selects the row chunk (NB * 8 rows) — the chunks of a wide launch run as
+                             // separate CTAs instead of a serial loop inside one CTA
     // LayerNorm folded into the consumer (round 2; removes the serial last-CTA LayerNorm tail of the producer):
     //   W (LN(x)) + b  =  rstd * (W' x - mean * c) + d,   W' = W diag(gamma), c = W' 1, d = W beta + b
     // Producer (EPI_RESID with ln_part_out): besides the fp32 update it stores bf16(x_new) into xb_out (the next
@@ -268,8 +270,10 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 2 : 1) skinny_gemm_
     // Row chunks of NB * 8 decode rows: with more than 32 rows in a launch (several micro-batches decoded together) the
     // CTA's weight slab is streamed from DRAM ONCE — it stays in registers when K fits one round (K = 1280), later
     // chunks of a longer K re-read it from L2 — so the weight bytes per decode step do not grow with the rows.
-    for (int rb = 0; rb < p.B; rb += NB * 8) {
-    if (rb > 0) __syncthreads();        // `red` of the previous chunk has been consumed
+    const int rb0 = p.chunk_grid ? blockIdx.y * NB * 8 : 0;
+    const int rb1 = p.chunk_grid ? min(p.B, rb0 + NB * 8) : p.B;
+    for (int rb = rb0; rb < rb1; rb += NB * 8) {
+    if (rb > rb0) __syncthreads();      // `red` of the previous chunk has been consumed
     const __nv_bfloat16* xr[NB];
 #pragma unroll
     for (int j = 0; j < NB; ++j) xr[j] = p.X + (size_t)min(rb + j * 8 + g, p.B - 1) * p.ldx + k_begin + tg * 8;
@@ -281,7 +285,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 2 : 1) skinny_gemm_
 #pragma unroll
         for (int u = 0; u < UN; ++u) {
             if (s0 + u < steps) {
-                if (s0 > 0 || (rb > 0 && steps > UN)) { alo[u] = ldg_stream(wa + (s0 + u) * FRAG_STEP); ahi[u] = ldg_stream(wb + (s0 + u) * FRAG_STEP); }
+                if (s0 > 0 || (rb > rb0 && steps > UN)) { alo[u] = ldg_stream(wa + (s0 + u) * FRAG_STEP); ahi[u] = ldg_stream(wb + (s0 + u) * FRAG_STEP); }
 #pragma unroll
                 for (int j = 0; j < NB; ++j) xb[u][j] = __ldg(reinterpret_cast<const uint4*>(xr[j] + (s0 + u) * 32));
             }
@@ -367,7 +371,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 2 : 1) skinny_gemm_
         __syncthreads();
         if (threadIdx.x == 0) {
             const unsigned int prev = atomicAdd(p.ln_counter, 1u);
-            s_last = (prev == gridDim.x - 1);
+            s_last = (prev == gridDim.x * gridDim.y - 1);
             if (s_last) *p.ln_counter = 0;  // re-arm for the next launch
         }
         __syncthreads();
@@ -409,7 +413,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 2 : 1) skinny_gemm_
         __syncthreads();
         if (threadIdx.x == 0) {
             const unsigned int prev = atomicAdd(p.ln_counter, 1u);
-            s_last = (prev == gridDim.x - 1);
+            s_last = (prev == gridDim.x * gridDim.y - 1);
             if (s_last) *p.ln_counter = 0;  // re-arm for the next launch
         }
         __syncthreads();
@@ -908,6 +912,13 @@ using namespace tw::dec;
 
 static int g_use_pdl = 0;  // off by default: inside CUDA graphs plain edges measured faster (212 vs 220 ms / 447 steps); eager stepping gains 10 % with it
 extern "C" int tw_set_pdl(int32_t enabled) { g_use_pdl = enabled ? 1 : 0; return 0; }
+// wide launches (> 32 decode rows): 0 (default) = serial loop over the 24-row chunks inside one CTA, weights in registers;
+// TWB200_SKINNY_CHUNK_GRID=1 = the chunks run as separate CTAs (grid.y).  Measured (profiles/r2x_bench_ab.jsonl): the
+// grid form shortens a 96-row step of ONE context (1.21 vs 1.31 ms) but loses 3 % in the five-context bench, where
+// CTA residency, not latency, is what the contexts compete for
+static int g_chunk_grid = [] { const char* e = getenv("TWB200_SKINNY_CHUNK_GRID"); return (e && !strcmp(e, "1")) ? 1 : 0; }();
+static int g_cross_stream = [] { const char* e = getenv("TWB200_CROSS_ATTN"); return (e && !strcmp(e, "stream")) ? 1 : 0; }();
+extern "C" int tw_set_cross_attn_stream(int32_t enabled) { g_cross_stream = enabled ? 1 : 0; return 0; }
 
 // launch with the programmatic-stream-serialization attribute (the kernel's own griddepcontrol.wait orders it
 // after its predecessor); captured into CUDA graphs as a programmatic dependency edge
@@ -932,11 +943,14 @@ template <int EPI, int WARPS, bool LNF = false>
 static int launch_nb(const SkinnyParams& p, int grid, cudaStream_t st) {
     // rows per chunk: up to 32 rows one chunk of ceil(B / 8) groups; beyond that chunks of 24 rows (NB = 3: no spills)
     const int nb = p.B <= 32 ? (p.B + 7) / 8 : 3;
+    SkinnyParams q = p;
+    q.chunk_grid = (g_chunk_grid && p.B > nb * 8) ? 1 : 0;
+    const dim3 g3(grid, q.chunk_grid ? (p.B + nb * 8 - 1) / (nb * 8) : 1);
     switch (nb) {
-        case 1: TW_CUDA_CHECK(launch_pdl(skinny_gemm_kernel<1, EPI, WARPS, LNF>, dim3(grid), dim3(WARPS * 32), 0, st, p)); break;
-        case 2: TW_CUDA_CHECK(launch_pdl(skinny_gemm_kernel<2, EPI, WARPS, LNF>, dim3(grid), dim3(WARPS * 32), 0, st, p)); break;
-        case 3: TW_CUDA_CHECK(launch_pdl(skinny_gemm_kernel<3, EPI, WARPS, LNF>, dim3(grid), dim3(WARPS * 32), 0, st, p)); break;
-        case 4: TW_CUDA_CHECK(launch_pdl(skinny_gemm_kernel<4, EPI, WARPS, LNF>, dim3(grid), dim3(WARPS * 32), 0, st, p)); break;
+        case 1: TW_CUDA_CHECK(launch_pdl(skinny_gemm_kernel<1, EPI, WARPS, LNF>, g3, dim3(WARPS * 32), 0, st, q)); break;
+        case 2: TW_CUDA_CHECK(launch_pdl(skinny_gemm_kernel<2, EPI, WARPS, LNF>, g3, dim3(WARPS * 32), 0, st, q)); break;
+        case 3: TW_CUDA_CHECK(launch_pdl(skinny_gemm_kernel<3, EPI, WARPS, LNF>, g3, dim3(WARPS * 32), 0, st, q)); break;
+        case 4: TW_CUDA_CHECK(launch_pdl(skinny_gemm_kernel<4, EPI, WARPS, LNF>, g3, dim3(WARPS * 32), 0, st, q)); break;
         default: set_error("skinny gemm: batch %d > %d", p.B, MAXB); return 2;
     }
     TW_CUDA_CHECK(cudaGetLastError());
@@ -1124,12 +1138,23 @@ extern "C" int tw_dec_cross_attn(const void* q_bf16, void* out_bf16, const void*
                                  int32_t splits, float* part, uint32_t* counters, void* stream) {
     TW_REQUIRE(q_bf16 && out_bf16 && k_bf16 && v_bf16, "tw_dec_cross_attn: null argument");
     if (tw::ensure_device(q_bf16)) return 1;
-    TW_REQUIRE(splits >= 1 && (src_len + splits - 1) / splits <= ATT_MAXKEYS,
-               "tw_dec_cross_attn: %d keys / %d splits exceeds %d per CTA", src_len, splits, ATT_MAXKEYS);
+    TW_REQUIRE(splits >= 1, "tw_dec_cross_attn: splits %d < 1", splits);
     TW_REQUIRE(splits == 1 || (part && counters), "tw_dec_cross_attn: split needs scratch");
     TW_REQUIRE(kv_row_stride % 8 == 0 && kv_batch_stride % 8 == 0 && kv_head_stride % 8 == 0,
                "tw_dec_cross_attn: K/V strides must be multiples of 8 elements");
     if (batch <= 0) return 0;
+    // opt-in (tw_set_cross_attn_stream / TWB200_CROSS_ATTN=stream): the persistent TMA-fed streaming kernel of
+    // cross_attn.cu; `splits` is then the capacity of `part` and the kernel balances the split count itself.  Measured
+    // on B200 (profiles/r2u_cross_probe.jsonl, r2v_bench_ab.jsonl): 4 % faster than the kernel below at >= 72 rows
+    // (6.6-6.7 TB/s), 12-20 % slower at <= 24 rows, no difference in the five-context bench — so it is not the default
+    if (g_cross_stream) {
+        const int rc = tw::cross_attn_stream_launch(q_bf16, out_bf16, k_bf16, v_bf16, kv_row_stride, kv_batch_stride,
+                                                    kv_head_stride, enc_row, src_len, batch, heads, splits, part, counters,
+                                                    (cudaStream_t)stream, g_use_pdl != 0);
+        if (rc >= 0) return rc;
+    }
+    TW_REQUIRE((src_len + splits - 1) / splits <= ATT_MAXKEYS,
+               "tw_dec_cross_attn: %d keys / %d splits exceeds %d per CTA", src_len, splits, ATT_MAXKEYS);
     AttnParams p{};
     p.q = (const __nv_bfloat16*)q_bf16; p.out = (__nv_bfloat16*)out_bf16; p.D = heads * 64; p.H = heads;
     p.is_cross = 1; p.ck = (const __nv_bfloat16*)k_bf16; p.cv = (const __nv_bfloat16*)v_bf16;

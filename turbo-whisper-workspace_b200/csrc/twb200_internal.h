@@ -23,4 +23,9 @@ int current_device();
 // per-device one-time setup (kernel attributes): an atomic bit per device, safe across the engine-context threads
 bool device_needs_setup(std::atomic<unsigned long long>& done_mask);
 void mark_device_done(std::atomic<unsigned long long>& done_mask);
+// cross_attn.cu: persistent TMA-fed decoder cross-attention; 0 = launched, -1 = layout not supported (caller falls back
+// to the scalar kernel of decode.cu), other = error (tw_last_error)
+int cross_attn_stream_launch(const void* q, void* out, const void* k, const void* v, long long row_stride,
+                             long long batch_stride, long long head_stride, const int* enc_row, int S, int B, int H,
+                             int split_cap, float* part, unsigned int* counters, cudaStream_t stream, bool pdl);
 }  // namespace tw
