@@ -601,13 +601,14 @@ def run_own(args, rank, world, local_rank):
             "roofline": {"bound": "hbm", "kernel": "decode_attn_kernel (cross-attention over the encoder K/V; largest "
                                                    "single kernel of a step by time)",
                          "achieved": ca_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ca_gbs / pk["hbm_gbs"],
-                         "traffic": traffic.get("decode_attn_kernel"), "traffic_source": traffic.get("source"),
+                         "traffic": traffic.get("decode_attn_kernel" if R == B else "decode_attn_kernel_%d_rows" % R),
+                         "traffic_source": traffic.get("source"),
                          "peak_source": pk["source"], "bytes_per_launch": ca_bytes, "ms_per_launch": ca_ms,
                          "rows_per_launch": R,
                          "note": "timed at the row count of the timed region's generate calls; the peak is the measured COPY "
                                  "bandwidth (read + write), a read-only stream can exceed it slightly",
                          "at_24_rows": {"achieved": ca24_gbs, "frac": ca24_gbs / pk["hbm_gbs"], "ms_per_launch": ca24_ms,
-                                        "bytes_per_launch": ca24_bytes}},
+                                        "bytes_per_launch": ca24_bytes, "traffic": traffic.get("decode_attn_kernel")}},
             "roofline_encoder_gemm": {"bound": "tensor", "kernel": "gemm_bf16_2cta_kernel (tcgen05; encoder qkv/out/fc1/fc2 "
                                       "shapes, fused bias/GELU/residual)", "achieved": gemm_tf,
                                       "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": gemm_tf / pk["bf16_tflops"],

@@ -10,7 +10,7 @@ mkdir -p gpurun_out
 step() { echo "== $1" >&2; }
 step "gpu test suite";        timeout 900 python -m pytest tests -m gpu -x -q --durations=10 -s > gpurun_out/${T}_gpu_suite.log 2>&1; tail -3 gpurun_out/${T}_gpu_suite.log
 step "smoke";                 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1 | tee gpurun_out/${T}_smoke.log
-step "bench N=1";             timeout 900 python bench.py --steps 8 --warmup 3 > gpurun_out/${T}_bench_1gpu.json 2> gpurun_out/${T}_bench.err; echo "rc=$?"; cut -c1-300 gpurun_out/${T}_bench_1gpu.json
+step "bench N=1";             timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/${T}_bench_1gpu.json 2> gpurun_out/${T}_bench.err; echo "rc=$?"; cut -c1-300 gpurun_out/${T}_bench_1gpu.json
 step "reference arm";         timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${T}_bench_reference.json 2> gpurun_out/${T}_bench_reference.err; cut -c1-260 gpurun_out/${T}_bench_reference.json
 step "kernel micro-benches";  timeout 150 python tools/bench_kernels.py 24 2>/dev/null | grep '^{' > gpurun_out/${T}_kernels.jsonl; cut -c1-200 gpurun_out/${T}_kernels.jsonl
 step "beams / word mode";     timeout 300 python tools/bench_beams.py 2>/dev/null | grep '^{' > gpurun_out/${T}_beams.jsonl; cat gpurun_out/${T}_beams.jsonl; timeout 200 python tools/bench_word_mode.py 4 2>/dev/null | grep '^{' > gpurun_out/${T}_word_mode_e2e.jsonl; cat gpurun_out/${T}_word_mode_e2e.jsonl

@@ -5,7 +5,8 @@
 Arguments are .ncu-rep reports (read through `ncu -i REP --page raw --csv`) or raw-page CSV exports of them.  Every
 launch is listed (kernel with template arguments, grid, dram__bytes_read.sum + dram__bytes_write.sum, duration under
 ncu), and two aggregates are named for bench.py's `roofline.traffic` (no literals in bench.py):
-  decode_attn_kernel      mean over the CROSS-attention launches (those that stream the encoder K/V: > 50 MB)
+  decode_attn_kernel      mean over the CROSS-attention launches (those that stream the encoder K/V: > 50 MB) at 24
+                          decode rows; `decode_attn_kernel_<rows>_rows` for captures at other row counts
   gemm_bf16_2cta_kernel   mean over the four GEMMs of one encoder layer (qkv, out+res, fc1+GELU, fc2+res = the launches
                           bench.py's GEMM probe times), i.e. the GEMM launches between the first and the third LayerNorm
 """
@@ -50,9 +51,14 @@ def main(paths):
                              "us_under_ncu": round(num(r[du]) * TIME.get(units[du], 1.0), 2) if du is not None else None,
                              "report": os.path.basename(path)})
     res = {}
-    cross = [l["dram_bytes"] for l in launches if l["kernel"].startswith("decode_attn_kernel") and l["dram_bytes"] > 50e6]
-    if cross:
-        res["decode_attn_kernel"] = sum(cross) / len(cross)
+    # cross-attention launches by decode rows (grid = splits x heads x rows = 80 CTAs per row at 20 heads x 4 splits):
+    # `decode_attn_kernel` stays the 24-row figure, wider captures (tools/ncu_target.py 96 ...) add `..._<rows>_rows`
+    by_rows = {}
+    for l in launches:
+        if l["kernel"].startswith("decode_attn_kernel") and l["dram_bytes"] > 50e6 and l["grid"]:
+            by_rows.setdefault(l["grid"] // 80, []).append(l["dram_bytes"])
+    for rows, vals in sorted(by_rows.items()):
+        res["decode_attn_kernel" if rows == 24 else "decode_attn_kernel_%d_rows" % rows] = sum(vals) / len(vals)
     ln_seen, layer = 0, []
     for l in launches:
         if l["kernel"].startswith("layernorm_kernel"):
@@ -63,7 +69,7 @@ def main(paths):
         res["gemm_bf16_2cta_kernel"] = sum(layer) / 4
         res["gemm_layer_shapes"] = dict(zip(("qkv", "out+res", "fc1+gelu", "fc2+res"), layer))
     res["source"] = ("ncu --set full --clock-control none, dram__bytes_read.sum + dram__bytes_write.sum per launch, "
-                     "large-v3-turbo B = 24 (tools/ncu_target.py): " + ", ".join(os.path.basename(p) for p in paths))
+                     "large-v3-turbo, tools/ncu_target.py at 24 decode rows (and at the row count a key names): " + ", ".join(os.path.basename(p) for p in paths))
     res["launches"] = launches
     print(json.dumps(res, indent=1))
 
