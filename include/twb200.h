@@ -196,6 +196,10 @@ int tw_dec_self_attn(const void* q_bf16, void* out_bf16, const void* kv_pool_lay
  * `splits` is then the capacity of `part`, the kernel picks the split count that balances the SMs.  Same results to
  * fp32 rounding; faster at >= 72 rows, slower at <= 24, so it is off by default. */
 int tw_set_cross_attn_stream(int32_t enabled);
+/* host only: the key-split plan the streaming kernel would use for `rows` decode rows on a device with `sms` SMs
+ * (splits per (row, head), 128-key chunks per split, CTAs launched); no device is touched. */
+int tw_cross_attn_plan(int32_t rows, int32_t heads, int32_t src_len, int32_t split_cap, int32_t sms, int32_t* splits,
+                       int32_t* chunks_per_split, int32_t* grid);
 int tw_dec_cross_attn(const void* q_bf16, void* out_bf16, const void* k_bf16, const void* v_bf16,
                       int64_t kv_row_stride, int64_t kv_batch_stride, int64_t kv_head_stride, const int32_t* enc_row,
                       int32_t src_len, int32_t batch, int32_t heads, int32_t splits, float* part, uint32_t* counters,

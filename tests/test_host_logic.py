@@ -108,6 +108,48 @@ def test_balanced_microbatches_keep_every_context_busy():
     assert [b - a for a, b in local.last_stats["microbatches"]] == [12, 11]
 
 
+def test_wide_generate_calls_are_balanced_like_the_bench_cuts_them():
+    """bench.py cuts the timed region's windows with the scheduler's own rule: at the driver's --steps 20 (480 windows per
+    GPU) and the bench defaults (96 rows x 5 contexts) every context gets ONE 96-window call; fewer steps shrink the
+    calls evenly instead of leaving contexts idle."""
+    assert S.balanced_microbatch(480, 5, 96) == 96
+    assert S.balanced_microbatch(480, 3, 96) == 80 and S.balanced_microbatch(480, 4, 96) == 60
+    assert S.balanced_microbatch(192, 5, 96) == 39 and S.balanced_microbatch(72, 5, 96) == 15
+    assert S.balanced_microbatch(180, 5, 96) == 36          # the 1 h file of config 3 on one GPU
+    clips = [np.full(100 + i, i / 1000.0, dtype=np.float32) for i in range(480)]
+    sch = S.WindowScheduler(None, None, None, devices=["g"], engine_factory=lambda d: FakeEngine(d, 96), contexts_per_device=5)
+    rows = sch.run(clips)
+    assert rows == [[(100 + i) % 1000, i] for i in range(480)]
+    assert [b - a for a, b in sch.last_stats["microbatches"]] == [96] * 5
+
+
+def test_cross_attention_split_plan_balances_the_sms():
+    """The streaming cross-attention kernel (csrc/cross_attn.cu) picks its key splits per launch: the fullest SM may hold
+    at most ~10 % more 128-key chunks than the average for the shapes the engine launches, splits never exceed the
+    scratch capacity, and one row on a big device still spreads over the SMs."""
+    import ctypes as C
+    from turbo_whisper_workspace_b200 import _lib
+    lib = _lib.load()
+
+    def plan(rows, heads=20, S_=1500, cap=12, sms=148):
+        sp, cps, grid = C.c_int32(), C.c_int32(), C.c_int32()
+        _lib.check(lib.tw_cross_attn_plan(rows, heads, S_, cap, sms, C.byref(sp), C.byref(cps), C.byref(grid)), "plan")
+        return sp.value, cps.value, grid.value
+    nch = 12                                              # ceil(1500 / 128)
+    for rows in (12, 16, 24, 40, 72, 96):
+        sp, cps, grid = plan(rows)
+        assert 1 <= sp <= 12 and sp * cps >= nch and (sp - 1) * cps < nch and grid <= 2 * 148
+        items = rows * 20 * sp
+        fullest = -(-items // 148) * cps
+        assert fullest <= 1.12 * rows * 20 * nch / 148, (rows, sp, cps)
+    assert plan(96)[0] == 1 and plan(24)[0] in (3, 4)     # wide launches need no split; 24 rows: 9.7 x 4 or 12.97 x 3 chunks per SM
+    assert plan(24, cap=1) == (1, 12, 296)                # no scratch: one item per (row, head)
+    assert plan(24, cap=3)[0] <= 3
+    sp, cps, grid = plan(1)
+    assert (sp, cps, grid) == (6, 2, 120)                 # a single row: 20 heads x 6 splits, one 2-chunk item per SM
+    assert plan(2, heads=6, S_=130, cap=12) == (2, 1, 24)
+
+
 def test_word_mode_microbatches_follow_hf_batches():
     """return_timestamps="word": micro-batches are the HF pipeline's batches of `batch_size` consecutive windows
     (capped at the engine's rows) whatever the number of devices / contexts, and rows come back as (ids, times)."""

@@ -68,6 +68,7 @@ SIGNATURES = {
     "tw_attention_enc": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int64, c_void_p]),
     "tw_set_pdl": (C.c_int, [c_int32]),
     "tw_set_cross_attn_stream": (C.c_int, [c_int32]),
+    "tw_cross_attn_plan": (C.c_int, [c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "tw_dec_embed": (C.c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p,
                                c_void_p, c_void_p, c_void_p]),
     "tw_dec_linear": (C.c_int, [C.POINTER(SkinnyArgs), c_int32, c_void_p, c_int32, c_void_p]),

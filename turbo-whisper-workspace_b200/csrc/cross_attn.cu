@@ -376,3 +376,17 @@ int cross_attn_stream_launch(const void* q, void* out, const void* k, const void
 }
 
 }  // namespace tw
+
+// host-only view of the split choice (tests/test_host_logic.py checks the balance it promises)
+extern "C" int tw_cross_attn_plan(int32_t rows, int32_t heads, int32_t src_len, int32_t split_cap, int32_t sms,
+                                  int32_t* splits, int32_t* chunks_per_split, int32_t* grid) {
+    using namespace tw::xattn;
+    TW_REQUIRE(rows > 0 && heads > 0 && src_len >= KCH && split_cap >= 1 && sms > 0 && splits && chunks_per_split && grid,
+               "tw_cross_attn_plan: bad argument");
+    int sp = 1, cps = 1;
+    choose_splits(rows * heads, (src_len + KCH - 1) / KCH, split_cap, sms, sp, cps);
+    *splits = sp;
+    *chunks_per_split = cps;
+    *grid = std::min(rows * heads * sp, CTAS_PER_SM * sms);
+    return 0;
+}
