@@ -8,7 +8,8 @@ dev = torch.device("cuda:0")
 H, S, D, L = 20, 1500, 1280, 4
 p = lambda t: C.c_void_p(t.data_ptr())
 cap = int(os.environ.get("TWB200_CROSS_SPLITS", 12))
-for B in (96, 72, 48, 24, 16, 12, 5, 1):
+ROWS = [int(os.environ['PROBE_ROWS'])] if os.environ.get('PROBE_ROWS') else [96, 72, 48, 24, 16, 12, 5, 1]
+for B in ROWS:
     ckv = torch.randn(L * 2 * H, B, S, 64, device=dev).to(torch.bfloat16)
     q = torch.randn(B, D, device=dev).to(torch.bfloat16)
     out = torch.empty(B, D, dtype=torch.bfloat16, device=dev)
