@@ -916,7 +916,9 @@ extern "C" int tw_set_pdl(int32_t enabled) { g_use_pdl = enabled ? 1 : 0; return
 // TWB200_SKINNY_CHUNK_GRID=1 = the chunks run as separate CTAs (grid.y).  Measured (profiles/r2x_bench_ab.jsonl): the
 // grid form shortens a 96-row step of ONE context (1.21 vs 1.31 ms) but loses 3 % in the five-context bench, where
 // CTA residency, not latency, is what the contexts compete for
-static int g_chunk_grid = [] { const char* e = getenv("TWB200_SKINNY_CHUNK_GRID"); return (e && !strcmp(e, "1")) ? 1 : 0; }();
+// TWB200_SKINNY_CHUNK_GRID=2 = grid form only for the launches that leave SMs idle (N / 16 <= 96 CTAs: the N = 1280 projections):
+// -8 % per 96-row step alone, no difference in the bench (profiles/r2x3_bench_ab_selective_chunk_grid.jsonl)
+static int g_chunk_grid = [] { const char* e = getenv("TWB200_SKINNY_CHUNK_GRID"); return e ? atoi(e) : 0; }();
 static int g_cross_stream = [] { const char* e = getenv("TWB200_CROSS_ATTN"); return (e && !strcmp(e, "stream")) ? 1 : 0; }();
 extern "C" int tw_set_cross_attn_stream(int32_t enabled) { g_cross_stream = enabled ? 1 : 0; return 0; }
 
@@ -944,7 +946,7 @@ static int launch_nb(const SkinnyParams& p, int grid, cudaStream_t st) {
     // rows per chunk: up to 32 rows one chunk of ceil(B / 8) groups; beyond that chunks of 24 rows (NB = 3: no spills)
     const int nb = p.B <= 32 ? (p.B + 7) / 8 : 3;
     SkinnyParams q = p;
-    q.chunk_grid = (g_chunk_grid && p.B > nb * 8) ? 1 : 0;
+    q.chunk_grid = ((g_chunk_grid == 1 || (g_chunk_grid == 2 && grid <= 96)) && p.B > nb * 8) ? 1 : 0;
     const dim3 g3(grid, q.chunk_grid ? (p.B + nb * 8 - 1) / (nb * 8) : 1);
     switch (nb) {
         case 1: TW_CUDA_CHECK(launch_pdl(skinny_gemm_kernel<1, EPI, WARPS, LNF>, g3, dim3(WARPS * 32), 0, st, q)); break;
