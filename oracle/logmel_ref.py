@@ -85,6 +85,29 @@ def log_mel(pcm: np.ndarray, dtype=np.float32) -> np.ndarray:
     return ((logspec + 4.0) / 4.0).astype(np.float32)
 
 
+def log_mel_long(pcm: np.ndarray, dtype=np.float32) -> np.ndarray:
+    """[128, n // 160] features of a clip LONGER than 30 s, as the ASR pipeline builds them for un-chunked long-form
+    input ($TF/pipelines/automatic_speech_recognition.py:446-454: truncation=False, padding="longest"): the whole
+    waveform goes through the same STFT (reflect padding only at the two ends of the clip), the last frame is
+    dropped, and the `max - 8` clamp uses the maximum of the WHOLE clip
+    ($TF/models/whisper/feature_extraction_whisper.py:135-164)."""
+    x = np.asarray(pcm, dtype=np.float32).reshape(-1).astype(dtype)
+    xp = np.pad(x, (N_FFT // 2, N_FFT // 2), mode="reflect")
+    n_frames = 1 + (len(xp) - N_FFT) // HOP
+    win = hann_periodic().astype(dtype)[None, :]
+    fb = mel_filter_bank().astype(dtype)
+    out = np.empty((N_MELS, n_frames - 1), dtype=dtype)
+    for f0 in range(0, n_frames - 1, 4096):      # blocks of frames: a 1 h clip would not fit as one index matrix
+        f1 = min(n_frames - 1, f0 + 4096)
+        idx = np.arange(N_FFT)[None, :] + HOP * np.arange(f0, f1)[:, None]
+        frames = xp[idx] * win
+        spec = np.fft.rfft(frames.astype(np.float64 if dtype == np.float64 else np.float32), axis=1)
+        power = (np.abs(spec) ** 2).astype(dtype)
+        out[:, f0:f1] = np.log10(np.maximum(power @ fb, 1e-10)).T
+    out = np.maximum(out, out.max() - 8.0)
+    return ((out + 4.0) / 4.0).astype(np.float32)
+
+
 def attention_mask(n_valid: int) -> np.ndarray:
     """Frame mask of the extractor: sample mask [::160] ($TF/...feature_extraction_whisper.py:331-339)."""
     m = np.zeros(N_SAMPLES, dtype=np.int32)

@@ -483,6 +483,9 @@ class WhisperRef:
                  token_ts: Optional[dict] = None) -> List[List[int]]:
         """WhisperGenerationMixin.generate for a batch of <=30 s windows (short-form), greedy, timestamps on.
         feats [B, n_mels, 3000] fp32.  Returns the generated ids per row (segments concatenated, no padding).
+        feats wider than 3000 frames = HF's long-form mode ($TF/models/whisper/generation_whisper.py:654-658, the same
+        seek loop over `total_input_frames`; the language is detected on the first 3000 frames :1649; timestamps are
+        mandatory :1388-1394) — one row at a time, as the ASR pipeline calls it for an un-chunked long input.
 
         ``alignment_heads`` + ``num_frames`` (attention_mask.sum(-1) per row) + ``token_ts`` = the
         return_token_timestamps=True path (greedy only): token_ts["segments"][b] receives the per-token times of the
@@ -493,7 +496,10 @@ class WhisperRef:
         TB = gc.no_timestamps_token_id + 1
         B = feats.shape[0]
         feats = feats.to(torch.float32)
-        enc0 = self.encode(feats)
+        if feats.shape[-1] > 3000 and not return_timestamps:
+            raise ValueError("You have passed more than 3000 mel input features (> 30 seconds) which automatically enables "
+                             "long-form generation which requires the model to predict timestamp tokens.")
+        enc0 = self.encode(feats[..., :3000])
         langs = self.detect_language(enc0, gc)
         tail = [] if return_timestamps else [gc.no_timestamps_token_id]   # <|notimestamps|> joins the prompt
         init = torch.tensor([[gc.decoder_start_token_id, langs[b], gc.task_to_id[task]] + tail for b in range(B)],

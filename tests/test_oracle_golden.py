@@ -99,6 +99,32 @@ def test_generate_oracle_vs_hf_golden(model_gold, variant):
 
 
 @pytest.mark.parametrize("variant", ["decisive", "varied"])
+def test_longform_generate_oracle_vs_hf_golden(variant):
+    """Un-chunked long-form input (75.3 s = 7530 frames in ONE generate call): the oracle's whole-clip log-mel equals the
+    HF extractor's (truncation=False) and its seek loop over all frames is token-exact with transformers
+    (tests/golden/make_golden_longform.py)."""
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "longform_tiny.json")))
+    pcm = np.concatenate([helpers.synth_clip(0), helpers.synth_clip(1, kind="mod"),
+                          helpers.synth_clip(2, seconds=15.3, kind="mod")])
+    feats = L.log_mel_long(pcm)
+    assert feats.shape == (128, pcm.shape[0] // 160)
+    if variant == "varied":
+        from transformers import WhisperFeatureExtractor
+        hf = WhisperFeatureExtractor(feature_size=128)(pcm, sampling_rate=16000, truncation=False, padding="longest",
+                                                      return_tensors="np")["input_features"][0]
+        assert np.abs(hf - feats).max() <= 1e-4
+        # the first 2998 frames do not see the clip-global clamp or the far end: same as the 30 s extractor's
+        # unless the global maximum lifts the floor
+        short = L.log_mel(pcm[:480000])
+        assert np.abs(np.maximum(short[:, :2998], feats.min()) - feats[:, :2998]).max() <= 1e-4
+    dims = R.WhisperDims(**helpers.TINY)
+    ref = R.WhisperRef(dims, helpers.variant_state_dict(dims, variant))
+    assert ref.generate(torch.from_numpy(feats)[None])[0] == gold[variant]["tokens"]
+    with pytest.raises(ValueError):
+        ref.generate(torch.from_numpy(feats)[None], return_timestamps=False)
+
+
+@pytest.mark.parametrize("variant", ["decisive", "varied"])
 def test_generate_without_timestamps_oracle_vs_hf_golden(variant):
     """generate(return_timestamps=False): <|notimestamps|> in the prompt, suppress lists only — token-exact with
     transformers, including the extra seek iterations the (unmasked) timestamp ids of these random models cause."""

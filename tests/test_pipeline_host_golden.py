@@ -43,6 +43,10 @@ class OracleScheduler:
             rows += [(ids[b], ts["segments"][b]) for b in range(len(sub))]
         return rows
 
+    def run_long(self, audio, task="transcribe", language=None, num_beams=1):
+        feats = torch.from_numpy(L.log_mel_long(audio))[None]
+        return self.ref.generate(feats, task=task, num_beams=num_beams)[0]
+
 
 @pytest.fixture(scope="module")
 def wav(tmp_path_factory):
@@ -136,3 +140,31 @@ def test_host_pipeline_edge_inputs_match_hf_golden():
             assert sorted(r.keys()) == g["keys"] and r["text"] == g["text"], (name, rt)
             if rt:
                 assert _norm(r)["chunks"] == g["chunks"], (name, rt)
+
+
+
+@pytest.mark.parametrize("variant", ["decisive", "varied", "varied_beams3"])
+def test_host_pipeline_unchunked_longform_matches_hf_golden(variant):
+    """A 75.3 s clip WITHOUT chunk_length_s: HF extracts features of the whole clip and generate's seek loop walks all 7530
+    frames (tests/golden/make_golden_longform.py).  The host path (windowing decision, the one-row model output without
+    stride, native _decode_asr over timestamps that restart in every 30 s segment) must give HF's dict; without
+    timestamps HF's ValueError; the oracle's long-form generate is pinned token-exact in tests/test_oracle_golden.py."""
+    gold = json.load(open(os.path.join(GOLD, "longform_tiny.json")))
+    pcm = np.concatenate([helpers.synth_clip(0), helpers.synth_clip(1, kind="mod"),
+                          helpers.synth_clip(2, seconds=15.3, kind="mod")])
+    assert pcm.shape[0] == gold["samples"]
+    model = variant.split("_")[0]
+    pipe = B200WhisperPipeline(None, WhisperDims(**helpers.TINY), helpers.build_tokenizer(), scheduler=OracleScheduler(model))
+    kw = {"task": "transcribe"}
+    if variant.endswith("beams3"):
+        kw["num_beams"] = 3
+    r = pipe(pcm, return_timestamps=True, generate_kwargs=kw)
+    assert _norm(r) == {"text": gold[variant]["text"], "chunks": gold[variant]["chunks"]}
+    if variant == "varied":
+        with pytest.raises(ValueError, match="long-form generation which requires the model to predict timestamp tokens"):
+            pipe(pcm, generate_kwargs={"task": "transcribe"})
+        with pytest.raises(NotImplementedError):
+            pipe(pcm, return_timestamps="word")
+        # a list call mixing a long clip and a short one keeps the order of the inputs
+        both = pipe([pcm[:16000 * 20], pcm], return_timestamps=True, generate_kwargs=kw)
+        assert _norm(both[1]) == _norm(r) and both[0]["chunks"]

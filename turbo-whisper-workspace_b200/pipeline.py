@@ -325,14 +325,28 @@ class B200WhisperPipeline:
             # cross-attention; micro-batches follow HF's batches of `batch_size` consecutive windows (capped by the
             # engine's max_batch) because a row's DTW spans the decode steps of its batch's longest row
             run_kw.update(token_timestamps=True, group=bs)
+        if any("longform" in p for p in prepared):
+            if not return_timestamps:
+                raise ValueError(
+                    "You have passed more than 3000 mel input features (> 30 seconds) which automatically enables "
+                    "long-form generation which requires the model to predict timestamp tokens. Please either pass "
+                    "`return_timestamps=True` or make sure to pass no more than 3000 mel input features.")
+            if return_timestamps == "word":
+                raise NotImplementedError("word timestamps for un-chunked long-form input are not implemented; pass "
+                                          "chunk_length_s as the reference does")
         token_rows = self.scheduler.run(clips, task=task, language=language, **run_kw) if clips else []
         if return_timestamps == "word":
             token_times = [np.asarray(t, dtype=np.float32) for _, t in token_rows]
             token_rows = [r for r, _ in token_rows]
+        long_rows = {i: self.scheduler.run_long(p["longform"], task=task, language=language, num_beams=num_beams)
+                     for i, p in enumerate(prepared) if "longform" in p}
         t2 = time.perf_counter()
         self.last_token_rows = token_rows      # the engines' rows of this call, window order (bench.py's output check)
         results, w0 = [], 0
-        for p in prepared:
+        for i, p in enumerate(prepared):
+            if i in long_rows:
+                results.append(self._finish(p, [long_rows[i]], None, bs, return_timestamps, return_language))
+                continue
             n = len(p["windows"])
             results.append(self._finish(p, token_rows[w0:w0 + n], None if token_times is None else token_times[w0:w0 + n],
                                         bs, return_timestamps, return_language))
@@ -365,12 +379,15 @@ class B200WhisperPipeline:
                 # `transcribe` turns it into its {"error": ...} dict exactly as it does today
                 raise StopIteration
         else:
-            if audio.shape[0] > N_SAMPLES:
-                raise NotImplementedError(
-                    "un-chunked long-form transcription (> 30 s without chunk_length_s) is not implemented; "
-                    "pass chunk_length_s as the reference does")
             windows = [(0, audio.shape[0], (audio.shape[0], 0, 0), True)]
             with_stride = False
+            if audio.shape[0] > N_SAMPLES:
+                # un-chunked long-form input ($TF/pipelines/automatic_speech_recognition.py:446-454): features of the
+                # WHOLE clip (truncation=False) and ONE generate call whose seek loop walks all of its frames
+                # ($TF/models/whisper/generation_whisper.py:654-658).  Not the reference's path (it always passes
+                # chunk_length_s); sequential by construction, so it runs on one engine context
+                return {"windows": windows, "with_stride": False, "clips": [], "extra": extra,
+                        "n_samples": int(audio.shape[0]), "longform": audio}
         # the feature extractor truncates every window to its first 30 s (truncation=True, max_length=480000)
         clips = [audio[s:e][:N_SAMPLES] for (s, e, _, _) in windows]
         return {"windows": windows, "with_stride": with_stride, "clips": clips, "extra": extra,

@@ -197,6 +197,12 @@ class WindowScheduler:
                            "microbatches": list(queue.handed), "seconds": time.perf_counter() - t0}
         return [r for r in results]
 
+    def run_long(self, audio: np.ndarray, task: str = "transcribe", language: Optional[str] = None,
+                 num_beams: int = 1) -> List[int]:
+        """Token row of ONE un-chunked long-form clip (> 30 s): HF's long-form generate is a sequential seek loop over the
+        clip's frames, so it runs on one engine context."""
+        return self.engines[0][0].generate_long_from_pcm(audio, task=task, language=language, num_beams=num_beams)
+
     def close(self):
         self.engines = []
 
@@ -255,6 +261,13 @@ class DistributedWindowScheduler:
         self.last_stats = {"workers": self.world_size, "rank": self.rank, "local_range": (s, e),
                            "seconds": time.perf_counter() - t0}
         return rows
+
+    def run_long(self, audio: np.ndarray, task: str = "transcribe", language: Optional[str] = None,
+                 num_beams: int = 1) -> List[int]:
+        """Un-chunked long-form input does not shard (one sequential seek loop): every rank computes the same row."""
+        if hasattr(self.engine, "run_long"):
+            return self.engine.run_long(audio, task=task, language=language, num_beams=num_beams)
+        return self.engine.generate_long_from_pcm(audio, task=task, language=language, num_beams=num_beams)
 
     def close(self):
         if hasattr(self.engine, "close"):
