@@ -54,6 +54,16 @@ int tw_logmel_init(void* tables_dev, const float* mel_filters_host_201x128);
 int tw_logmel(const void* tables_dev, const float* pcm, int64_t pcm_stride, const int32_t* n_valid,
               int32_t batch, void* scratch, float* out_f32, void* out_bf16_t,
               int64_t out_t_bstride, int32_t out_t_row_off, void* stream);
+/* Whole-clip features for un-chunked long-form input (WhisperFeatureExtractor with truncation=False over the full
+ * waveform, $TF/models/whisper/feature_extraction_whisper.py:135-164; the ASR pipeline's path for > 30 s without
+ * chunk_length_s, $TF/pipelines/automatic_speech_recognition.py:446-454).  pcm_long: device fp32, covered by n_windows
+ * overlapping 30 s windows that start hop_samples apart (window b = pcm_long[b*hop_samples .. +480000), readable and
+ * zero beyond the clip; the caller appends the 200 reflected samples of the clip's end).  Window b writes its frames
+ * [frame_lo[b], frame_hi[b]) to rows out_t_row_off + out_row0[b].. of out_bf16_t (time-major [rows,128]); the max - 8
+ * clamp uses the maximum over all written frames (max_scratch: one device uint32).  The arrays are device int32. */
+int tw_logmel_long(const void* tables_dev, const float* pcm_long, int64_t hop_samples, int32_t n_windows,
+                   const int32_t* frame_lo, const int32_t* frame_hi, const int32_t* out_row0, uint32_t* max_scratch,
+                   void* out_bf16_t, int64_t total_frames, int32_t out_t_row_off, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K4  LayerNorm over the last dimension, fp32 in -> bf16 out (eps as nn.LayerNorm, 1e-5).

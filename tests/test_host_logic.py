@@ -150,6 +150,44 @@ def test_cross_attention_split_plan_balances_the_sms():
     assert plan(2, heads=6, S_=130, cap=12) == (2, 1, 24)
 
 
+def test_longform_window_plan_tiles_the_clip_exactly():
+    """ops.longform_plan / longform_buffer (un-chunked long-form features, tw_logmel_long): every clip frame is written by
+    exactly one window, and a 30 s STFT of that window (reflect padding at the WINDOW's edges, as the kernel does)
+    gives bit-identical power spectra to the STFT of the whole clip for the frames the window owns — including the
+    clip's own reflect padding at both ends.  numpy restatement of the kernel's framing; no GPU."""
+    from turbo_whisper_workspace_b200 import ops
+    from oracle import logmel_ref as L
+    win = L.hann_periodic().astype(np.float32)[None, :]
+
+    def power(x, frames):       # frames of a center=True, reflect-padded STFT of x
+        xp = np.pad(x, (200, 200), mode="reflect")
+        idx = np.arange(400)[None, :] + 160 * np.asarray(frames)[:, None]
+        return np.abs(np.fft.rfft((xp[idx] * win).astype(np.float32), axis=1)) ** 2
+
+    rng = np.random.default_rng(0)
+    for n in (480001, 480000 + 160 * 2 + 7, 2997 * 160 + 480000, 1204800, 16000 * 200 + 159):
+        plan = ops.longform_plan(n)
+        T = n // 160
+        assert plan["frames"] == T and plan["hop_samples"] == 2997 * 160
+        owner = np.full(T, -1)
+        for b, (lo, hi, r0) in enumerate(zip(plan["lo"], plan["hi"], plan["row0"])):
+            assert 0 <= lo < hi <= 2999 and r0 == 2997 * b + lo
+            assert (owner[r0:r0 + hi - lo] == -1).all()
+            owner[r0:r0 + hi - lo] = b
+        assert (owner >= 0).all()
+        audio = rng.standard_normal(n).astype(np.float32)
+        buf = ops.longform_buffer(audio, plan)
+        assert buf.shape[0] >= (len(plan["lo"]) - 1) * plan["hop_samples"] + 480000
+        # a few windows are enough: the first, the second, the last two
+        for b in sorted(set([0, 1, len(plan["lo"]) - 2, len(plan["lo"]) - 1]) & set(range(len(plan["lo"])))):
+            lo, hi, r0 = plan["lo"][b], plan["hi"][b], plan["row0"][b]
+            pick = sorted(set([lo, lo + 1, (lo + hi) // 2, hi - 2, hi - 1]) & set(range(lo, hi)))
+            w = buf[b * plan["hop_samples"]: b * plan["hop_samples"] + 480000]
+            got = power(w, pick)
+            want = power(audio, [r0 + (j - lo) for j in pick])
+            assert np.array_equal(got, want), (n, b)
+
+
 def test_word_mode_microbatches_follow_hf_batches():
     """return_timestamps="word": micro-batches are the HF pipeline's batches of `batch_size` consecutive windows
     (capped at the engine's rows) whatever the number of devices / contexts, and rows come back as (ids, times)."""

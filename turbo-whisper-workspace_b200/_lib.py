@@ -63,6 +63,8 @@ SIGNATURES = {
     "tw_logmel_init": (C.c_int, [c_void_p, c_void_p]),
     "tw_logmel": (C.c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_void_p, c_void_p, c_void_p,
                             c_int64, c_int32, c_void_p]),
+    "tw_logmel_long": (C.c_int, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_int64, c_int32, c_void_p]),
     "tw_layernorm": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_float, c_void_p]),
     "tw_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), c_void_p]),
     "tw_attention_enc": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int64, c_void_p]),

@@ -24,6 +24,7 @@
 #include "common.cuh"
 #include "twb200_internal.h"
 #include <math.h>
+#include <algorithm>
 
 namespace tw {
 namespace logmel {
@@ -345,6 +346,114 @@ __global__ void __launch_bounds__(NT) logmel_kernel(const float* __restrict__ pc
     __syncthreads();
     if (tid == 0) { sc.clip_max = 0u; sc.arrived = 0u; }      // re-arm for the next call on this stream
 }
+
+// ---- whole-clip features for un-chunked long-form input (WhisperFeatureExtractor with truncation=False,
+// $TF/models/whisper/feature_extraction_whisper.py:135-164 over the full waveform; the ASR pipeline's path for inputs
+// longer than 30 s without chunk_length_s, $TF/pipelines/automatic_speech_recognition.py:446-454).  The clip is covered by
+// OVERLAPPING 30 s windows that start `hop_samples` apart: a frame only depends on 400 samples, so every frame of a
+// window that does not touch the window's own reflect padding equals the clip's frame; window b contributes its frames
+// [frame_lo[b], frame_hi[b]) to rows out_row0[b].. of the clip's time-major output.  The clamp uses the maximum of the
+// WHOLE clip: this kernel stores un-floored values and raises ONE maximum, logmel_floor_kernel applies the floor.
+__global__ void __launch_bounds__(NT) logmel_long_kernel(const float* __restrict__ pcm, long long hop_samples,
+                                                        const Tables* __restrict__ tab, const int* __restrict__ frame_lo,
+                                                        const int* __restrict__ frame_hi, const int* __restrict__ out_row0,
+                                                        unsigned int* __restrict__ long_max,
+                                                        __nv_bfloat16* __restrict__ out_t, int row_off) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem& s = *reinterpret_cast<Smem*>(smem_raw);
+    const int b = blockIdx.y, tile = blockIdx.x;
+    const int f0 = tile * FR;
+    const int lo = frame_lo[b], hi = frame_hi[b];
+    if (f0 + FR <= lo || f0 >= hi) return;       // block-uniform: no frame of this tile belongs to the window's share
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    for (int i = tid; i < NC; i += NT) s.tw200[i] = tab->tw200[i];
+    for (int i = tid; i < N_BINS; i += NT) s.tw400[i] = tab->tw400[i];
+    for (int i = tid; i < N_FFT; i += NT) s.window[i] = tab->window[i];
+    for (int i = tid; i < MEL_MAX_TAPS * 32; i += NT) {
+        const int tap = i >> 5, l = i & 31;
+        s.mel_w4[tap][l] = make_float4(tab->mel_w[4 * l][tap], tab->mel_w[4 * l + 1][tap], tab->mel_w[4 * l + 2][tap],
+                                       tab->mel_w[4 * l + 3][tap]);
+    }
+    if (tid < 32) s.mel_start4[tid] = make_int4(tab->mel_start[4 * tid], tab->mel_start[4 * tid + 1], tab->mel_start[4 * tid + 2],
+                                                tab->mel_start[4 * tid + 3]);
+    phase_load(tid, NT, pcm + (size_t)b * hop_samples, N_SAMPLES, f0, s.x);
+    __syncthreads();
+
+    float2* wa = s.a[warp];
+    float2* wb = s.b[warp];
+    float* pw = reinterpret_cast<float*>(wb);
+    float vmax = -INFINITY;
+    __nv_bfloat16* ot = out_t + (size_t)(row_off + out_row0[b] - lo) * N_MEL;    // row of window frame 0 (may lie before row 0)
+#pragma unroll
+    for (int i = 0; i < FPW; ++i) {
+        const int fl = warp * FPW + i;
+        const int f = f0 + fl;
+        if (f >= lo && f < hi) {                  // warp-uniform
+            phase_fft_r8(lane, 32, s.x + fl * HOP, s.window, wa);
+            __syncwarp();
+            phase_fft_r5(lane, 32, 8, s.tw200, wa, wb);
+            __syncwarp();
+            phase_fft_r5(lane, 32, 40, s.tw200, wb, wa);
+            __syncwarp();
+            phase_power(lane, 32, s.tw400, wa, pw);
+            __syncwarp();
+            const int4 st4 = s.mel_start4[lane];
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int tp = 0; tp < MEL_MAX_TAPS; ++tp) {
+                const float4 w = s.mel_w4[tp][lane];
+                acc[0] = fmaf(w.x, pw[min(st4.x + tp, N_BINS - 1)], acc[0]);
+                acc[1] = fmaf(w.y, pw[min(st4.y + tp, N_BINS - 1)], acc[1]);
+                acc[2] = fmaf(w.z, pw[min(st4.z + tp, N_BINS - 1)], acc[2]);
+                acc[3] = fmaf(w.w, pw[min(st4.w + tp, N_BINS - 1)], acc[3]);
+            }
+            float y[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float l = __log2f(fmaxf(acc[q], 1e-10f)) * 0.30102999566398120f;
+                vmax = fmaxf(vmax, l);
+                y[q] = scaled(l);
+            }
+            uint2 pk;
+            pk.x = pack_bf16x2(y[0], y[1]);
+            pk.y = pack_bf16x2(y[2], y[3]);
+            reinterpret_cast<uint2*>(ot + (size_t)f * N_MEL)[lane] = pk;
+            __syncwarp();
+        }
+    }
+    vmax = warp_max(vmax);
+    if (lane == 0) s.red[0][warp] = vmax;
+    __syncthreads();
+    if (tid == 0) {
+        float mx = s.red[0][0];
+#pragma unroll
+        for (int i = 1; i < NWARP; ++i) mx = fmaxf(mx, s.red[0][i]);
+        if (mx > -INFINITY) atomicMax(long_max, float_to_umono(mx));
+    }
+}
+
+// raise every value below the clip's floor (max - 8 in log10 units, compared after the bf16 rounding of the output, like
+// the floor pass of logmel_kernel)
+__global__ void __launch_bounds__(256) logmel_floor_kernel(uint4* __restrict__ mel, long long n_vec,
+                                                          const unsigned int* __restrict__ long_max) {
+    const float floor_y = scaled_floor(umono_to_float(*long_max));
+    const uint32_t floor_bf = pack_bf16x2(floor_y, floor_y);
+    const float floor_bf_f = __uint_as_float(floor_bf << 16);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (long long)gridDim.x * blockDim.x) {
+        uint4 v = mel[i];
+        uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+        bool changed = false;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float lo = __uint_as_float(w[k] << 16), hi = __uint_as_float(w[k] & 0xffff0000u);
+            if (lo < floor_bf_f) { lo = floor_bf_f; changed = true; }
+            if (hi < floor_bf_f) { hi = floor_bf_f; changed = true; }
+            w[k] = (__float_as_uint(lo) >> 16) | (__float_as_uint(hi) & 0xffff0000u);
+        }
+        if (changed) mel[i] = v;
+    }
+}
 #endif  // TW_HOST_TEST
 
 // Host: build the constant tables from the dense [201,128] fp32 filterbank (HF mel_filters).
@@ -422,6 +531,36 @@ extern "C" int tw_logmel(const void* tables_dev, const float* pcm, int64_t pcm_s
     logmel_kernel<<<dim3(N_TILES, batch), NT, sizeof(Smem), (cudaStream_t)stream>>>(
         pcm, (long long)pcm_stride, n_valid, (const Tables*)tables_dev, (Scratch*)scratch, out_f32,
         (__nv_bfloat16*)out_bf16_t, (long long)out_t_bstride, out_t_row_off);
+    TW_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tw_logmel_long(const void* tables_dev, const float* pcm_long, int64_t hop_samples, int32_t n_windows,
+                              const int32_t* frame_lo, const int32_t* frame_hi, const int32_t* out_row0,
+                              uint32_t* max_scratch, void* out_bf16_t, int64_t total_frames, int32_t out_t_row_off,
+                              void* stream) {
+    TW_REQUIRE(tables_dev && pcm_long && frame_lo && frame_hi && out_row0 && max_scratch && out_bf16_t,
+               "tw_logmel_long: null argument");
+    if (tw::ensure_device(pcm_long)) return 1;
+    TW_REQUIRE(n_windows >= 0 && n_windows <= 65535, "tw_logmel_long: %d windows out of range", n_windows);
+    TW_REQUIRE(hop_samples > 0 && hop_samples % HOP == 0, "tw_logmel_long: hop_samples must be a positive multiple of %d", HOP);
+    TW_REQUIRE(((uintptr_t)out_bf16_t & 15) == 0 && total_frames >= 0, "tw_logmel_long: the output must be 16-byte aligned");
+    if (n_windows == 0 || total_frames == 0) return 0;
+    static std::atomic<unsigned long long> attr_done{0};
+    if (device_needs_setup(attr_done)) {
+        TW_CUDA_CHECK(cudaFuncSetAttribute(logmel_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+        mark_device_done(attr_done);
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    TW_CUDA_CHECK(cudaMemsetAsync(max_scratch, 0, sizeof(uint32_t), st));     // below every real value in the ordered map
+    logmel_long_kernel<<<dim3(N_TILES, n_windows), NT, sizeof(Smem), st>>>(
+        pcm_long, (long long)hop_samples, (const Tables*)tables_dev, frame_lo, frame_hi, out_row0, max_scratch,
+        (__nv_bfloat16*)out_bf16_t, out_t_row_off);
+    TW_CUDA_CHECK(cudaGetLastError());
+    const long long n_vec = (long long)total_frames * N_MEL / 8;
+    uint4* first = reinterpret_cast<uint4*>((__nv_bfloat16*)out_bf16_t + (size_t)out_t_row_off * N_MEL);
+    const int blocks = (int)std::min<long long>((n_vec + 255) / 256, 148 * 8);
+    logmel_floor_kernel<<<blocks, 256, 0, st>>>(first, n_vec, max_scratch);
     TW_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

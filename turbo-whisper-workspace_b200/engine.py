@@ -874,6 +874,24 @@ class WhisperEngine:
                 return run()
         return run()
 
+    def generate_long_from_pcm(self, audio: np.ndarray, task: str = "transcribe", language: Optional[str] = None,
+                               num_beams: int = 1, trace: Optional[dict] = None) -> List[int]:
+        """ONE clip longer than 30 s, un-chunked (the ASR pipeline without chunk_length_s,
+        $TF/pipelines/automatic_speech_recognition.py:446-454): features of the whole clip (tw_logmel_long) and HF's
+        long-form generate — the same seek loop as :meth:`generate`, over all n // 160 frames
+        ($TF/models/whisper/generation_whisper.py:654-658, :785-870); timestamps are mandatory (:1388-1394).  Sequential
+        by construction: one window is encoded and decoded per iteration.  Returns the generated ids (segments
+        concatenated; timestamp tokens restart in every 30 s segment, which `_decode_asr` undoes)."""
+        def run():
+            mel = self.logmel.long(audio)
+            self.stats["launches"] += 2
+            self.stats["h2d_bytes"] += int(np.asarray(audio).size) * 4
+            return self.generate(1, task=task, language=language, num_beams=num_beams, long_mel=mel, trace=trace)[0]
+        if self.stream is not None:
+            with torch.cuda.stream(self.stream):
+                return run()
+        return run()
+
     def _strip(self, row: List[int]) -> List[int]:
         """generate_with_fallback's pad / eos stripping ($TF/...generation_whisper.py:1063-1086)."""
         pad, eos = self.gen.pad_token_id, self.gen.eos_token_id
@@ -890,15 +908,22 @@ class WhisperEngine:
 
     def generate(self, B: int, task: str = "transcribe", language: Optional[str] = None,
                  trace: Optional[dict] = None, return_timestamps: bool = True, num_beams: int = 1,
-                 token_timestamps: bool = False, num_frames: Optional[Sequence[int]] = None) -> List[List[int]]:
+                 token_timestamps: bool = False, num_frames: Optional[Sequence[int]] = None,
+                 long_mel: Optional[torch.Tensor] = None) -> List[List[int]]:
         """Short-form seek loop over the features in self.mel_t[:B] (greedy; timestamp grammar on unless
         ``return_timestamps`` is False, in which case <|notimestamps|> joins the prompt).
 
         ``token_timestamps`` (greedy only; ``num_frames[b]`` = valid mel frames of row b, the attention-mask sum):
         the decode steps also tap the alignment heads' cross-attention, and ``self.last_token_ts[b]`` receives one
         fp32 time per returned id (seek offset added, as `segments[...]["token_timestamps"]` of HF's generate;
-        ``self.last_token_ts_raw[b]`` = the padded `token_timestamps` output, no offset)."""
+        ``self.last_token_ts_raw[b]`` = the padded `token_timestamps` output, no offset).
+
+        ``long_mel`` (bf16 [T, 128], T > 3000, B == 1): HF's long-form mode — the loop runs over T frames and every
+        iteration's window is gathered from ``long_mel`` (zero-padded to 3000 frames, _get_input_segment :1831-1850)."""
         gen = self.gen
+        if long_mel is not None:
+            if B != 1 or token_timestamps or not return_timestamps:
+                raise ValueError("long-form generate takes one clip, needs timestamps and has no token timestamps")
         if token_timestamps:
             if num_frames is None or len(num_frames) != B:
                 raise ValueError("token_timestamps needs num_frames for every row")
@@ -916,19 +941,27 @@ class WhisperEngine:
         ts_begin = gen.timestamp_begin
         P = 3 if return_timestamps else 4
         seek = [0] * B
-        max_frames = [N_FRAMES] * B
+        max_frames = [N_FRAMES] * B if long_mel is None else [int(long_mel.shape[0])]
         langs = [lang_id] * B
         out: List[List[int]] = [[] for _ in range(B)]
         it = 0
         with torch.cuda.device(self.device):
             while any(s < m for s, m in zip(seek, max_frames)):
                 it += 1
-                if it > 64:
+                if it > 64 + 4 * (max(max_frames) // N_FRAMES):
                     raise RuntimeError("whisper seek loop does not advance (degenerate timestamp output)")
                 rows = [b for b in range(B) if seek[b] < max_frames[b]]
                 nfr = {b: min(max_frames[b] - seek[b], N_FRAMES) for b in rows}
                 n = len(rows)
-                if it == 1:
+                if long_mel is not None:
+                    # the window [seek, seek + 3000) of the whole-clip features, zeros past the clip's last frame
+                    # (device-to-device copies: data movement, no arithmetic)
+                    k = nfr[0]
+                    self.mel_s[0, 1:1 + k].copy_(long_mel[seek[0]:seek[0] + k])
+                    if k < N_FRAMES:
+                        self.mel_s[0, 1 + k:1 + N_FRAMES].zero_()
+                    mel = self.mel_s
+                elif it == 1:
                     mel = self.mel_t       # seek = 0 for every row: the window is the clip itself
                 else:
                     ops.shift_frames(self.mel_t, self.mel_s,

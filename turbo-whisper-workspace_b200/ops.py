@@ -86,6 +86,62 @@ class LogMel:
                                 _ptr(out_f32), _ptr(out_t), tb, out_t_row_off, _stream()), "tw_logmel")
 
 
+    def long(self, audio: np.ndarray) -> torch.Tensor:
+        """Whole-clip features of one clip longer than 30 s (un-chunked long-form input): host fp32 PCM -> cuda bf16
+        [n // 160, 128], time-major (tw_logmel_long; window plan: :func:`longform_plan`)."""
+        lib = _lib.load()
+        audio = np.asarray(audio, dtype=np.float32).reshape(-1)
+        plan = longform_plan(audio.shape[0])
+        host = torch.from_numpy(longform_buffer(audio, plan))
+        with torch.cuda.device(self.device):
+            pcm = host.to(self.device, non_blocking=False)
+            ints = torch.tensor([plan["lo"], plan["hi"], plan["row0"]], dtype=torch.int32).to(self.device)
+            mx = torch.zeros(1, dtype=torch.int32, device=self.device)
+            out = torch.empty(plan["frames"], N_MELS, dtype=torch.bfloat16, device=self.device)
+            check(lib.tw_logmel_long(_ptr(self.tables), _ptr(pcm), plan["hop_samples"], len(plan["lo"]), _ptr(ints[0]),
+                                     _ptr(ints[1]), _ptr(ints[2]), _ptr(mx), _ptr(out), plan["frames"], 0, _stream()),
+                  "tw_logmel_long")
+            torch.cuda.current_stream(self.device).synchronize()      # `pcm` / `ints` are freed when this returns
+        return out
+
+
+LONG_HOP_FRAMES = 2997      # frames 2 .. 2998 of a 30 s window do not touch its reflect padding
+
+
+def longform_plan(n_samples: int) -> dict:
+    """Cover a clip of n_samples (> 30 s) by overlapping 30 s windows for tw_logmel_long.  The clip has n // 160 frames
+    (WhisperFeatureExtractor: 1 + n // 160 STFT frames, the last one dropped); frame t depends on samples
+    [160 t - 200, 160 t + 200).  Window b starts at sample 2997 * 160 * b, so its frame j is clip frame 2997 b + j, and it
+    is exact for j in [2, 2998] (no reflect padding of the WINDOW involved); window 0 also owns frames 0 and 1, whose
+    reflect padding is the clip's own.  -> frames, hop_samples, per window lo / hi (frame range it writes) and row0
+    (clip frame of frame lo), buffer_samples (what the kernel may read)."""
+    frames = n_samples // 160
+    lo, hi, row0 = [], [], []
+    b = 0
+    while True:
+        first = 0 if b == 0 else 2
+        last = min(N_FRAMES - 1, frames - LONG_HOP_FRAMES * b)      # exclusive
+        if last <= first:
+            break
+        lo.append(first)
+        hi.append(last)
+        row0.append(LONG_HOP_FRAMES * b + first)
+        b += 1
+    hop = LONG_HOP_FRAMES * 160
+    return {"frames": frames, "hop_samples": hop, "lo": lo, "hi": hi, "row0": row0,
+            "buffer_samples": (len(lo) - 1) * hop + 480000 if lo else 0}
+
+
+def longform_buffer(audio: np.ndarray, plan: dict) -> np.ndarray:
+    """The fp32 buffer the windows read: the clip, the 200 samples of numpy 'reflect' padding of its END
+    (x[n + k] = x[n - 2 - k]; torch.stft(center=True, pad_mode="reflect") of the whole waveform), zeros after."""
+    n = audio.shape[0]
+    buf = np.zeros(max(plan["buffer_samples"], n + 200), dtype=np.float32)
+    buf[:n] = audio
+    buf[n:n + 200] = audio[n - 2:n - 202:-1]
+    return buf
+
+
 def layernorm(x, gamma, beta, out=None, eps: float = 1e-5):
     """fp32 [rows, cols] -> bf16 [rows, cols]."""
     lib = _lib.load()
